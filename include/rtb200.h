@@ -1,0 +1,291 @@
+/*
+ * rtb200.h — C ABI of the B200-native path-tracing hot path for the
+ * RayTracingInRust engine.
+ *
+ * This header is the drop-in boundary.  The reference has no FFI today: the
+ * code this library replaces is the nested pixel/sample loop that is inlined in
+ * main() (reference src/main.rs:767-834) together with ray_color
+ * (src/main.rs:41-120) and everything ray_color calls.  A Rust host keeps scene
+ * construction, the camera parameters and the PPM writer, serialises its
+ * `Box<dyn Hittable>` graph into the plain-old-data RtSceneDesc below with a
+ * `flatten()` visitor, and calls rt_render().  INTEGRATION.md shows the
+ * `extern "C"` block and build.rs a maintainer would add.
+ *
+ * Every structure here is plain C: fixed-width integers, doubles, pointers and
+ * counts.  No C++ types, no torch types, no CUDA types cross this boundary.
+ * All arithmetic the reference performs is f64, so every real number in this
+ * interface is a double; the only fp32 quantity is the accumulated image
+ * (W*H*3 sums), which is what ncclReduce combines across GPUs.
+ *
+ * Error model (reference: panics, src/bvh.rs:28,55,61, src/hit.rs:95): every
+ * entry point returns an RtStatus; nothing unwinds across the boundary;
+ * rt_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef RTB200_H
+#define RTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTB200_ABI_VERSION 1u
+#define RT_NONE 0xFFFFFFFFu
+
+/* ------------------------------------------------------------------------ */
+/* Status codes                                                              */
+/* ------------------------------------------------------------------------ */
+typedef enum RtStatus {
+    RT_OK = 0,
+    RT_ERR_BAD_ARGUMENT = 1,  /* null pointer, zero size, index out of range   */
+    RT_ERR_EMPTY_SCENE = 2,   /* reference: panic "no object in the scene"     */
+    RT_ERR_UNSUPPORTED = 3,   /* scene-graph shape the device compiler rejects */
+    RT_ERR_CUDA = 4,          /* a CUDA runtime call failed / no usable device */
+    RT_ERR_NO_LIGHTS = 5,     /* HEAD integrator with an empty light list
+                                 (reference: unwrap() panic, src/hit.rs:94-96) */
+    RT_ERR_INTERNAL = 6
+} RtStatus;
+
+/* ------------------------------------------------------------------------ */
+/* Scene description: a serialised scene graph                               */
+/* ------------------------------------------------------------------------ */
+
+/* Node kinds mirror the reference's Hittable implementors one to one. */
+typedef enum RtNodeKind {
+    RT_NODE_SPHERE = 0,        /* src/sphere.rs:38-120   v = cx cy cz r                       */
+    RT_NODE_MOVING_SPHERE = 1, /* src/sphere.rs:122-201  v = c0x c0y c0z c1x c1y c1z t0 t1 r  */
+    RT_NODE_RECT = 2,          /* src/rect.rs:15-111     v = a0 a1 b0 b1 k ; axis = RtPlane   */
+    RT_NODE_TRIANGLE = 3,      /* src/tri.rs:9-71        v = v0xyz v1xyz v2xyz                */
+    RT_NODE_CUBE = 4,          /* src/cube.rs:7-46       v = minxyz maxxyz (six AARects)      */
+    RT_NODE_LIST = 5,          /* src/hit.rs:47-97       child = first slot in child_index[]  */
+    RT_NODE_BVH = 6,           /* src/bvh.rs:12-96       same as LIST; v = time0 time1        */
+    RT_NODE_TRANSLATE = 7,     /* src/translate.rs:6-40  child ; v = offset xyz               */
+    RT_NODE_ROTATE = 8,        /* src/rotate.rs:23-110   child ; axis = RtAxis ; v = degrees  */
+    RT_NODE_FLIP = 9,          /* src/hit.rs:99-133      child (FlipNormal)                   */
+    RT_NODE_MEDIUM = 10        /* src/medium.rs:10-65    child = boundary ; v = density ;
+                                  material = the Isotropic phase function                    */
+} RtNodeKind;
+
+/* src/rect.rs:8-13,26-32: which axis is constant, and the (a,b) axes. */
+typedef enum RtPlane { RT_PLANE_YZ = 0, RT_PLANE_XZ = 1, RT_PLANE_XY = 2 } RtPlane;
+/* src/rotate.rs:8-21 */
+typedef enum RtAxis { RT_AXIS_X = 0, RT_AXIS_Y = 1, RT_AXIS_Z = 2 } RtAxis;
+
+typedef struct RtNode {
+    uint32_t kind;     /* RtNodeKind                                             */
+    uint32_t material; /* material index for primitives / cube / medium, else RT_NONE */
+    uint32_t child;    /* wrapper kinds: child node index.  LIST/BVH: first slot in
+                          RtSceneDesc.child_index                                 */
+    uint32_t count;    /* LIST/BVH: number of children                            */
+    uint32_t axis;     /* RECT: RtPlane.  ROTATE: RtAxis                          */
+    uint32_t reserved;
+    double v[10];      /* parameters, meaning per kind (see RtNodeKind)           */
+} RtNode;
+
+/* src/mat.rs:199-422.  PBR (src/mat.rs:86-197) is not on the accelerated path. */
+typedef enum RtMaterialKind {
+    RT_MAT_LAMBERTIAN = 0,    /* texture = albedo                      */
+    RT_MAT_METAL = 1,         /* albedo[3], fuzz                       */
+    RT_MAT_DIELECTRIC = 2,    /* ir                                    */
+    RT_MAT_DIFFUSE_LIGHT = 3, /* texture = emit                        */
+    RT_MAT_ISOTROPIC = 4      /* texture = albedo (legacy integrator)  */
+} RtMaterialKind;
+
+typedef struct RtMaterial {
+    uint32_t kind;
+    uint32_t texture;
+    double albedo[3];
+    double fuzz;
+    double ir;
+} RtMaterial;
+
+/* src/texture.rs */
+typedef enum RtTextureKind {
+    RT_TEX_CONSTANT = 0, /* color[3]                                        */
+    RT_TEX_CHECKER = 1,  /* a = odd texture, b = even texture               */
+    RT_TEX_NOISE = 2,    /* a = index into perlin[], scale                  */
+    RT_TEX_IMAGE = 3     /* a = index into images[]                         */
+} RtTextureKind;
+
+typedef struct RtTexture {
+    uint32_t kind;
+    uint32_t a;
+    uint32_t b;
+    uint32_t reserved;
+    double color[3];
+    double scale;
+} RtTexture;
+
+/* src/perlin.rs:60-75: 256 in-ball gradient vectors and three permutations. */
+typedef struct RtPerlin {
+    double ranvec[256 * 3];
+    uint32_t perm_x[256];
+    uint32_t perm_y[256];
+    uint32_t perm_z[256];
+} RtPerlin;
+
+/* src/texture.rs:83-121: tightly packed RGB8, row 0 at the top. */
+typedef struct RtImage {
+    uint32_t width;
+    uint32_t height;
+    uint64_t offset; /* byte offset of texel (0,0) in RtSceneDesc.texels */
+} RtImage;
+
+typedef struct RtSceneDesc {
+    uint32_t abi_version; /* RTB200_ABI_VERSION */
+    uint32_t world;       /* root node of the world (src/main.rs:41 `world`)  */
+    uint32_t lights;      /* root node of the light list (`lights`), a LIST; may be empty */
+    uint32_t reserved;
+    double background[3]; /* src/main.rs:118 */
+
+    const RtNode *nodes;
+    uint64_t n_nodes;
+    const uint32_t *child_index; /* node indices, referenced by LIST/BVH nodes */
+    uint64_t n_child_index;
+    const RtMaterial *materials;
+    uint64_t n_materials;
+    const RtTexture *textures;
+    uint64_t n_textures;
+    const RtPerlin *perlin;
+    uint64_t n_perlin;
+    const RtImage *images;
+    uint64_t n_images;
+    const uint8_t *texels;
+    uint64_t n_texel_bytes;
+} RtSceneDesc;
+
+/* The fields of the reference's Camera after Camera::new (src/camera.rs:5-49). */
+typedef struct RtCamera {
+    double origin[3];
+    double lower_left_corner[3];
+    double horizontal[3];
+    double vertical[3];
+    double cu[3];
+    double cv[3];
+    double lens_radius;
+    double time0;
+    double time1;
+} RtCamera;
+
+/* Which ray_color the sample loop runs. */
+typedef enum RtIntegrator {
+    RT_INTEGRATOR_HEAD = 0,  /* src/main.rs:86-110: scatter_mc_method + light/BSDF mixture */
+    RT_INTEGRATOR_LEGACY = 1 /* src/main.rs:84-85 (commented): Material::scatter           */
+} RtIntegrator;
+
+typedef struct RtRenderOpts {
+    uint32_t seed;         /* Philox stream seed; key = (pixel, sample), see DESIGN.md */
+    uint32_t integrator;   /* RtIntegrator */
+    uint32_t sample_begin; /* this call renders samples [sample_begin, sample_begin+sample_count) */
+    uint32_t sample_count; /* 0 = all of spp.  Multi-GPU: disjoint ranges per GPU        */
+    uint32_t flags;        /* RT_FLAG_* */
+    uint32_t reserved;
+} RtRenderOpts;
+
+#define RT_FLAG_NONE 0u
+/* Keep tracing a path whose throughput is exactly zero, as the reference does
+ * (src/main.rs:97 evaluates the recursive call even when scattering_pdf == 0).
+ * Off by default: the contribution is zero either way. */
+#define RT_FLAG_TRACE_ZERO_THROUGHPUT 1u
+
+typedef struct RtStats {
+    uint64_t paths;             /* (pixel, sample) paths started                        */
+    uint64_t rays;              /* path segments: world.hit calls from the integrator   */
+    uint64_t nonfinite_samples; /* samples whose radiance had a NaN/Inf component       */
+    double render_ms;           /* device time of the render kernels (CUDA events)      */
+    double total_ms;            /* host wall time of the call                           */
+    uint64_t kernel_launches;   /* kernels launched by this call                        */
+    uint64_t h2d_bytes;         /* bytes copied host->device by this call               */
+    uint64_t d2h_bytes;         /* bytes copied device->host by this call               */
+} RtStats;
+
+/* A ray (src/ray.rs:3-7).  Direction is never normalised. */
+typedef struct RtRay {
+    double origin[3];
+    double direction[3];
+    double time;
+} RtRay;
+
+/* What HitRecord (src/hit.rs:9-24) carries, plus the ids the reference lacks. */
+typedef struct RtHit {
+    int32_t node;        /* RtSceneDesc node index of the primitive / medium hit, -1 = miss */
+    int32_t face;        /* CUBE: which of the six rects (src/cube.rs:17-25 order), else 0   */
+    int32_t material;    /* material index                                                   */
+    int32_t front_face;  /* 0/1                                                              */
+    double t;
+    double position[3];
+    double normal[3];
+    double u, v;
+} RtHit;
+
+/* ------------------------------------------------------------------------ */
+/* Entry points                                                              */
+/* ------------------------------------------------------------------------ */
+
+typedef struct RtScene RtScene; /* opaque: device-resident compiled scene */
+
+/* Number of usable CUDA devices (0 when there is none).  Never fails. */
+int rt_device_count(void);
+
+/* Compile `desc` (copied; the caller keeps ownership of its buffers) into the
+ * device representation on CUDA device `device` and upload it once.
+ * Replaces: the scene borrow held by the loop at src/main.rs:624,827. */
+RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene);
+void rt_scene_destroy(RtScene *scene);
+
+/* Bytes of device memory the compiled scene occupies (h2d traffic of create). */
+uint64_t rt_scene_device_bytes(const RtScene *scene);
+
+/* render(world, camera, width, height, spp, max_depth) -> pixels.
+ * Replaces src/main.rs:772-834.  Writes W*H*3 fp32 radiance SUMS (not means)
+ * over the rendered sample range into caller-owned host memory, rows top-down
+ * (first row is j = H-1, src/main.rs:772), columns left to right, RGB
+ * interleaved.  The host divides by spp, applies format_color
+ * (src/vec.rs:125-131) and writes the PPM. */
+RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height,
+                   uint32_t spp, uint32_t max_depth, const RtRenderOpts *opts,
+                   float *out_rgb_sum, RtStats *stats);
+
+/* Same, but `out_rgb_sum_device` is device memory on the scene's device and the
+ * work is enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the
+ * default stream).  Returns after enqueueing; stats (if non-NULL) are complete
+ * after rt_render_wait().  This is the entry the multi-GPU host uses so that
+ * the fp32 sums can go straight into ncclReduce. */
+RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t width,
+                          uint32_t height, uint32_t spp, uint32_t max_depth,
+                          const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream);
+/* Block until the last rt_render_device on this scene finished; fill stats. */
+RtStatus rt_render_wait(const RtScene *scene, RtStats *stats);
+
+/* Parity hook 1: closest hit of world.hit(ray, 1e-5, +inf) (src/main.rs:48) for
+ * n caller-supplied rays.  Media are skipped (their hit draws a random number,
+ * src/medium.rs:42); they are covered by rt_path_radiance. */
+RtStatus rt_trace_first_hit(const RtScene *scene, const RtRay *rays, uint64_t n, RtHit *hits);
+
+/* Parity hook 2: radiance of individual paths.  For i in [0,n): the path of
+ * pixel (px[i], py[i]) — py counted bottom-up like j in src/main.rs:772 — and
+ * sample index sample[i].  rgb receives 3 doubles per path, segments (optional)
+ * the number of world.hit calls the path made. */
+RtStatus rt_path_radiance(const RtScene *scene, const RtCamera *camera, uint32_t width,
+                          uint32_t height, uint32_t max_depth, const RtRenderOpts *opts,
+                          const uint32_t *px, const uint32_t *py, const uint32_t *sample,
+                          uint64_t n, double *rgb, uint32_t *segments);
+
+/* Parity hook 3: the primary rays the render kernel generates (src/main.rs:813-820
+ * + src/camera.rs:51-59) for the same (pixel, sample) addressing. */
+RtStatus rt_camera_rays(const RtScene *scene, const RtCamera *camera, uint32_t width,
+                        uint32_t height, const RtRenderOpts *opts, const uint32_t *px,
+                        const uint32_t *py, const uint32_t *sample, uint64_t n, RtRay *rays);
+
+/* Thread-local description of the last error returned on this thread. */
+const char *rt_last_error(void);
+
+/* Library build info, e.g. "rtb200 abi 1 sm_100a f64". */
+const char *rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTB200_H */

@@ -1,0 +1,400 @@
+"""raytracinginrust_b200 — B200-native path-tracing hot path for the RayTracingInRust engine.
+
+This package is the Python harness over two native libraries built by
+`__graft_entry__.build()` (or `make -C raytracinginrust_b200/csrc`):
+
+  lib/librtb200.so       the product: CUDA kernels for sm_100a behind the C ABI of
+                         include/rtb200.h (what a Rust host links against)
+  lib/librtb200_host.so  the C++ host layer standing in for the Rust host: the
+                         reference's scene constructors, Camera::new, render(),
+                         format_color and the PPM writer
+
+There is no CPU fallback anywhere in this package: if the native libraries are not
+built, importing fails; if there is no CUDA device, every compute call raises RtError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+from ._abi import (RtCamera, RtHit, RtImage, RtMaterial, RtNode, RtPerlin, RtRay, RtRenderOpts, RtSceneDesc, RtStats,
+                   RtTexture, HIT_DTYPE, RAY_DTYPE, INTEGRATOR_HEAD, INTEGRATOR_LEGACY)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+REPO_ROOT = os.path.dirname(_HERE)
+ASSETS_DIR = os.path.join(REPO_ROOT, "assets")
+
+
+class RtError(RuntimeError):
+    def __init__(self, status, message):
+        name = _abi.STATUS_NAMES[status] if 0 <= status < len(_abi.STATUS_NAMES) else str(status)
+        super().__init__("%s: %s" % (name, message))
+        self.status = status
+
+
+def _load(name):
+    path = os.path.join(LIB_DIR, name)
+    if not os.path.exists(path):
+        raise ImportError(
+            "%s is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C raytracinginrust_b200/csrc`. There is no fallback path." % path)
+    return C.CDLL(path, mode=C.RTLD_GLOBAL)
+
+
+_dev = _load("librtb200.so")
+_host = _load("librtb200_host.so")
+
+_u32p = C.POINTER(C.c_uint32)
+_dev.rt_device_count.restype = C.c_int
+_dev.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.POINTER(C.c_void_p)]
+_dev.rt_scene_destroy.argtypes = [C.c_void_p]
+_dev.rt_scene_destroy.restype = None
+_dev.rt_scene_device_bytes.argtypes = [C.c_void_p]
+_dev.rt_scene_device_bytes.restype = C.c_uint64
+_dev.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                           C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(RtStats)]
+_dev.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.POINTER(RtRenderOpts), C.c_void_p, C.c_void_p]
+_dev.rt_render_wait.argtypes = [C.c_void_p, C.POINTER(RtStats)]
+_dev.rt_trace_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+_dev.rt_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32,
+                                  C.POINTER(RtRenderOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
+                                  C.c_void_p]
+_dev.rt_camera_rays.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+_dev.rt_last_error.restype = C.c_char_p
+_dev.rt_version.restype = C.c_char_p
+
+_host.rth_last_error.restype = C.c_char_p
+_host.rth_scene_build.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
+_host.rth_scene_free.argtypes = [C.c_void_p]
+_host.rth_scene_free.restype = None
+_host.rth_scene_desc.argtypes = [C.c_void_p]
+_host.rth_scene_desc.restype = C.POINTER(RtSceneDesc)
+_host.rth_scene_camera.argtypes = [C.c_void_p]
+_host.rth_scene_camera.restype = C.POINTER(RtCamera)
+_host.rth_scene_config.argtypes = [C.c_void_p, _u32p]
+_host.rth_scene_config.restype = None
+_host.rth_camera_new.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                 C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(RtCamera)]
+_host.rth_camera_new.restype = None
+_host.rth_format_image.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+_host.rth_format_image.restype = None
+_host.rth_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]
+_host.rth_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
+                             C.c_int, C.c_void_p, C.POINTER(RtStats)]
+_host.rth_obj_triangle_count.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+
+
+def _check(status):
+    if status != _abi.RT_OK:
+        raise RtError(status, _dev.rt_last_error().decode())
+
+
+def _check_host(status):
+    if status != _abi.RT_OK:
+        raise RtError(status, _host.rth_last_error().decode())
+
+
+def device_count():
+    return int(_dev.rt_device_count())
+
+
+def version():
+    return _dev.rt_version().decode()
+
+
+def render_opts(seed=1, integrator=INTEGRATOR_HEAD, sample_begin=0, sample_count=0, flags=0):
+    o = RtRenderOpts()
+    o.seed, o.integrator, o.sample_begin, o.sample_count, o.flags = seed, integrator, sample_begin, sample_count, flags
+    return o
+
+
+def _vec3(v):
+    return (C.c_double * 3)(float(v[0]), float(v[1]), float(v[2]))
+
+
+def camera_new(lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dist, time0=0.0, time1=1.0):
+    """Camera::new (src/camera.rs:19-49)."""
+    cam = RtCamera()
+    _host.rth_camera_new(_vec3(lookfrom), _vec3(lookat), _vec3(vup), vfov, aspect_ratio, aperture, focus_dist, time0,
+                         time1, C.byref(cam))
+    return cam
+
+
+# ---------------------------------------------------------------------------------------
+# Scene descriptions
+# ---------------------------------------------------------------------------------------
+class SceneDesc:
+    """An RtSceneDesc plus the buffers it points into."""
+
+    def __init__(self, desc, keepalive=()):
+        self.desc = desc
+        self._keep = keepalive
+
+    @property
+    def ptr(self):
+        return C.pointer(self.desc) if not isinstance(self.desc, C.POINTER(RtSceneDesc)) else self.desc
+
+    @property
+    def struct(self):
+        return self.desc.contents if isinstance(self.desc, C.POINTER(RtSceneDesc)) else self.desc
+
+
+class SceneBuilder:
+    """Python-side flatten target: builds an RtSceneDesc node by node.  Method names and
+    argument order follow the reference's constructors (Sphere::new, AARect::new, ...)."""
+
+    def __init__(self):
+        self.nodes, self.child_index, self.materials, self.textures = [], [], [], []
+        self.perlin, self.images, self.texels = [], [], bytearray()
+
+    # textures (src/texture.rs)
+    def _tex(self, kind, a=_abi.RT_NONE, b=_abi.RT_NONE, color=(0, 0, 0), scale=0.0):
+        t = RtTexture()
+        t.kind, t.a, t.b, t.scale = kind, a, b, scale
+        t.color[:] = [float(c) for c in color]
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def constant_texture(self, color):
+        return self._tex(_abi.TEX_CONSTANT, color=color)
+
+    def check_texture(self, odd, even):
+        return self._tex(_abi.TEX_CHECKER, a=odd, b=even)
+
+    def noise_texture(self, scale, ranvec, perm_x, perm_y, perm_z):
+        p = RtPerlin()
+        p.ranvec[:] = [float(x) for x in np.asarray(ranvec, dtype=np.float64).reshape(-1)]
+        p.perm_x[:] = [int(x) for x in perm_x]
+        p.perm_y[:] = [int(x) for x in perm_y]
+        p.perm_z[:] = [int(x) for x in perm_z]
+        self.perlin.append(p)
+        return self._tex(_abi.TEX_NOISE, a=len(self.perlin) - 1, scale=scale)
+
+    def image_texture(self, data, width, height):
+        im = RtImage()
+        im.width, im.height, im.offset = width, height, len(self.texels)
+        raw = bytes(data)
+        assert len(raw) == width * height * 3
+        self.texels += raw
+        self.images.append(im)
+        return self._tex(_abi.TEX_IMAGE, a=len(self.images) - 1)
+
+    # materials (src/mat.rs)
+    def _mat(self, kind, texture=_abi.RT_NONE, albedo=(0, 0, 0), fuzz=0.0, ir=0.0):
+        m = RtMaterial()
+        m.kind, m.texture, m.fuzz, m.ir = kind, texture, fuzz, ir
+        m.albedo[:] = [float(c) for c in albedo]
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def lambertian(self, texture):
+        return self._mat(_abi.MAT_LAMBERTIAN, texture=texture)
+
+    def metal(self, albedo, fuzz):
+        return self._mat(_abi.MAT_METAL, albedo=albedo, fuzz=fuzz)
+
+    def dielectric(self, ir):
+        return self._mat(_abi.MAT_DIELECTRIC, ir=ir)
+
+    def diffuse_light(self, texture):
+        return self._mat(_abi.MAT_DIFFUSE_LIGHT, texture=texture)
+
+    def isotropic(self, texture):
+        return self._mat(_abi.MAT_ISOTROPIC, texture=texture)
+
+    # hittables
+    def _node(self, kind, material=_abi.RT_NONE, child=_abi.RT_NONE, count=0, axis=0, v=()):
+        n = RtNode()
+        n.kind, n.material, n.child, n.count, n.axis = kind, material, child, count, axis
+        for i, x in enumerate(v):
+            n.v[i] = float(x)
+        self.nodes.append(n)
+        return len(self.nodes) - 1
+
+    def sphere(self, center, radius, material):
+        return self._node(_abi.NODE_SPHERE, material, v=list(center) + [radius])
+
+    def moving_sphere(self, center0, center1, time0, time1, radius, material):
+        return self._node(_abi.NODE_MOVING_SPHERE, material, v=list(center0) + list(center1) + [time0, time1, radius])
+
+    def rect(self, plane, a0, a1, b0, b1, k, material):
+        return self._node(_abi.NODE_RECT, material, axis=plane, v=[a0, a1, b0, b1, k])
+
+    def triangle(self, v0, v1, v2, material):
+        return self._node(_abi.NODE_TRIANGLE, material, v=list(v0) + list(v1) + list(v2))
+
+    def cube(self, pmin, pmax, material):
+        return self._node(_abi.NODE_CUBE, material, v=list(pmin) + list(pmax))
+
+    def _children(self, kind, kids, v=()):
+        first = len(self.child_index)
+        self.child_index += [int(k) for k in kids]
+        return self._node(kind, child=first, count=len(kids), v=v)
+
+    def list(self, kids):
+        return self._children(_abi.NODE_LIST, kids)
+
+    def bvh(self, kids, time0=0.0, time1=1.0):
+        return self._children(_abi.NODE_BVH, kids, v=[time0, time1])
+
+    def translate(self, child, offset):
+        return self._node(_abi.NODE_TRANSLATE, child=child, v=list(offset))
+
+    def rotate(self, axis, child, angle):
+        return self._node(_abi.NODE_ROTATE, child=child, axis=axis, v=[angle])
+
+    def flip(self, child):
+        return self._node(_abi.NODE_FLIP, child=child)
+
+    def medium(self, boundary, density, texture):
+        return self._node(_abi.NODE_MEDIUM, material=self.isotropic(texture), child=boundary, v=[density])
+
+    def finish(self, world, lights, background=(0.0, 0.0, 0.0)):
+        def arr(ctype, items):
+            a = (ctype * max(len(items), 1))(*items)
+            return a
+
+        nodes = arr(RtNode, self.nodes)
+        kids = (C.c_uint32 * max(len(self.child_index), 1))(*self.child_index)
+        mats = arr(RtMaterial, self.materials)
+        texs = arr(RtTexture, self.textures)
+        perl = arr(RtPerlin, self.perlin)
+        imgs = arr(RtImage, self.images)
+        texels = (C.c_uint8 * max(len(self.texels), 1)).from_buffer_copy(bytes(self.texels) or b"\0")
+        d = RtSceneDesc()
+        d.abi_version = _abi.ABI_VERSION
+        d.world, d.lights = world, lights
+        d.background[:] = [float(c) for c in background]
+        d.nodes, d.n_nodes = nodes, len(self.nodes)
+        d.child_index, d.n_child_index = kids, len(self.child_index)
+        d.materials, d.n_materials = mats, len(self.materials)
+        d.textures, d.n_textures = texs, len(self.textures)
+        d.perlin, d.n_perlin = perl, len(self.perlin)
+        d.images, d.n_images = imgs, len(self.images)
+        d.texels, d.n_texel_bytes = texels, len(self.texels)
+        return SceneDesc(d, (nodes, kids, mats, texs, perl, imgs, texels))
+
+
+class HostScene:
+    """One of the reference's scenes (src/main.rs:153-513) built by the C++ host layer."""
+
+    NAMES = ("random", "cornell", "cornell_smoke", "final", "mesh", "light_room", "two_spheres")
+
+    def __init__(self, name, construction_seed=1, assets_dir=ASSETS_DIR, mesh_detail=0):
+        self.name = name
+        self._h = C.c_void_p()
+        _check_host(_host.rth_scene_build(name.encode(), construction_seed, assets_dir.encode(), mesh_detail,
+                                          C.byref(self._h)))
+        cfg = (C.c_uint32 * 5)()
+        _host.rth_scene_config(self._h, cfg)
+        self.integrator, self.width, self.height, self.spp, self.max_depth = [int(x) for x in cfg]
+        self.camera = _host.rth_scene_camera(self._h).contents
+        self.scene_desc = SceneDesc(_host.rth_scene_desc(self._h), (self,))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _host.rth_scene_free(self._h)
+            self._h = None
+
+    def render(self, width, height, spp, max_depth, opts=None, device=0):
+        """render(world, camera, width, height, spp, max_depth) -> pixels, end to end with host
+        buffers: flatten + compile + upload + kernels + read-back (src/main.rs:772-834)."""
+        opts = opts or render_opts(integrator=self.integrator)
+        out = np.empty((height, width, 3), dtype=np.float32)
+        stats = RtStats()
+        _check_host(_host.rth_render(self._h, width, height, spp, max_depth, C.byref(opts), device,
+                                     out.ctypes.data_as(C.c_void_p), C.byref(stats)))
+        return out, stats
+
+
+class DeviceScene:
+    """A scene compiled and resident on one GPU (rt_scene_create)."""
+
+    def __init__(self, scene_desc, device=0):
+        self._h = C.c_void_p()
+        self._desc = scene_desc
+        _check(_dev.rt_scene_create(scene_desc.ptr, device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _dev.rt_scene_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def device_bytes(self):
+        return int(_dev.rt_scene_device_bytes(self._h))
+
+    def render(self, camera, width, height, spp, max_depth, opts=None):
+        opts = opts or render_opts()
+        out = np.empty((height, width, 3), dtype=np.float32)
+        stats = RtStats()
+        _check(_dev.rt_render(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
+                              out.ctypes.data_as(C.c_void_p), C.byref(stats)))
+        return out, stats
+
+    def render_device(self, camera, width, height, spp, max_depth, opts, out_ptr, stream_ptr=0):
+        """Enqueue a render into device memory `out_ptr` (W*H*3 fp32) on CUDA stream `stream_ptr`."""
+        _check(_dev.rt_render_device(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
+                                     C.c_void_p(out_ptr), C.c_void_p(stream_ptr)))
+
+    def render_wait(self):
+        stats = RtStats()
+        _check(_dev.rt_render_wait(self._h, C.byref(stats)))
+        return stats
+
+    def trace_first_hit(self, rays):
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
+        _check(_dev.rt_trace_first_hit(self._h, rays.ctypes.data_as(C.c_void_p), rays.shape[0],
+                                       hits.ctypes.data_as(C.c_void_p)))
+        return hits
+
+    def path_radiance(self, camera, width, height, max_depth, opts, px, py, sample):
+        px, py, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (px, py, sample))
+        n = px.shape[0]
+        rgb = np.zeros((n, 3), dtype=np.float64)
+        seg = np.zeros(n, dtype=np.uint32)
+        _check(_dev.rt_path_radiance(self._h, C.byref(camera), width, height, max_depth, C.byref(opts),
+                                     px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                     sample.ctypes.data_as(C.c_void_p), n, rgb.ctypes.data_as(C.c_void_p),
+                                     seg.ctypes.data_as(C.c_void_p)))
+        return rgb, seg
+
+    def camera_rays(self, camera, width, height, opts, px, py, sample):
+        px, py, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (px, py, sample))
+        n = px.shape[0]
+        rays = np.zeros(n, dtype=RAY_DTYPE)
+        _check(_dev.rt_camera_rays(self._h, C.byref(camera), width, height, C.byref(opts),
+                                   px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                   sample.ctypes.data_as(C.c_void_p), n, rays.ctypes.data_as(C.c_void_p)))
+        return rays
+
+
+# ---------------------------------------------------------------------------------------
+# Output: format_color (src/vec.rs:125-131) and the P3 writer (src/main.rs:767-769,832)
+# ---------------------------------------------------------------------------------------
+def format_image(rgb_sum, samples_per_pixel):
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    out = np.empty(rgb_sum.shape, dtype=np.uint8)
+    _host.rth_format_image(rgb_sum.ctypes.data_as(C.c_void_p), rgb_sum.size // 3, samples_per_pixel,
+                           out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def write_ppm(path, rgb_sum, samples_per_pixel):
+    rgb_sum = np.ascontiguousarray(rgb_sum, dtype=np.float32)
+    h, w = rgb_sum.shape[:2]
+    _check_host(_host.rth_write_ppm(path.encode(), rgb_sum.ctypes.data_as(C.c_void_p), w, h, samples_per_pixel))
+
+
+def obj_triangle_count(path):
+    nv, nt = C.c_uint64(), C.c_uint64()
+    _check_host(_host.rth_obj_triangle_count(path.encode(), C.byref(nv), C.byref(nt)))
+    return int(nv.value), int(nt.value)

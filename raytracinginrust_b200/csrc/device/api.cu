@@ -1,0 +1,397 @@
+// api.cu — the C ABI of include/rtb200.h: scene upload, render, parity hooks.
+// There is no CPU fallback: every entry point that computes needs a CUDA device
+// and fails with RT_ERR_CUDA when there is none.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../../include/rtb200.h"
+#include "compile.h"
+#include "kernels.h"
+
+using namespace rtb200dev;
+
+namespace {
+thread_local std::string g_err;
+
+RtStatus fail(RtStatus s, const std::string &m) {
+    g_err = m;
+    return s;
+}
+RtStatus cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return RT_ERR_CUDA;
+}
+#define CU(call)                                             \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+}  // namespace
+
+struct RtScene {
+    int device = 0;
+    DScene ds{};
+    std::vector<void *> allocations;
+    uint64_t device_bytes = 0;
+    uint32_t n_lights = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int render_blocks = 0;
+    // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
+    double *planes = nullptr;
+    size_t planes_bytes = 0;
+    float *out_dev = nullptr;
+    size_t out_bytes = 0;
+    unsigned long long *counters = nullptr;
+    unsigned long long *counters_host = nullptr;  // pinned
+    // last async render
+    bool pending = false;
+    cudaStream_t pending_stream = nullptr;
+    double t_call0 = 0.0;
+    uint64_t pending_launches = 0;
+
+    ~RtScene() {
+        cudaSetDevice(device);
+        for (void *p : allocations) cudaFree(p);
+        if (planes) cudaFree(planes);
+        if (out_dev) cudaFree(out_dev);
+        if (counters) cudaFree(counters);
+        if (counters_host) cudaFreeHost(counters_host);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+template <class T>
+RtStatus upload(RtScene &s, const std::vector<T> &v, const T *&dev) {
+    size_t bytes = v.size() * sizeof(T);
+    void *p = nullptr;
+    CU(cudaMalloc(&p, bytes ? bytes : 16));
+    s.allocations.push_back(p);
+    if (bytes) CU(cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice));
+    s.device_bytes += bytes;
+    dev = (const T *)p;
+    return RT_OK;
+}
+
+RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                     const RtRenderOpts *opts, RenderParams &P) {
+    if (width < 2 || height < 2) return fail(RT_ERR_BAD_ARGUMENT, "width and height must be at least 2 (main.rs:817-818 divides by W-1, H-1)");
+    if ((uint64_t)width * height > (1ull << 31)) return fail(RT_ERR_BAD_ARGUMENT, "image too large");
+    RtRenderOpts o{};
+    if (opts) o = *opts;
+    if (o.integrator > RT_INTEGRATOR_LEGACY) return fail(RT_ERR_BAD_ARGUMENT, "unknown integrator");
+    if (o.integrator == RT_INTEGRATOR_HEAD && s.n_lights == 0)
+        return fail(RT_ERR_NO_LIGHTS, "HEAD integrator needs a non-empty light list (reference: unwrap() panic at hit.rs:94-96)");
+    uint32_t begin = o.sample_begin;
+    uint32_t count = o.sample_count ? o.sample_count : (spp > begin ? spp - begin : 0);
+    if (count == 0) return fail(RT_ERR_BAD_ARGUMENT, "empty sample range");
+    if ((uint64_t)begin + count > 0xFFFFFFFFull) return fail(RT_ERR_BAD_ARGUMENT, "sample range overflows");
+    std::memset(&P, 0, sizeof(P));
+    P.width = width;
+    P.height = height;
+    P.max_depth = max_depth;
+    P.seed = o.seed;
+    P.integrator = o.integrator;
+    P.flags = o.flags;
+    P.sample_begin = begin;
+    P.sample_end = begin + count;
+    P.tiles_x = (width + 7) / 8;
+    P.tiles_y = (height + 3) / 4;
+    P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
+    // enough items that the tail of the persistent grid is a small fraction of the run
+    uint64_t resident = (uint64_t)(s.render_blocks > 0 ? s.render_blocks : 148) * kRenderBlock;
+    uint64_t target_items = resident * 64ull;
+    uint64_t chunks = (target_items + P.items_per_chunk - 1) / P.items_per_chunk;
+    if (chunks < 1) chunks = 1;
+    if (chunks > count) chunks = count;
+    if (chunks > 256) chunks = 256;
+    P.chunk_size = (uint32_t)((count + chunks - 1) / chunks);
+    P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
+    P.n_items = P.items_per_chunk * P.n_chunks;
+    return RT_OK;
+}
+
+RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
+    size_t plane_bytes = (size_t)P.n_chunks * P.width * P.height * 3 * sizeof(double);
+    if (plane_bytes > s.planes_bytes) {
+        if (s.planes) cudaFree(s.planes);
+        s.planes = nullptr;
+        s.planes_bytes = 0;
+        CU(cudaMalloc((void **)&s.planes, plane_bytes));
+        s.planes_bytes = plane_bytes;
+    }
+    size_t out_bytes = (size_t)P.width * P.height * 3 * sizeof(float);
+    if (need_out && out_bytes > s.out_bytes) {
+        if (s.out_dev) cudaFree(s.out_dev);
+        s.out_dev = nullptr;
+        s.out_bytes = 0;
+        CU(cudaMalloc((void **)&s.out_dev, out_bytes));
+        s.out_bytes = out_bytes;
+    }
+    return RT_OK;
+}
+
+RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, float *out_dev, cudaStream_t st) {
+    CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * kNumCounters, st));
+    CU(cudaEventRecord(s.ev0, st));
+    CU(launch_render(s.ds, cam, P, s.render_blocks, s.planes, s.counters, st));
+    CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
+    CU(cudaEventRecord(s.ev1, st));
+    CU(cudaMemcpyAsync(s.counters_host, s.counters, sizeof(unsigned long long) * kNumCounters, cudaMemcpyDeviceToHost, st));
+    s.pending_launches = 2;
+    return RT_OK;
+}
+
+RtStatus finish_render(RtScene &s, cudaStream_t st, RtStats *stats, uint64_t d2h_bytes) {
+    CU(cudaStreamSynchronize(st));
+    if (stats) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->paths = s.counters_host[kCounterPaths];
+        stats->rays = s.counters_host[kCounterRays];
+        stats->nonfinite_samples = s.counters_host[kCounterNonFinite];
+        stats->render_ms = ms;
+        stats->total_ms = now_ms() - s.t_call0;
+        stats->kernel_launches = s.pending_launches;
+        stats->h2d_bytes = sizeof(DScene) + sizeof(RtCamera) + sizeof(RenderParams);  // kernel arguments only
+        stats->d2h_bytes = d2h_bytes + sizeof(unsigned long long) * kNumCounters;
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *rt_last_error(void) { return g_err.c_str(); }
+const char *rt_version(void) { return "rtb200 abi 1 sm_100a f64"; }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
+    if (!desc || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *out_scene = nullptr;
+    CompiledScene cs;
+    std::string err;
+    RtStatus st = compile_scene(*desc, cs, err);
+    if (st != RT_OK) return fail(st, err);
+    int n = rt_device_count();
+    if (n == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    std::unique_ptr<RtScene> s(new RtScene());
+    s->device = device;
+    s->n_lights = (uint32_t)cs.lights.size();
+    DScene &d = s->ds;
+#define UP(field)                                   \
+    do {                                            \
+        RtStatus u__ = upload(*s, cs.field, d.field); \
+        if (u__ != RT_OK) return u__;               \
+    } while (0)
+    UP(prims);
+    UP(ops);
+    UP(chains);
+    UP(groups);
+    UP(nodes);
+    UP(media);
+    UP(lights);
+    UP(materials);
+    UP(textures);
+    UP(images);
+    UP(perlin);
+    UP(texels);
+#undef UP
+    d.n_world_groups = cs.n_world_groups;
+    d.n_media = (uint32_t)cs.media.size();
+    d.n_lights = (uint32_t)cs.lights.size();
+    d.n_prims = (uint32_t)cs.prims.size();
+    for (int a = 0; a < 3; ++a) d.background[a] = cs.background[a];
+    CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s->ev0));
+    CU(cudaEventCreate(&s->ev1));
+    CU(cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * kNumCounters));
+    CU(cudaMallocHost((void **)&s->counters_host, sizeof(unsigned long long) * kNumCounters));
+    CU(render_grid_size(device, &s->render_blocks));
+    *out_scene = s.release();
+    return RT_OK;
+}
+
+void rt_scene_destroy(RtScene *scene) { delete scene; }
+
+uint64_t rt_scene_device_bytes(const RtScene *scene) { return scene ? scene->device_bytes : 0; }
+
+RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                          uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream) {
+    if (!scene || !camera || !out_rgb_sum_device) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    RtScene &s = *const_cast<RtScene *>(scene);
+    s.t_call0 = now_ms();
+    CU(cudaSetDevice(s.device));
+    RenderParams P;
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    if (st != RT_OK) return st;
+    st = ensure_scratch(s, P, false);
+    if (st != RT_OK) return st;
+    st = enqueue_render(s, *camera, P, out_rgb_sum_device, (cudaStream_t)cuda_stream);
+    if (st != RT_OK) return st;
+    s.pending = true;
+    s.pending_stream = (cudaStream_t)cuda_stream;
+    return RT_OK;
+}
+
+RtStatus rt_render_wait(const RtScene *scene, RtStats *stats) {
+    if (!scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    RtScene &s = *const_cast<RtScene *>(scene);
+    if (!s.pending) return fail(RT_ERR_BAD_ARGUMENT, "no render pending");
+    CU(cudaSetDevice(s.device));
+    s.pending = false;
+    return finish_render(s, s.pending_stream, stats, 0);
+}
+
+RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                   uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum, RtStats *stats) {
+    if (!scene || !camera || !out_rgb_sum) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    RtScene &s = *const_cast<RtScene *>(scene);
+    s.t_call0 = now_ms();
+    CU(cudaSetDevice(s.device));
+    RenderParams P;
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    if (st != RT_OK) return st;
+    st = ensure_scratch(s, P, true);
+    if (st != RT_OK) return st;
+    st = enqueue_render(s, *camera, P, s.out_dev, s.stream);
+    if (st != RT_OK) return st;
+    size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
+    CU(cudaMemcpyAsync(out_rgb_sum, s.out_dev, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    return finish_render(s, s.stream, stats, out_bytes);
+}
+
+RtStatus rt_trace_first_hit(const RtScene *scene, const RtRay *rays, uint64_t n, RtHit *hits) {
+    if (!scene || (n && (!rays || !hits))) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    if (n == 0) return RT_OK;
+    RtScene &s = *const_cast<RtScene *>(scene);
+    CU(cudaSetDevice(s.device));
+    RtRay *d_rays = nullptr;
+    RtHit *d_hits = nullptr;
+    CU(cudaMalloc((void **)&d_rays, n * sizeof(RtRay)));
+    cudaError_t e = cudaMalloc((void **)&d_hits, n * sizeof(RtHit));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rays, rays, n * sizeof(RtRay), cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = launch_first_hit(s.ds, d_rays, n, d_hits, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hits, d_hits, n * sizeof(RtHit), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_rays);
+    if (d_hits) cudaFree(d_hits);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_trace_first_hit");
+    return RT_OK;
+}
+
+static RtStatus hook_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t max_depth,
+                            const RtRenderOpts *opts, bool need_lights, RenderParams &P) {
+    if (width < 2 || height < 2) return fail(RT_ERR_BAD_ARGUMENT, "width and height must be at least 2");
+    RtRenderOpts o{};
+    if (opts) o = *opts;
+    if (o.integrator > RT_INTEGRATOR_LEGACY) return fail(RT_ERR_BAD_ARGUMENT, "unknown integrator");
+    if (need_lights && o.integrator == RT_INTEGRATOR_HEAD && s.n_lights == 0)
+        return fail(RT_ERR_NO_LIGHTS, "HEAD integrator needs a non-empty light list (reference: unwrap() panic at hit.rs:94-96)");
+    std::memset(&P, 0, sizeof(P));
+    P.width = width;
+    P.height = height;
+    P.max_depth = max_depth;
+    P.seed = o.seed;
+    P.integrator = o.integrator;
+    P.flags = o.flags;
+    return RT_OK;
+}
+
+static RtStatus upload_u32x3(cudaStream_t st, const uint32_t *px, const uint32_t *py, const uint32_t *sample, uint64_t n,
+                             uint32_t **d_out) {
+    uint32_t *d = nullptr;
+    CU(cudaMalloc((void **)&d, 3 * n * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpyAsync(d, px, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, py, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + 2 * n, sample, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return cuda_fail(e, "upload path ids");
+    }
+    *d_out = d;
+    return RT_OK;
+}
+
+RtStatus rt_path_radiance(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height,
+                          uint32_t max_depth, const RtRenderOpts *opts, const uint32_t *px, const uint32_t *py,
+                          const uint32_t *sample, uint64_t n, double *rgb, uint32_t *segments) {
+    if (!scene || !camera || (n && (!px || !py || !sample || !rgb))) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    if (n == 0) return RT_OK;
+    RtScene &s = *const_cast<RtScene *>(scene);
+    CU(cudaSetDevice(s.device));
+    RenderParams P;
+    RtStatus st = hook_params(s, width, height, max_depth, opts, true, P);
+    if (st != RT_OK) return st;
+    for (uint64_t k = 0; k < n; ++k)
+        if (px[k] >= width || py[k] >= height) return fail(RT_ERR_BAD_ARGUMENT, "pixel out of range");
+    uint32_t *d_ids = nullptr;
+    st = upload_u32x3(s.stream, px, py, sample, n, &d_ids);
+    if (st != RT_OK) return st;
+    double *d_rgb = nullptr;
+    uint32_t *d_seg = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_rgb, 3 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&d_seg, n * sizeof(uint32_t));
+    if (e == cudaSuccess) e = launch_path_radiance(s.ds, *camera, P, d_ids, d_ids + n, d_ids + 2 * n, n, d_rgb, d_seg, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgb, d_rgb, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess && segments) e = cudaMemcpyAsync(segments, d_seg, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_ids);
+    if (d_rgb) cudaFree(d_rgb);
+    if (d_seg) cudaFree(d_seg);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_path_radiance");
+    return RT_OK;
+}
+
+RtStatus rt_camera_rays(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height,
+                        const RtRenderOpts *opts, const uint32_t *px, const uint32_t *py, const uint32_t *sample,
+                        uint64_t n, RtRay *rays) {
+    if (!scene || !camera || (n && (!px || !py || !sample || !rays))) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    if (n == 0) return RT_OK;
+    RtScene &s = *const_cast<RtScene *>(scene);
+    CU(cudaSetDevice(s.device));
+    RenderParams P;
+    RtStatus st = hook_params(s, width, height, 1, opts, false, P);
+    if (st != RT_OK) return st;
+    uint32_t *d_ids = nullptr;
+    st = upload_u32x3(s.stream, px, py, sample, n, &d_ids);
+    if (st != RT_OK) return st;
+    RtRay *d_rays = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d_rays, n * sizeof(RtRay));
+    if (e == cudaSuccess) e = launch_camera_rays(*camera, P, d_ids, d_ids + n, d_ids + 2 * n, n, d_rays, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rays, d_rays, n * sizeof(RtRay), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_ids);
+    if (d_rays) cudaFree(d_rays);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_camera_rays");
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,738 @@
+// compile.cpp — scene-graph compiler and SAH BVH builder (host side of the device
+// library).  Replaces the Box<dyn Hittable> tree (src/hit.rs, src/bvh.rs:18-73) with
+// the flat tables of tables.h.  Only *culling* structures are new here: the
+// primitives, their parameters and the wrapper order are taken over unchanged, so
+// every ray/primitive test sees the same f64 numbers the reference would.
+#include "compile.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <functional>
+#include <queue>
+
+namespace rtb200dev {
+namespace {
+
+const double PI = 3.14159265358979323846264338327950288;
+const uint32_t LINEAR_MAX = 6;  // groups with at most this many primitives are scanned linearly
+const uint32_t LEAF_MAX = 2;    // primitives per BVH leaf
+const int N_BINS = 16;
+const int FORCE_MEDIAN_DEPTH = 32;  // bounds the tree depth (traversal stack is 64 entries)
+
+struct Box {
+    double lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = DBL_MAX;
+            hi[a] = -DBL_MAX;
+        }
+    }
+    void grow(const Box &b) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::fmin(lo[a], b.lo[a]);
+            hi[a] = std::fmax(hi[a], b.hi[a]);
+        }
+    }
+    void grow(const double p[3]) {
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::fmin(lo[a], p[a]);
+            hi[a] = std::fmax(hi[a], p[a]);
+        }
+    }
+    double area() const {
+        double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        return 2.0 * (dx * dy + dy * dz + dz * dx);
+    }
+    bool finite() const {
+        for (int a = 0; a < 3; ++a)
+            if (!std::isfinite(lo[a]) || !std::isfinite(hi[a])) return false;
+        return true;
+    }
+    // Outward padding that dominates the rounding of an f64 slab test and gives
+    // zero-thickness boxes (rects) a volume.
+    void pad() {
+        double m = 1e-3;
+        for (int a = 0; a < 3; ++a) m = std::fmax(m, std::fmax(std::fabs(lo[a]), std::fabs(hi[a])));
+        double e = 1e-9 * m;
+        for (int a = 0; a < 3; ++a) {
+            lo[a] -= e;
+            hi[a] += e;
+        }
+    }
+};
+
+void rect_axes(uint32_t plane, int &k, int &a, int &b) {  // rect.rs:26-32
+    switch (plane) {
+        case RT_PLANE_YZ: k = 0; a = 1; b = 2; break;
+        case RT_PLANE_XZ: k = 1; a = 0; b = 2; break;
+        default: k = 2; a = 0; b = 1; break;
+    }
+}
+void rotate_axes(uint32_t axis, int &r, int &a, int &b) {  // rotate.rs:15-21
+    switch (axis) {
+        case RT_AXIS_X: r = 0; a = 1; b = 2; break;
+        case RT_AXIS_Y: r = 1; a = 0; b = 2; break;
+        default: r = 2; a = 0; b = 1; break;
+    }
+}
+
+Box prim_box(const DPrim &p) {
+    Box b;
+    b.reset();
+    switch (p.kind) {
+        case PRIM_SPHERE: {
+            double r = std::fabs(p.d[3]);
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = p.d[a] - r;
+                b.hi[a] = p.d[a] + r;
+            }
+            break;
+        }
+        case PRIM_MSPHERE: {  // union of the boxes at center0 and center1 (sphere.rs:191-201, §Q18)
+            double r = std::fabs(p.d[8]);
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::fmin(p.d[a], p.d[3 + a]) - r;
+                b.hi[a] = std::fmax(p.d[a], p.d[3 + a]) + r;
+            }
+            break;
+        }
+        case PRIM_RECT: {  // correct bounds on the rect's own plane (the reference's are wrong, §Q5)
+            int k, a, bb;
+            rect_axes(p.axis, k, a, bb);
+            b.lo[a] = std::fmin(p.d[0], p.d[1]);
+            b.hi[a] = std::fmax(p.d[0], p.d[1]);
+            b.lo[bb] = std::fmin(p.d[2], p.d[3]);
+            b.hi[bb] = std::fmax(p.d[2], p.d[3]);
+            b.lo[k] = b.hi[k] = p.d[4];
+            break;
+        }
+        case PRIM_TRI: {
+            double v0[3] = {p.d[0], p.d[1], p.d[2]};
+            double v1[3] = {p.d[0] + p.d[3], p.d[1] + p.d[4], p.d[2] + p.d[5]};
+            double v2[3] = {p.d[0] + p.d[6], p.d[1] + p.d[7], p.d[2] + p.d[8]};
+            b.grow(v0);
+            b.grow(v1);
+            b.grow(v2);
+            // v1, v2 are re-derived from v0 + e: cover the rounding of that sum
+            for (int a = 0; a < 3; ++a) {
+                double e = 4e-16 * std::fmax(std::fabs(b.lo[a]), std::fabs(b.hi[a]));
+                b.lo[a] -= e;
+                b.hi[a] += e;
+            }
+            break;
+        }
+        case PRIM_BOX:
+            for (int a = 0; a < 3; ++a) {
+                b.lo[a] = std::fmin(p.d[a], p.d[3 + a]);
+                b.hi[a] = std::fmax(p.d[a], p.d[3 + a]);
+            }
+            break;
+    }
+    return b;
+}
+
+// object space -> the space above the chain: inverse ops, innermost first
+// (translate.rs:26, rotate.rs:94-95)
+void point_to_outer(const std::vector<DOp> &ops, double p[3]) {
+    for (size_t i = ops.size(); i-- > 0;) {
+        const DOp &op = ops[i];
+        if (op.kind == OP_TRANSLATE) {
+            for (int a = 0; a < 3; ++a) p[a] += op.offset[a];
+        } else if (op.kind == OP_ROTATE) {
+            int r, a, b;
+            rotate_axes(op.axis, r, a, b);
+            double pa = op.cos_theta * p[a] + op.sin_theta * p[b];
+            double pb = -op.sin_theta * p[a] + op.cos_theta * p[b];
+            p[a] = pa;
+            p[b] = pb;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Binned SAH BVH2
+// ---------------------------------------------------------------------------
+struct TNode {
+    Box box;
+    int left = -1, right = -1;  // inner
+    uint32_t first = 0, count = 0;  // leaf (into the order[] permutation)
+};
+
+struct Builder {
+    const std::vector<Box> &boxes;
+    std::vector<uint32_t> &order;
+    std::vector<TNode> nodes;
+    uint32_t max_depth = 0;
+    std::vector<double> cx[3];
+
+    Builder(const std::vector<Box> &b, std::vector<uint32_t> &o) : boxes(b), order(o) {
+        for (int a = 0; a < 3; ++a) {
+            cx[a].resize(b.size());
+            for (size_t i = 0; i < b.size(); ++i) cx[a][i] = 0.5 * (b[i].lo[a] + b[i].hi[a]);
+        }
+    }
+
+    int build(uint32_t first, uint32_t count, uint32_t depth) {
+        int id = (int)nodes.size();
+        nodes.emplace_back();
+        Box box, cbox;
+        box.reset();
+        cbox.reset();
+        for (uint32_t i = first; i < first + count; ++i) {
+            box.grow(boxes[order[i]]);
+            double c[3] = {cx[0][order[i]], cx[1][order[i]], cx[2][order[i]]};
+            cbox.grow(c);
+        }
+        nodes[id].box = box;
+        max_depth = std::max(max_depth, depth);
+        if (count <= LEAF_MAX) {
+            nodes[id].first = first;
+            nodes[id].count = count;
+            return id;
+        }
+        int axis = 0;
+        double ext[3] = {cbox.hi[0] - cbox.lo[0], cbox.hi[1] - cbox.lo[1], cbox.hi[2] - cbox.lo[2]};
+        if (ext[1] > ext[axis]) axis = 1;
+        if (ext[2] > ext[axis]) axis = 2;
+        uint32_t mid = first + count / 2;
+        bool done = false;
+        if ((int)depth < FORCE_MEDIAN_DEPTH && ext[axis] > 0.0) {
+            // binned SAH over all three axes
+            double best_cost = DBL_MAX;
+            int best_axis = -1, best_bin = -1;
+            for (int ax = 0; ax < 3; ++ax) {
+                if (!(ext[ax] > 0.0)) continue;
+                Box bb[N_BINS];
+                uint32_t bn[N_BINS];
+                for (int k = 0; k < N_BINS; ++k) {
+                    bb[k].reset();
+                    bn[k] = 0;
+                }
+                double scale = (double)N_BINS / ext[ax];
+                for (uint32_t i = first; i < first + count; ++i) {
+                    int k = (int)((cx[ax][order[i]] - cbox.lo[ax]) * scale);
+                    k = std::min(std::max(k, 0), N_BINS - 1);
+                    bb[k].grow(boxes[order[i]]);
+                    bn[k]++;
+                }
+                double right_area[N_BINS];
+                uint32_t right_n[N_BINS];
+                Box acc;
+                acc.reset();
+                uint32_t n = 0;
+                for (int k = N_BINS - 1; k > 0; --k) {
+                    if (bn[k]) acc.grow(bb[k]);
+                    n += bn[k];
+                    right_area[k] = n ? acc.area() : 0.0;
+                    right_n[k] = n;
+                }
+                acc.reset();
+                n = 0;
+                for (int k = 0; k < N_BINS - 1; ++k) {
+                    if (bn[k]) acc.grow(bb[k]);
+                    n += bn[k];
+                    if (n == 0 || right_n[k + 1] == 0) continue;
+                    double cost = acc.area() * (double)n + right_area[k + 1] * (double)right_n[k + 1];
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best_axis = ax;
+                        best_bin = k;
+                    }
+                }
+            }
+            if (best_axis >= 0) {
+                double scale = (double)N_BINS / ext[best_axis];
+                double lo = cbox.lo[best_axis];
+                auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
+                    int k = (int)((cx[best_axis][p] - lo) * scale);
+                    k = std::min(std::max(k, 0), N_BINS - 1);
+                    return k <= best_bin;
+                });
+                mid = (uint32_t)(it - order.begin());
+                done = mid > first && mid < first + count;
+            }
+        }
+        if (!done) {  // object median on the widest axis
+            mid = first + count / 2;
+            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
+                             [&](uint32_t a, uint32_t b) { return cx[axis][a] < cx[axis][b]; });
+        }
+        int l = build(first, mid - first, depth + 1);
+        int r = build(mid, first + count - mid, depth + 1);
+        nodes[id].left = l;
+        nodes[id].right = r;
+        return id;
+    }
+};
+
+// Builds the BVH of prims[first, first+count) (reordering them) and appends the
+// nodes, breadth-first, to out.nodes.  Returns the root node index.
+int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
+    std::vector<Box> boxes(count);
+    for (uint32_t i = 0; i < count; ++i) {
+        boxes[i] = prim_box(out.prims[first + i]);
+        boxes[i].pad();
+    }
+    std::vector<uint32_t> order(count);
+    for (uint32_t i = 0; i < count; ++i) order[i] = i;
+    Builder b(boxes, order);
+    b.nodes.reserve(2 * count);
+    int root = b.build(0, count, 1);
+    out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth);
+    // permute the primitives into leaf order
+    std::vector<DPrim> tmp(count);
+    for (uint32_t i = 0; i < count; ++i) tmp[i] = out.prims[first + order[i]];
+    std::copy(tmp.begin(), tmp.end(), out.prims.begin() + first);
+    // breadth-first emission of the inner nodes
+    uint32_t base = (uint32_t)out.nodes.size();
+    std::vector<int> bfs;  // temp-node ids of inner nodes in BFS order
+    std::vector<int32_t> slot(b.nodes.size(), -1);
+    bfs.push_back(root);
+    slot[root] = 0;
+    for (size_t h = 0; h < bfs.size(); ++h) {
+        const TNode &n = b.nodes[bfs[h]];
+        for (int c : {n.left, n.right}) {
+            if (b.nodes[c].left >= 0) {
+                slot[c] = (int32_t)bfs.size();
+                bfs.push_back(c);
+            }
+        }
+    }
+    out.nodes.resize(base + bfs.size());
+    auto encode = [&](int c) -> int32_t {
+        const TNode &n = b.nodes[c];
+        if (n.left >= 0) return (int32_t)(base + slot[c]);
+        uint32_t code = ((first + n.first) << 3) | (n.count - 1);
+        return (int32_t)~code;
+    };
+    for (size_t h = 0; h < bfs.size(); ++h) {
+        const TNode &n = b.nodes[bfs[h]];
+        DBvhNode &dn = out.nodes[base + h];
+        const Box &b0 = b.nodes[n.left].box, &b1 = b.nodes[n.right].box;
+        for (int a = 0; a < 3; ++a) {
+            dn.lo0[a] = b0.lo[a];
+            dn.hi0[a] = b0.hi[a];
+            dn.lo1[a] = b1.lo[a];
+            dn.hi1[a] = b1.hi[a];
+        }
+        dn.child0 = encode(n.left);
+        dn.child1 = encode(n.right);
+        dn.pad0 = dn.pad1 = 0;
+    }
+    return (int32_t)base;
+}
+
+// ---------------------------------------------------------------------------
+// Graph walk
+// ---------------------------------------------------------------------------
+struct GroupBuild {
+    std::vector<DOp> xform;  // chain without flips
+    uint32_t chain = 0;
+    std::vector<DPrim> prims;
+};
+struct PendingMedium {
+    uint32_t node;
+    std::vector<DOp> stack;
+    uint32_t rank;
+};
+
+bool same_ops(const std::vector<DOp> &a, const std::vector<DOp> &b) {
+    if (a.size() != b.size()) return false;
+    for (size_t i = 0; i < a.size(); ++i) {
+        if (a[i].kind != b[i].kind || a[i].axis != b[i].axis) return false;
+        if (std::memcmp(&a[i].sin_theta, &b[i].sin_theta, sizeof(double) * 5) != 0) return false;
+    }
+    return true;
+}
+
+struct Walker {
+    const RtSceneDesc &d;
+    CompiledScene &out;
+    std::string &err;
+    RtStatus status = RT_OK;
+    std::vector<DOp> stack;
+    std::vector<std::vector<DOp>> chain_ops;  // interned chains
+    uint32_t rank = 0;
+    std::vector<GroupBuild> *groups = nullptr;
+    std::vector<PendingMedium> *media = nullptr;  // null while walking a medium boundary
+
+    bool fail(RtStatus s, const std::string &m) {
+        if (status == RT_OK) {
+            status = s;
+            err = m;
+        }
+        return false;
+    }
+    uint32_t intern_chain(const std::vector<DOp> &ops) {
+        for (size_t i = 0; i < chain_ops.size(); ++i)
+            if (same_ops(chain_ops[i], ops)) return (uint32_t)i;
+        chain_ops.push_back(ops);
+        return (uint32_t)(chain_ops.size() - 1);
+    }
+    GroupBuild &group_for_stack() {
+        std::vector<DOp> xf;
+        for (const DOp &op : stack)
+            if (op.kind != OP_FLIP) xf.push_back(op);
+        for (GroupBuild &g : *groups)
+            if (same_ops(g.xform, xf)) return g;
+        groups->emplace_back();
+        groups->back().xform = xf;
+        groups->back().chain = intern_chain(xf);
+        return groups->back();
+    }
+    bool check_material(uint32_t m) {
+        if (m >= d.n_materials) return fail(RT_ERR_BAD_ARGUMENT, "material index out of range");
+        return true;
+    }
+    void emit(DPrim p, uint32_t node_id) {
+        p.chain = intern_chain(stack);
+        p.node = (int32_t)node_id;
+        p.rank = rank++;
+        p.pad0 = p.pad1 = 0;
+        for (int i = 0; i < 12; ++i)
+            if (p.d[i] != p.d[i]) {
+                fail(RT_ERR_BAD_ARGUMENT, "NaN primitive parameter");
+                return;
+            }
+        group_for_stack().prims.push_back(p);
+    }
+    bool walk(uint32_t id, uint32_t depth) {
+        if (status != RT_OK) return false;
+        if (id >= d.n_nodes) return fail(RT_ERR_BAD_ARGUMENT, "node index out of range");
+        if (depth > d.n_nodes + 1) return fail(RT_ERR_BAD_ARGUMENT, "cycle in scene graph");
+        const RtNode &n = d.nodes[id];
+        DPrim p;
+        std::memset(&p, 0, sizeof(p));
+        p.material = n.material;
+        switch (n.kind) {
+            case RT_NODE_SPHERE:
+                if (!check_material(n.material)) return false;
+                p.kind = PRIM_SPHERE;
+                for (int i = 0; i < 4; ++i) p.d[i] = n.v[i];
+                emit(p, id);
+                break;
+            case RT_NODE_MOVING_SPHERE:
+                if (!check_material(n.material)) return false;
+                p.kind = PRIM_MSPHERE;
+                for (int i = 0; i < 9; ++i) p.d[i] = n.v[i];
+                emit(p, id);
+                break;
+            case RT_NODE_RECT:
+                if (!check_material(n.material)) return false;
+                if (n.axis > 2) return fail(RT_ERR_BAD_ARGUMENT, "bad rect plane");
+                p.kind = PRIM_RECT;
+                p.axis = n.axis;
+                for (int i = 0; i < 5; ++i) p.d[i] = n.v[i];
+                emit(p, id);
+                break;
+            case RT_NODE_TRIANGLE: {
+                if (!check_material(n.material)) return false;
+                p.kind = PRIM_TRI;
+                // tri.rs:27-28: e1 = v1 - v0, e2 = v2 - v0 ; tri.rs:41: normal = normalize(e1 x e2)
+                double e1[3], e2[3];
+                for (int a = 0; a < 3; ++a) {
+                    p.d[a] = n.v[a];
+                    e1[a] = n.v[3 + a] - n.v[a];
+                    e2[a] = n.v[6 + a] - n.v[a];
+                    p.d[3 + a] = e1[a];
+                    p.d[6 + a] = e2[a];
+                }
+                double c[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+                double len = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+                // A degenerate triangle gives a NaN normal in the reference too; keep the
+                // primitive (its hit test uses only v0,e1,e2) but store a zero normal marker.
+                for (int a = 0; a < 3; ++a) p.d[9 + a] = len > 0.0 ? c[a] / len : 0.0;
+                emit(p, id);
+                break;
+            }
+            case RT_NODE_CUBE:
+                if (!check_material(n.material)) return false;
+                p.kind = PRIM_BOX;
+                for (int i = 0; i < 6; ++i) p.d[i] = n.v[i];
+                emit(p, id);
+                break;
+            case RT_NODE_LIST:
+            case RT_NODE_BVH: {
+                if ((uint64_t)n.child + n.count > d.n_child_index) return fail(RT_ERR_BAD_ARGUMENT, "child range out of bounds");
+                if (n.kind == RT_NODE_BVH && n.count == 0) return fail(RT_ERR_EMPTY_SCENE, "no object in the scene");  // bvh.rs:55
+                for (uint32_t i = 0; i < n.count; ++i)
+                    if (!walk(d.child_index[n.child + i], depth + 1)) return false;
+                break;
+            }
+            case RT_NODE_TRANSLATE: {
+                DOp op;
+                std::memset(&op, 0, sizeof(op));
+                op.kind = OP_TRANSLATE;
+                for (int a = 0; a < 3; ++a) op.offset[a] = n.v[a];
+                stack.push_back(op);
+                bool ok = walk(n.child, depth + 1);
+                stack.pop_back();
+                if (!ok) return false;
+                break;
+            }
+            case RT_NODE_ROTATE: {
+                if (n.axis > 2) return fail(RT_ERR_BAD_ARGUMENT, "bad rotate axis");
+                DOp op;
+                std::memset(&op, 0, sizeof(op));
+                op.kind = OP_ROTATE;
+                op.axis = n.axis;
+                double radiants = (PI / 180.0) * n.v[0];  // rotate.rs:34-36
+                op.sin_theta = std::sin(radiants);
+                op.cos_theta = std::cos(radiants);
+                stack.push_back(op);
+                bool ok = walk(n.child, depth + 1);
+                stack.pop_back();
+                if (!ok) return false;
+                break;
+            }
+            case RT_NODE_FLIP: {
+                DOp op;
+                std::memset(&op, 0, sizeof(op));
+                op.kind = OP_FLIP;
+                stack.push_back(op);
+                bool ok = walk(n.child, depth + 1);
+                stack.pop_back();
+                if (!ok) return false;
+                break;
+            }
+            case RT_NODE_MEDIUM: {
+                if (!check_material(n.material)) return false;
+                if (!media) return fail(RT_ERR_UNSUPPORTED, "a ConstantMedium inside a medium boundary is not supported");
+                media->push_back(PendingMedium{id, stack, rank++});
+                break;
+            }
+            default:
+                return fail(RT_ERR_BAD_ARGUMENT, "unknown node kind");
+        }
+        return status == RT_OK;
+    }
+};
+
+bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::string &err) {
+    for (GroupBuild &g : gb) {
+        if (g.prims.empty()) continue;
+        DGroup dg;
+        std::memset(&dg, 0, sizeof(dg));
+        dg.chain = g.chain;
+        dg.first_prim = (uint32_t)out.prims.size();
+        dg.n_prims = (uint32_t)g.prims.size();
+        if (out.prims.size() + g.prims.size() >= (1u << 28)) {
+            err = "too many primitives";
+            return false;
+        }
+        out.prims.insert(out.prims.end(), g.prims.begin(), g.prims.end());
+        Box ob;
+        ob.reset();
+        for (const DPrim &p : g.prims) ob.grow(prim_box(p));
+        if (!ob.finite()) {
+            err = "non-finite primitive bounds";
+            return false;
+        }
+        ob.pad();
+        Box wb;
+        wb.reset();
+        for (int c = 0; c < 8; ++c) {
+            double p[3] = {(c & 1) ? ob.hi[0] : ob.lo[0], (c & 2) ? ob.hi[1] : ob.lo[1], (c & 4) ? ob.hi[2] : ob.lo[2]};
+            point_to_outer(g.xform, p);
+            wb.grow(p);
+        }
+        wb.pad();
+        for (int a = 0; a < 3; ++a) {
+            dg.bmin[a] = wb.lo[a];
+            dg.bmax[a] = wb.hi[a];
+        }
+        dg.bvh_root = -1;
+        if (dg.n_prims > LINEAR_MAX) dg.bvh_root = build_group_bvh(out, dg.first_prim, dg.n_prims);
+        out.groups.push_back(dg);
+    }
+    return true;
+}
+
+bool texture_needs_uv(const RtSceneDesc &d, uint32_t id, int depth) {
+    if (id >= d.n_textures || depth > 16) return false;
+    const RtTexture &t = d.textures[id];
+    if (t.kind == RT_TEX_IMAGE) return true;
+    if (t.kind == RT_TEX_CHECKER) return texture_needs_uv(d, t.a, depth + 1) || texture_needs_uv(d, t.b, depth + 1);
+    return false;
+}
+
+}  // namespace
+
+RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &err) {
+    if (d.abi_version != RTB200_ABI_VERSION) {
+        err = "abi version mismatch";
+        return RT_ERR_BAD_ARGUMENT;
+    }
+    if (!d.nodes || d.n_nodes == 0) {
+        err = "no object in the scene";
+        return RT_ERR_EMPTY_SCENE;
+    }
+    if ((d.n_child_index && !d.child_index) || (d.n_materials && !d.materials) || (d.n_textures && !d.textures) ||
+        (d.n_perlin && !d.perlin) || (d.n_images && !d.images) || (d.n_texel_bytes && !d.texels)) {
+        err = "null table pointer with a non-zero count";
+        return RT_ERR_BAD_ARGUMENT;
+    }
+    // ---- textures / materials ----
+    for (uint64_t i = 0; i < d.n_textures; ++i) {
+        const RtTexture &t = d.textures[i];
+        DTexture dt;
+        std::memset(&dt, 0, sizeof(dt));
+        dt.kind = t.kind;
+        dt.a = t.a;
+        dt.b = t.b;
+        for (int a = 0; a < 3; ++a) dt.color[a] = t.color[a];
+        dt.scale = t.scale;
+        switch (t.kind) {
+            case RT_TEX_CONSTANT: break;
+            case RT_TEX_CHECKER:
+                // children must precede or follow; only the range is checked (cycles would loop: bound the walk on device)
+                if (t.a >= d.n_textures || t.b >= d.n_textures) {
+                    err = "checker texture child out of range";
+                    return RT_ERR_BAD_ARGUMENT;
+                }
+                break;
+            case RT_TEX_NOISE:
+                if (t.a >= d.n_perlin) {
+                    err = "noise texture perlin index out of range";
+                    return RT_ERR_BAD_ARGUMENT;
+                }
+                break;
+            case RT_TEX_IMAGE:
+                if (t.a >= d.n_images) {
+                    err = "image texture index out of range";
+                    return RT_ERR_BAD_ARGUMENT;
+                }
+                break;
+            default:
+                err = "unknown texture kind";
+                return RT_ERR_BAD_ARGUMENT;
+        }
+        out.textures.push_back(dt);
+    }
+    for (uint64_t i = 0; i < d.n_images; ++i) {
+        const RtImage &im = d.images[i];
+        if (im.width == 0 || im.height == 0 || im.offset + (uint64_t)im.width * im.height * 3 > d.n_texel_bytes) {
+            err = "image outside the texel pool";
+            return RT_ERR_BAD_ARGUMENT;
+        }
+        out.images.push_back(DImage{im.width, im.height, im.offset});
+    }
+    out.perlin.resize(d.n_perlin);
+    for (uint64_t i = 0; i < d.n_perlin; ++i) {
+        static_assert(sizeof(DPerlin) == sizeof(RtPerlin), "perlin layout");
+        std::memcpy(&out.perlin[i], &d.perlin[i], sizeof(DPerlin));
+        for (int k = 0; k < 256; ++k)
+            if (d.perlin[i].perm_x[k] > 255 || d.perlin[i].perm_y[k] > 255 || d.perlin[i].perm_z[k] > 255) {
+                err = "perlin permutation entry out of range";
+                return RT_ERR_BAD_ARGUMENT;
+            }
+    }
+    if (d.n_texel_bytes) out.texels.assign(d.texels, d.texels + d.n_texel_bytes);
+    for (uint64_t i = 0; i < d.n_materials; ++i) {
+        const RtMaterial &m = d.materials[i];
+        DMaterial dm;
+        std::memset(&dm, 0, sizeof(dm));
+        dm.kind = m.kind;
+        dm.texture = m.texture;
+        for (int a = 0; a < 3; ++a) dm.albedo[a] = m.albedo[a];
+        dm.fuzz = m.fuzz;
+        dm.ir = m.ir;
+        if (m.kind > RT_MAT_ISOTROPIC) {
+            err = "unknown material kind";
+            return RT_ERR_UNSUPPORTED;
+        }
+        bool textured = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC;
+        if (textured && m.texture >= d.n_textures) {
+            err = "texture index out of range";
+            return RT_ERR_BAD_ARGUMENT;
+        }
+        dm.needs_uv = textured && texture_needs_uv(d, m.texture, 0) ? 1u : 0u;
+        out.materials.push_back(dm);
+    }
+    for (int a = 0; a < 3; ++a) out.background[a] = d.background[a];
+
+    // ---- world ----
+    Walker w{d, out, err};
+    std::vector<GroupBuild> world_groups;
+    std::vector<PendingMedium> pending;
+    w.groups = &world_groups;
+    w.media = &pending;
+    if (!w.walk(d.world, 0)) return w.status;
+    if (!finalize_groups(out, world_groups, err)) return RT_ERR_BAD_ARGUMENT;
+    out.n_world_groups = (uint32_t)out.groups.size();
+    if (out.n_world_groups == 0 && pending.empty()) {
+        err = "no object in the scene";
+        return RT_ERR_EMPTY_SCENE;
+    }
+    // ---- media: each boundary is its own sub-scene ----
+    for (const PendingMedium &pm : pending) {
+        const RtNode &n = d.nodes[pm.node];
+        std::vector<GroupBuild> bgroups;
+        w.groups = &bgroups;
+        w.media = nullptr;
+        w.stack = pm.stack;
+        if (!w.walk(n.child, 0)) return w.status;
+        DMedium dm;
+        std::memset(&dm, 0, sizeof(dm));
+        dm.first_group = (uint32_t)out.groups.size();
+        if (!finalize_groups(out, bgroups, err)) return RT_ERR_BAD_ARGUMENT;
+        dm.n_groups = (uint32_t)out.groups.size() - dm.first_group;
+        dm.chain = w.intern_chain(pm.stack);
+        dm.material = n.material;
+        dm.node = (int32_t)pm.node;
+        dm.rank = pm.rank;
+        dm.density = n.v[0];
+        out.media.push_back(dm);
+    }
+    w.stack.clear();
+    // ---- chains / ops ----
+    for (const std::vector<DOp> &ops : w.chain_ops) {
+        DChain c{(uint32_t)out.ops.size(), (uint32_t)ops.size()};
+        out.ops.insert(out.ops.end(), ops.begin(), ops.end());
+        out.chains.push_back(c);
+    }
+    // ---- lights (pdf.rs PDF::Hittable over the light list) ----
+    if (d.lights >= d.n_nodes || d.nodes[d.lights].kind != RT_NODE_LIST) {
+        err = "lights must be a LIST node";
+        return RT_ERR_BAD_ARGUMENT;
+    }
+    const RtNode &ln = d.nodes[d.lights];
+    if ((uint64_t)ln.child + ln.count > d.n_child_index) {
+        err = "light list out of bounds";
+        return RT_ERR_BAD_ARGUMENT;
+    }
+    if (ln.count > 2048) {
+        err = "more than 2048 lights";  // the light index comes from 11 spare Philox bits
+        return RT_ERR_UNSUPPORTED;
+    }
+    for (uint32_t i = 0; i < ln.count; ++i) {
+        uint32_t id = d.child_index[ln.child + i];
+        uint32_t guard = 0;
+        // FlipNormal forwards pdf_value/random (hit.rs:126-132); every other wrapper keeps the
+        // trait defaults (hit.rs:29-30): pdf 0 and direction (1,0,0).
+        while (id < d.n_nodes && d.nodes[id].kind == RT_NODE_FLIP && guard++ < d.n_nodes) id = d.nodes[id].child;
+        if (id >= d.n_nodes) {
+            err = "light node out of range";
+            return RT_ERR_BAD_ARGUMENT;
+        }
+        const RtNode &n = d.nodes[id];
+        DLight l;
+        std::memset(&l, 0, sizeof(l));
+        if (n.kind == RT_NODE_RECT) {
+            l.kind = LIGHT_RECT;
+            l.axis = n.axis;
+            for (int k = 0; k < 5; ++k) l.d[k] = n.v[k];
+        } else if (n.kind == RT_NODE_SPHERE) {
+            l.kind = LIGHT_SPHERE;
+            for (int k = 0; k < 4; ++k) l.d[k] = n.v[k];
+        } else {
+            l.kind = LIGHT_DEFAULT;
+        }
+        out.lights.push_back(l);
+    }
+    return RT_OK;
+}
+
+}  // namespace rtb200dev

@@ -1,0 +1,204 @@
+// kernels.cu — CUDA kernels of the hot path and their launchers (sm_100a).
+//
+// render_kernel replaces the nested pixel / sample loop of src/main.rs:772-834.
+// Design (DESIGN.md "Kernels"): persistent threads, one path per lane, per-lane
+// regeneration.  A work item is (sample chunk, pixel); a lane pulls items from a
+// global counter, runs the chunk's samples one after the other in sample order,
+// and writes the chunk's f64 sum to its own slot of a [chunk][pixel] plane —
+// no atomics on pixel data, so the image is bit-reproducible run to run.
+// reduce_planes_kernel then adds the planes in chunk order into the fp32 image.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "trace.cuh"
+
+namespace rtb200dev {
+
+// pixel order inside the item space: 8x4 tiles so that the 32 lanes of a warp start
+// on neighbouring pixels (coherent primary rays and BVH paths)
+__device__ __forceinline__ bool item_pixel(const RenderParams &P, uint64_t lin, uint32_t &i, uint32_t &row) {
+    uint32_t tile = (uint32_t)(lin >> 5), within = (uint32_t)(lin & 31u);
+    uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    i = tx * 8u + (within & 7u);
+    row = ty * 4u + (within >> 3);
+    return i < P.width && row < P.height;
+}
+
+__global__ void __launch_bounds__(kRenderBlock)
+render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
+              const __grid_constant__ RenderParams P, double *__restrict__ planes,
+              unsigned long long *__restrict__ counters) {
+    unsigned long long n_paths = 0, n_rays = 0, n_bad = 0;
+    PathState ps;
+    bool alive = false, have_item = false;
+    uint32_t i = 0, row = 0, s = 0, s_end = 0;
+    uint64_t slot = 0;
+    V3 sum = mk(0.0, 0.0, 0.0);
+    for (;;) {
+        if (!alive) {
+            if (!have_item || s == s_end) {
+                if (have_item) {
+                    double *dst = planes + 3 * slot;
+                    dst[0] = sum.x;
+                    dst[1] = sum.y;
+                    dst[2] = sum.z;
+                    have_item = false;
+                }
+                // next (chunk, pixel) item; skip the padding of partial tiles
+                for (;;) {
+                    unsigned long long item = atomicAdd(&counters[kCounterWork], 1ull);
+                    if (item >= P.n_items) break;
+                    uint32_t chunk = (uint32_t)(item / P.items_per_chunk);
+                    uint64_t lin = item - (uint64_t)chunk * P.items_per_chunk;
+                    if (!item_pixel(P, lin, i, row)) continue;
+                    s = P.sample_begin + chunk * P.chunk_size;
+                    s_end = min(s + P.chunk_size, P.sample_end);
+                    slot = (uint64_t)chunk * P.width * P.height + (uint64_t)row * P.width + i;
+                    sum = mk(0.0, 0.0, 0.0);
+                    have_item = true;
+                    break;
+                }
+                if (!have_item) break;
+            }
+            // row 0 of the image is j = H-1 (main.rs:772)
+            path_begin(ps, cam, P.width, P.height, i, P.height - 1u - row, s, P.seed, P.max_depth);
+            ++s;
+            ++n_paths;
+            alive = true;
+        }
+        alive = path_step(sc, ps, P.integrator, P.flags);
+        if (!alive) {
+            n_rays += ps.segments;
+            // no NaN guard, like the reference (§Q10); only counted
+            if (!(isfinite(ps.radiance.x) && isfinite(ps.radiance.y) && isfinite(ps.radiance.z))) ++n_bad;
+            sum = sum + ps.radiance;  // vec.rs:253-260 Sum, in sample order
+        }
+    }
+    atomicAdd(&counters[kCounterPaths], n_paths);
+    atomicAdd(&counters[kCounterRays], n_rays);
+    atomicAdd(&counters[kCounterNonFinite], n_bad);
+}
+
+// out[p] (+)= sum over chunks of planes[c][p], c ascending: a fixed summation order
+__global__ void reduce_planes_kernel(const double *__restrict__ planes, float *__restrict__ out, uint64_t n_values,
+                                     uint32_t n_chunks) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (; k < n_values; k += stride) {
+        double acc = 0.0;
+        for (uint32_t c = 0; c < n_chunks; ++c) acc += planes[(uint64_t)c * n_values + k];
+        out[k] = (float)acc;
+    }
+}
+
+__global__ void first_hit_kernel(const __grid_constant__ DScene sc, const RtRay *__restrict__ rays, uint64_t n,
+                                 RtHit *__restrict__ hits) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Ray r;
+    r.o = ld3(rays[k].origin);
+    r.d = ld3(rays[k].direction);
+    r.time = rays[k].time;
+    Rng rng{0, 0, 0, 0};
+    Best best;
+    RtHit h;
+    if (!world_hit<false>(sc, r, rng, best)) {
+        h.node = -1;
+        h.face = 0;
+        h.material = -1;
+        h.front_face = 0;
+        h.t = 0.0;
+        h.u = h.v = 0.0;
+        for (int a = 0; a < 3; ++a) h.position[a] = h.normal[a] = 0.0;
+    } else {
+        HitRec rec;
+        resolve_hit<true>(sc, r, best, rec);
+        h.node = rec.node;
+        h.face = rec.face;
+        h.material = (int32_t)rec.material;
+        h.front_face = rec.front_face ? 1 : 0;
+        h.t = rec.t;
+        h.u = rec.u;
+        h.v = rec.v;
+        h.position[0] = rec.p.x; h.position[1] = rec.p.y; h.position[2] = rec.p.z;
+        h.normal[0] = rec.normal.x; h.normal[1] = rec.normal.y; h.normal[2] = rec.normal.z;
+    }
+    hits[k] = h;
+}
+
+__global__ void path_radiance_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
+                                     const __grid_constant__ RenderParams P, const uint32_t *__restrict__ px,
+                                     const uint32_t *__restrict__ py, const uint32_t *__restrict__ sample, uint64_t n,
+                                     double *__restrict__ rgb, uint32_t *__restrict__ segments) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    PathState ps;
+    path_begin(ps, cam, P.width, P.height, px[k], py[k], sample[k], P.seed, P.max_depth);
+    while (path_step(sc, ps, P.integrator, P.flags)) {
+    }
+    rgb[3 * k] = ps.radiance.x;
+    rgb[3 * k + 1] = ps.radiance.y;
+    rgb[3 * k + 2] = ps.radiance.z;
+    if (segments) segments[k] = ps.segments;
+}
+
+__global__ void camera_rays_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__ RenderParams P,
+                                   const uint32_t *__restrict__ px, const uint32_t *__restrict__ py,
+                                   const uint32_t *__restrict__ sample, uint64_t n, RtRay *__restrict__ rays) {
+    uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    Rng rng{P.seed, py[k] * P.width + px[k], sample[k], 0};
+    Ray r = camera_ray(cam, P.width, P.height, px[k], py[k], rng);
+    RtRay o;
+    o.origin[0] = r.o.x; o.origin[1] = r.o.y; o.origin[2] = r.o.z;
+    o.direction[0] = r.d.x; o.direction[1] = r.d.y; o.direction[2] = r.d.z;
+    o.time = r.time;
+    rays[k] = o;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+cudaError_t render_grid_size(int device, int *blocks_out) {
+    int sms = 0, per_sm = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, kRenderBlock, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    *blocks_out = sms * per_sm;  // persistent: exactly one resident wave
+    return cudaSuccess;
+}
+
+cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int blocks, double *planes,
+                          unsigned long long *counters, cudaStream_t stream) {
+    render_kernel<<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
+    return cudaGetLastError();
+}
+cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
+                                 cudaStream_t stream) {
+    uint64_t want = (n_values + 255) / 256;
+    int blocks = (int)(want < 148ull * 16 ? (want ? want : 1) : 148ull * 16);
+    reduce_planes_kernel<<<blocks, 256, 0, stream>>>(planes, out, n_values, n_chunks);
+    return cudaGetLastError();
+}
+cudaError_t launch_first_hit(const DScene &sc, const RtRay *rays, uint64_t n, RtHit *hits, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    first_hit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, rays, n, hits);
+    return cudaGetLastError();
+}
+cudaError_t launch_path_radiance(const DScene &sc, const RtCamera &cam, const RenderParams &P, const uint32_t *px,
+                                 const uint32_t *py, const uint32_t *sample, uint64_t n, double *rgb,
+                                 uint32_t *segments, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    path_radiance_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(sc, cam, P, px, py, sample, n, rgb, segments);
+    return cudaGetLastError();
+}
+cudaError_t launch_camera_rays(const RtCamera &cam, const RenderParams &P, const uint32_t *px, const uint32_t *py,
+                               const uint32_t *sample, uint64_t n, RtRay *rays, cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    camera_rays_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(cam, P, px, py, sample, n, rays);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb200dev

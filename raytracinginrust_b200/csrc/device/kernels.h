@@ -1,0 +1,41 @@
+// kernels.h — launch parameters and launcher declarations (host-visible).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../../include/rtb200.h"
+#include "tables.h"
+
+namespace rtb200dev {
+
+constexpr int kRenderBlock = 128;
+
+enum Counter : int { kCounterWork = 0, kCounterPaths = 1, kCounterRays = 2, kCounterNonFinite = 3, kNumCounters = 4 };
+
+struct RenderParams {
+    uint32_t width, height;
+    uint32_t max_depth;
+    uint32_t seed;
+    uint32_t integrator;
+    uint32_t flags;
+    uint32_t sample_begin, sample_end;  // this launch renders samples [begin, end)
+    uint32_t chunk_size;                // samples per work item
+    uint32_t n_chunks;
+    uint32_t tiles_x, tiles_y;          // 8x4 pixel tiles
+    uint64_t items_per_chunk;           // tiles_x * tiles_y * 32 (includes padding of partial tiles)
+    uint64_t n_items;                   // n_chunks * items_per_chunk
+};
+
+cudaError_t render_grid_size(int device, int *blocks_out);
+cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int blocks, double *planes,
+                          unsigned long long *counters, cudaStream_t stream);
+cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
+                                 cudaStream_t stream);
+cudaError_t launch_first_hit(const DScene &sc, const RtRay *rays, uint64_t n, RtHit *hits, cudaStream_t stream);
+cudaError_t launch_path_radiance(const DScene &sc, const RtCamera &cam, const RenderParams &P, const uint32_t *px,
+                                 const uint32_t *py, const uint32_t *sample, uint64_t n, double *rgb,
+                                 uint32_t *segments, cudaStream_t stream);
+cudaError_t launch_camera_rays(const RtCamera &cam, const RenderParams &P, const uint32_t *px, const uint32_t *py,
+                               const uint32_t *sample, uint64_t n, RtRay *rays, cudaStream_t stream);
+
+}  // namespace rtb200dev

@@ -1,0 +1,130 @@
+// tables.h — the HBM-resident layout of a compiled scene (shared by the host-side
+// scene compiler and the CUDA kernels).  See DESIGN.md "Data layout in HBM".
+//
+// The reference walks a Box<dyn Hittable> tree (src/hit.rs:26-31) with dynamic
+// dispatch.  Here the tree is compiled once into flat tables:
+//   prims   tagged-union primitive records (sphere.rs, rect.rs, tri.rs, cube.rs)
+//   ops     translate / rotate / flip steps      (translate.rs, rotate.rs, hit.rs:99-133)
+//   chains  op sequences, outermost first: the wrappers above a primitive
+//   groups  primitives that share a ray transform; linear or with a BVH
+//   nodes   flattened SAH BVH2, two child boxes per node, breadth-first order
+//   media   ConstantMedium records (medium.rs) with their boundary sub-scene
+//   lights  the light list (pdf.rs PDF::Hittable -> hit.rs:90-96)
+#pragma once
+#include <stdint.h>
+
+namespace rtb200dev {
+
+enum PrimKind : uint32_t { PRIM_SPHERE = 0, PRIM_MSPHERE = 1, PRIM_RECT = 2, PRIM_TRI = 3, PRIM_BOX = 4 };
+enum OpKind : uint32_t { OP_TRANSLATE = 0, OP_ROTATE = 1, OP_FLIP = 2 };
+enum LightKind : uint32_t { LIGHT_RECT = 0, LIGHT_SPHERE = 1, LIGHT_DEFAULT = 2 };
+
+// 128 bytes, 16-byte aligned: a whole record is eight 128-bit loads.
+struct alignas(16) DPrim {
+    uint32_t kind;      // PrimKind
+    uint32_t material;  // index into materials
+    uint32_t chain;     // index into chains (full wrapper sequence incl. flips)
+    uint32_t axis;      // RECT: RtPlane
+    int32_t node;       // RtSceneDesc node index (reported by the parity hooks)
+    uint32_t rank;      // position in the reference's traversal order (tie-break)
+    uint32_t pad0, pad1;
+    // SPHERE  cx cy cz r
+    // MSPHERE c0x c0y c0z c1x c1y c1z t0 t1 r
+    // RECT    a0 a1 b0 b1 k
+    // TRI     v0xyz e1xyz e2xyz nxyz   (e1 = v1-v0, e2 = v2-v0, n = normalize(e1 x e2): the
+    //                                   same f64 expressions tri.rs:27-28,41 evaluates per hit)
+    // BOX     minxyz maxxyz
+    double d[12];
+};
+
+struct alignas(16) DOp {
+    uint32_t kind;  // OpKind
+    uint32_t axis;  // ROTATE: RtAxis
+    double sin_theta, cos_theta;
+    double offset[3];
+};
+
+struct DChain {
+    uint32_t first_op, n_ops;
+};
+
+struct alignas(16) DGroup {
+    uint32_t chain;       // ray transform of this group (flips are skipped when transforming)
+    uint32_t first_prim;  // into prims
+    uint32_t n_prims;
+    int32_t bvh_root;     // node index, or -1: scan the primitives linearly
+    double bmin[3], bmax[3];  // conservative bounds in the space the ray is given in (culling only)
+};
+
+// Two child boxes per node.  child >= 0: inner node; child < 0: leaf, ~child = (first_prim << 3) | (count-1).
+struct alignas(16) DBvhNode {
+    double lo0[3], hi0[3];
+    double lo1[3], hi1[3];
+    int32_t child0, child1;
+    int32_t pad0, pad1;
+};
+
+struct alignas(16) DMedium {
+    uint32_t first_group, n_groups;  // boundary sub-scene
+    uint32_t chain;                  // wrappers above the medium itself
+    uint32_t material;               // the Isotropic phase function
+    int32_t node;                    // RtSceneDesc node index; also the RNG sub-slot
+    uint32_t rank;
+    double density;
+};
+
+struct alignas(16) DLight {
+    uint32_t kind;  // LightKind
+    uint32_t axis;  // RECT: RtPlane
+    double d[5];    // RECT a0 a1 b0 b1 k ; SPHERE cx cy cz r
+    double pad;
+};
+
+struct alignas(16) DMaterial {
+    uint32_t kind;     // RtMaterialKind
+    uint32_t texture;
+    uint32_t needs_uv;  // the texture tree reads (u,v): only image textures do
+    uint32_t pad;
+    double albedo[3];
+    double fuzz, ir;
+    double pad2;
+};
+
+struct alignas(16) DTexture {
+    uint32_t kind, a, b, pad;
+    double color[3];
+    double scale;
+};
+
+struct DImage {
+    uint32_t width, height;
+    uint64_t offset;
+};
+
+struct DPerlin {
+    double ranvec[256 * 3];
+    uint32_t perm_x[256], perm_y[256], perm_z[256];
+};
+
+// Pointers are device pointers once uploaded.
+struct DScene {
+    const DPrim *prims;
+    const DOp *ops;
+    const DChain *chains;
+    const DGroup *groups;
+    const DBvhNode *nodes;
+    const DMedium *media;
+    const DLight *lights;
+    const DMaterial *materials;
+    const DTexture *textures;
+    const DImage *images;
+    const DPerlin *perlin;
+    const uint8_t *texels;
+    uint32_t n_world_groups;  // the world sub-scene is groups [0, n_world_groups)
+    uint32_t n_media;
+    uint32_t n_lights;
+    uint32_t n_prims;
+    double background[3];
+};
+
+}  // namespace rtb200dev

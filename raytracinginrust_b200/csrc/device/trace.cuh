@@ -1,0 +1,804 @@
+// trace.cuh — device code of the path-tracing hot path (sm_100a, f64).
+//
+// Everything the reference's ray_color (src/main.rs:41-120) calls, as inlined
+// device functions over the flat tables of tables.h.  Arithmetic is f64 with the
+// reference's operation order; every value-producing expression cites the
+// reference line it restates.  Only culling (group bounds, BVH boxes) is new.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+
+#include "../../../include/rtb200.h"
+#include "tables.h"
+
+namespace rtb200dev {
+
+#define RT_DEV __device__ __forceinline__
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
+constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
+constexpr uint32_t kMediumFlag = 0x80000000u;
+constexpr int kStackSize = 64;
+
+// ---------------------------------------------------------------------------
+// Vec3 (src/vec.rs)
+// ---------------------------------------------------------------------------
+struct V3 {
+    double x, y, z;
+};
+RT_DEV V3 mk(double x, double y, double z) { return V3{x, y, z}; }
+RT_DEV V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_DEV V3 operator*(V3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
+RT_DEV V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+RT_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_DEV V3 operator/(V3 a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+RT_DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // vec.rs:38-40
+RT_DEV double length(V3 a) { return sqrt(dot(a, a)); }                        // vec.rs:42-44
+RT_DEV V3 cross(V3 a, V3 b) {                                                 // vec.rs:46-54
+    return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+RT_DEV V3 normalized(V3 a) { return a / length(a); }  // vec.rs:56-58
+RT_DEV double powi2(double x) { return x * x; }
+RT_DEV double powi5(double x) {
+    double x2 = x * x;
+    double x4 = x2 * x2;
+    return x4 * x;
+}
+RT_DEV double comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+RT_DEV void set_comp(V3 &v, int i, double s) {
+    if (i == 0) v.x = s;
+    else if (i == 1) v.y = s;
+    else v.z = s;
+}
+RT_DEV V3 ld3(const double *p) { return mk(p[0], p[1], p[2]); }
+RT_DEV bool near_zero(V3 a) {  // vec.rs:107-110
+    const double EPS = 1.0e-8;
+    return fabs(a.x) < EPS && fabs(a.y) < EPS && fabs(a.z) < EPS;
+}
+RT_DEV V3 reflect(V3 v, V3 n) { return v + ((-dot(v, n)) * 2.0) * n; }  // vec.rs:112-114
+RT_DEV V3 refract(V3 v, V3 n, double etai_over_etat) {                  // vec.rs:116-121
+    double cos_theta = fmin(dot((-1.0) * v, n), 1.0);
+    V3 r_out_perp = etai_over_etat * (v + cos_theta * n);
+    V3 r_out_para = ((-1.0) * sqrt(fabs(1.0 - powi2(length(r_out_perp))))) * n;
+    return r_out_perp + r_out_para;
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10, slot-addressed (DESIGN.md "Random numbers")
+// ---------------------------------------------------------------------------
+enum Slot : uint32_t { SLOT_PIXEL = 0, SLOT_LENS = 1, SLOT_TIME = 2, SLOT_MEDIUM = 3, SLOT_SCATTER = 4, SLOT_BALL = 5 };
+
+struct Draw {
+    double a, b;
+    uint32_t bits_a, bits_b;
+};
+struct Rng {
+    uint32_t seed, pixel, sample, bounce;
+};
+
+RT_DEV void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0;
+        c1 = lo1;
+        c2 = n2;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+RT_DEV double u53(uint32_t hi, uint32_t lo) {
+    unsigned long long x = ((unsigned long long)hi << 32) | lo;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+RT_DEV Draw draw(const Rng &r, uint32_t slot, uint32_t sub) {
+    uint32_t c0 = r.bounce, c1 = slot, c2 = sub, c3 = r.seed;
+    philox4x32_10(c0, c1, c2, c3, r.pixel, r.sample);
+    Draw d;
+    d.a = u53(c0, c1);
+    d.b = u53(c2, c3);
+    d.bits_a = c1 & 0x7FFu;
+    d.bits_b = c3 & 0x7FFu;
+    return d;
+}
+RT_DEV double gen_range(double lo, double hi, double u) { return lo + (hi - lo) * u; }
+
+RT_DEV V3 random_in_unit_sphere(const Rng &rng) {  // vec.rs:78-85
+    for (uint32_t it = 0;; ++it) {
+        Draw d0 = draw(rng, SLOT_BALL, 2 * it);
+        Draw d1 = draw(rng, SLOT_BALL, 2 * it + 1);
+        V3 v = mk(gen_range(-1.0, 1.0, d0.a), gen_range(-1.0, 1.0, d0.b), gen_range(-1.0, 1.0, d1.a));
+        if (length(v) < 1.0) return v;
+    }
+}
+RT_DEV V3 random_in_unit_disk(const Rng &rng) {  // vec.rs:96-105
+    for (uint32_t it = 0;; ++it) {
+        Draw d = draw(rng, SLOT_LENS, it);
+        V3 p = mk(gen_range(-1.0, 1.0, d.a), gen_range(-1.0, 1.0, d.b), 0.0);
+        if (length(p) < 1.0) return p;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Ray (src/ray.rs) and ONB (src/onb.rs)
+// ---------------------------------------------------------------------------
+struct Ray {
+    V3 o, d;
+    double time;
+};
+RT_DEV V3 ray_at(const Ray &r, double t) { return r.o + t * r.d; }  // ray.rs:26-28
+
+struct ONB {
+    V3 u, v, w;
+};
+RT_DEV ONB onb_from_w(V3 n) {  // onb.rs:8-21
+    ONB o;
+    o.w = normalized(n);
+    V3 a = fabs(o.w.x) > 0.9 ? mk(0.0, 1.0, 0.0) : mk(1.0, 0.0, 0.0);
+    o.v = normalized(cross(o.w, a));
+    o.u = cross(o.w, o.v);
+    return o;
+}
+RT_DEV V3 onb_local(const ONB &o, V3 a) { return a.x * o.u + a.y * o.v + a.z * o.w; }  // onb.rs:35-37
+
+// ---------------------------------------------------------------------------
+// Wrapper chains: Translate (translate.rs:22-30), Rotate (rotate.rs:77-106), FlipNormal (hit.rs:113-120)
+// ---------------------------------------------------------------------------
+RT_DEV void rect_axes(uint32_t plane, int &k, int &a, int &b) {  // rect.rs:26-32
+    if (plane == RT_PLANE_YZ) { k = 0; a = 1; b = 2; }
+    else if (plane == RT_PLANE_XZ) { k = 1; a = 0; b = 2; }
+    else { k = 2; a = 0; b = 1; }
+}
+RT_DEV void rotate_axes(uint32_t axis, int &a, int &b) {  // rotate.rs:15-21
+    if (axis == RT_AXIS_X) { a = 1; b = 2; }
+    else if (axis == RT_AXIS_Y) { a = 0; b = 2; }
+    else { a = 0; b = 1; }
+}
+// rotate.rs:82-86: into the rotated (object) frame
+RT_DEV V3 rot_fwd(const DOp &op, V3 v) {
+    int a, b;
+    rotate_axes(op.axis, a, b);
+    double va = comp(v, a), vb = comp(v, b);
+    V3 r = v;
+    set_comp(r, a, op.cos_theta * va - op.sin_theta * vb);
+    set_comp(r, b, op.sin_theta * va + op.cos_theta * vb);
+    return r;
+}
+// rotate.rs:94-98: back out of the rotated frame
+RT_DEV V3 rot_back(const DOp &op, V3 v) {
+    int a, b;
+    rotate_axes(op.axis, a, b);
+    double va = comp(v, a), vb = comp(v, b);
+    V3 r = v;
+    set_comp(r, a, op.cos_theta * va + op.sin_theta * vb);
+    set_comp(r, b, -op.sin_theta * va + op.cos_theta * vb);
+    return r;
+}
+// Ray as seen below ops [first, first+n) of a chain (flips do not touch the ray).
+RT_DEV void chain_ray(const DScene &sc, uint32_t first, uint32_t n, V3 &o, V3 &d) {
+    for (uint32_t i = 0; i < n; ++i) {
+        const DOp &op = sc.ops[first + i];
+        if (op.kind == OP_TRANSLATE) {
+            o = o - ld3(op.offset);  // translate.rs:23
+        } else if (op.kind == OP_ROTATE) {
+            o = rot_fwd(op, o);
+            d = rot_fwd(op, d);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Primitive tests.  During the closest-hit search only t (and the cube face) is
+// produced; the full HitRecord is resolved once, for the winner.
+// ---------------------------------------------------------------------------
+// Sphere::hit / MovingSphere::hit root search (sphere.rs:56-73 == :150-167)
+RT_DEV bool sphere_root(V3 o, V3 d, V3 center, double radius, double t_min, double t_max, double &root_out) {
+    V3 oc = o - center;
+    double a = powi2(length(d));
+    double half_b = dot(oc, d);
+    double c = powi2(length(oc)) - powi2(radius);
+    double discriminant = powi2(half_b) - a * c;
+    if (discriminant < 0.0) return false;
+    double sqrt_d = sqrt(discriminant);
+    double root = (-half_b - sqrt_d) / a;
+    if (root < t_min || root > t_max) {
+        root = (-half_b + sqrt_d) / a;
+        if (root < t_min || root > t_max) return false;
+    }
+    root_out = root;
+    return true;
+}
+RT_DEV V3 msphere_center(const double *pd, double time) {  // sphere.rs:144-146
+    V3 c0 = ld3(pd), c1 = ld3(pd + 3);
+    return c0 + ((time - pd[6]) / (pd[7] - pd[6])) * (c1 - c0);
+}
+// AARect::hit up to the bounds test (rect.rs:49-58)
+RT_DEV bool rect_t(V3 o, V3 d, uint32_t plane, double a0, double a1, double b0, double b1, double k, double t_min,
+                   double t_max, double &t_out) {
+    int ki, ai, bi;
+    rect_axes(plane, ki, ai, bi);
+    double t = (k - comp(o, ki)) / comp(d, ki);
+    if (t < t_min || t > t_max) return false;
+    double a = comp(o, ai) + t * comp(d, ai);
+    double b = comp(o, bi) + t * comp(d, bi);
+    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
+    t_out = t;
+    return true;
+}
+// The six sides of a Cube in the order of cube.rs:17-25.
+RT_DEV void box_face(const double *pd, int face, uint32_t &plane, double &a0, double &a1, double &b0, double &b1, double &k) {
+    // pd = minx miny minz maxx maxy maxz
+    if (face < 2) {
+        plane = RT_PLANE_XY; a0 = pd[0]; a1 = pd[3]; b0 = pd[1]; b1 = pd[4]; k = face == 0 ? pd[5] : pd[2];
+    } else if (face < 4) {
+        plane = RT_PLANE_XZ; a0 = pd[0]; a1 = pd[3]; b0 = pd[2]; b1 = pd[5]; k = face == 2 ? pd[4] : pd[1];
+    } else {
+        plane = RT_PLANE_YZ; a0 = pd[1]; a1 = pd[4]; b0 = pd[2]; b1 = pd[5]; k = face == 4 ? pd[3] : pd[0];
+    }
+}
+// Cube::hit = HittableList::hit over the six rects (cube.rs:35-37, hit.rs:59-71)
+RT_DEV bool box_t(V3 o, V3 d, const double *pd, double t_min, double t_max, double &t_out, int &face_out) {
+    bool any = false;
+    double closest = t_max;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) {
+        uint32_t plane;
+        double a0, a1, b0, b1, k, t;
+        box_face(pd, f, plane, a0, a1, b0, b1, k);
+        if (rect_t(o, d, plane, a0, a1, b0, b1, k, t_min, closest, t)) {
+            closest = t;
+            face_out = f;
+            any = true;
+        }
+    }
+    t_out = closest;
+    return any;
+}
+// Triangle::hit up to the barycentric test (tri.rs:24-39); pd = v0 e1 e2 n
+RT_DEV bool tri_t(V3 o, V3 d, const double *pd, double t_min, double t_max, double &t_out, double &b1_out, double &b2_out) {
+    V3 s = o - ld3(pd);
+    V3 e1 = ld3(pd + 3), e2 = ld3(pd + 6);
+    V3 s1 = cross(d, e2);
+    V3 s2 = cross(s, e1);
+    double s1_e1 = dot(s1, e1);
+    double t = dot(s2, e2) / s1_e1;
+    double b1 = dot(s1, s) / s1_e1;
+    double b2 = dot(s2, d) / s1_e1;
+    if (t < t_min || t > t_max) return false;
+    if (b1 < 0.0 || b2 < 0.0 || (1.0 - b1 - b2) < 0.0) return false;
+    t_out = t;
+    b1_out = b1;
+    b2_out = b2;
+    return true;
+}
+
+struct Best {
+    double t;
+    uint32_t prim;  // index into prims, kMediumFlag|index into media, or kNoPrim
+    uint32_t rank;
+    int face;
+};
+
+RT_DEV void test_prim(const DScene &sc, uint32_t pi, V3 o, V3 d, double time, double t_min, Best &best) {
+    const DPrim &p = sc.prims[pi];
+    double t;
+    int face = 0;
+    bool h = false;
+    switch (p.kind) {
+        case PRIM_SPHERE: h = sphere_root(o, d, ld3(p.d), p.d[3], t_min, best.t, t); break;
+        case PRIM_MSPHERE: h = sphere_root(o, d, msphere_center(p.d, time), p.d[8], t_min, best.t, t); break;
+        case PRIM_RECT: h = rect_t(o, d, p.axis, p.d[0], p.d[1], p.d[2], p.d[3], p.d[4], t_min, best.t, t); break;
+        case PRIM_TRI: {
+            double b1, b2;
+            h = tri_t(o, d, p.d, t_min, best.t, t, b1, b2);
+            break;
+        }
+        default: h = box_t(o, d, p.d, t_min, best.t, t, face); break;
+    }
+    // Every test accepts t == t_max, and lists / BVH nodes keep the later object on an
+    // exact tie (hit.rs:64-66, bvh.rs:81-84; §Q17): later = higher rank.
+    if (h && (t < best.t || best.prim == kNoPrim || p.rank > best.rank)) {
+        best.t = t;
+        best.prim = pi;
+        best.rank = p.rank;
+        best.face = face;
+    }
+}
+
+// Conservative slab test against [t_min, t_max] (culling only).
+RT_DEV bool slab(V3 o, V3 inv, const double *lo, const double *hi, double t_min, double t_max, double &t_entry) {
+    double tx0 = (lo[0] - o.x) * inv.x, tx1 = (hi[0] - o.x) * inv.x;
+    double ty0 = (lo[1] - o.y) * inv.y, ty1 = (hi[1] - o.y) * inv.y;
+    double tz0 = (lo[2] - o.z) * inv.z, tz1 = (hi[2] - o.z) * inv.z;
+    double tin = fmax(fmax(fmin(tx0, tx1), fmin(ty0, ty1)), fmax(fmin(tz0, tz1), t_min));
+    double tout = fmin(fmin(fmax(tx0, tx1), fmax(ty0, ty1)), fmin(fmax(tz0, tz1), t_max));
+    t_entry = tin;
+    return tin <= tout;
+}
+
+// Closest hit of one group given the ray already in the group's space.
+RT_DEV void trace_group(const DScene &sc, const DGroup &g, V3 o, V3 d, double time, double t_min, Best &best) {
+    if (g.bvh_root < 0) {
+        for (uint32_t i = 0; i < g.n_prims; ++i) test_prim(sc, g.first_prim + i, o, d, time, t_min, best);
+        return;
+    }
+    V3 inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+    int stack[kStackSize];
+    int sp = 0;
+    int node = g.bvh_root;
+    for (;;) {
+        if (node >= 0) {
+            const DBvhNode &n = sc.nodes[node];
+            double e0, e1;
+            bool h0 = slab(o, inv, n.lo0, n.hi0, t_min, best.t, e0);
+            bool h1 = slab(o, inv, n.lo1, n.hi1, t_min, best.t, e1);
+            if (h0 && h1) {
+                int near_c = n.child0, far_c = n.child1;
+                if (e1 < e0) {
+                    near_c = n.child1;
+                    far_c = n.child0;
+                }
+                if (sp < kStackSize) stack[sp++] = far_c;
+                node = near_c;
+                continue;
+            }
+            if (h0) {
+                node = n.child0;
+                continue;
+            }
+            if (h1) {
+                node = n.child1;
+                continue;
+            }
+        } else {
+            uint32_t code = ~(uint32_t)node;
+            uint32_t first = code >> 3, count = (code & 7u) + 1u;
+            for (uint32_t i = 0; i < count; ++i) test_prim(sc, first + i, o, d, time, t_min, best);
+        }
+        if (sp == 0) break;
+        node = stack[--sp];
+    }
+}
+
+// Closest hit over a sub-scene (a range of groups) for the ray given in the outermost space.
+RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &r, double t_min, Best &best) {
+    V3 inv = mk(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+    for (uint32_t gi = 0; gi < n_groups; ++gi) {
+        const DGroup &g = sc.groups[first_group + gi];
+        double e;
+        if (!slab(r.o, inv, g.bmin, g.bmax, t_min, best.t, e)) continue;
+        V3 o = r.o, d = r.d;
+        DChain c = sc.chains[g.chain];
+        chain_ray(sc, c.first_op, c.n_ops, o, d);
+        trace_group(sc, g, o, d, r.time, t_min, best);
+    }
+}
+
+// ConstantMedium::hit (medium.rs:27-61) for every medium of the world, after the
+// surfaces: with slot-addressed draws the outcome does not depend on list order.
+RT_DEV void trace_media(const DScene &sc, const Ray &r, const Rng &rng, double t_min, Best &best) {
+    for (uint32_t mi = 0; mi < sc.n_media; ++mi) {
+        const DMedium &m = sc.media[mi];
+        Best b1{DBL_MAX, kNoPrim, 0, 0};
+        trace_groups(sc, m.first_group, m.n_groups, r, -DBL_MAX, b1);  // boundary.hit(r, -MAX, MAX)
+        if (b1.prim == kNoPrim) continue;
+        Best b2{DBL_MAX, kNoPrim, 0, 0};
+        trace_groups(sc, m.first_group, m.n_groups, r, b1.t + 0.0001, b2);  // boundary.hit(r, hit1.t + 0.0001, MAX)
+        if (b2.prim == kNoPrim) continue;
+        double t1 = b1.t, t2 = b2.t;
+        if (t1 < t_min) t1 = t_min;
+        if (t2 > best.t) t2 = best.t;
+        if (t1 < t2) {
+            // r.direction().length() of the ray the medium sees (below its own wrappers)
+            V3 o = r.o, d = r.d;
+            DChain c = sc.chains[m.chain];
+            chain_ray(sc, c.first_op, c.n_ops, o, d);
+            double len = length(d);
+            double distance_inside_boundary = (t2 - t1) * len;
+            Draw dr = draw(rng, SLOT_MEDIUM, (uint32_t)m.node);
+            double hit_distance = -(1.0 / m.density) * log(dr.a);
+            if (hit_distance < distance_inside_boundary) {
+                best.t = t1 + hit_distance / len;
+                best.prim = kMediumFlag | mi;
+                best.rank = m.rank;
+                best.face = 0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// HitRecord (hit.rs:9-24) of the winning primitive
+// ---------------------------------------------------------------------------
+struct HitRec {
+    V3 p, normal;
+    double t, u, v;
+    bool front_face;
+    uint32_t material;
+    int32_t node, face;
+};
+
+RT_DEV void set_face_normal(HitRec &rec, V3 ray_dir, V3 outward_normal) {  // hit.rs:34-41
+    rec.front_face = dot(ray_dir, outward_normal) < 0.0;
+    rec.normal = rec.front_face ? outward_normal : (-1.0) * outward_normal;
+}
+RT_DEV void get_sphere_uv(V3 p, double &u, double &v) {  // sphere.rs:11-25
+    double phi = atan2(-p.z, p.x) + kPi;
+    double theta = acos(-p.y);
+    u = phi / (2.0 * kPi);
+    v = theta / kPi;
+}
+
+// Wrapper post-processing, innermost first (translate.rs:26, rotate.rs:88-104, hit.rs:116)
+RT_DEV void chain_post(const DScene &sc, uint32_t chain, const Ray &world, HitRec &rec) {
+    DChain c = sc.chains[chain];
+    for (uint32_t i = c.n_ops; i-- > 0;) {
+        const DOp &op = sc.ops[c.first_op + i];
+        if (op.kind == OP_FLIP) {
+            rec.front_face = !rec.front_face;
+        } else if (op.kind == OP_TRANSLATE) {
+            rec.p = rec.p + ld3(op.offset);
+        } else {
+            rec.p = rot_back(op, rec.p);
+            V3 n = rot_back(op, rec.normal);
+            // §Q3: face orientation is recomputed with the ray of THIS Rotate's object space
+            V3 o = world.o, d = world.d;
+            chain_ray(sc, c.first_op, i + 1, o, d);
+            set_face_normal(rec, d, n);
+        }
+    }
+}
+
+template <bool WANT_UV>
+RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, HitRec &rec) {
+    rec.t = best.t;
+    rec.u = 0.0;
+    rec.v = 0.0;
+    if (best.prim & kMediumFlag) {  // medium.rs:46-56
+        const DMedium &m = sc.media[best.prim & ~kMediumFlag];
+        V3 o = world.o, d = world.d;
+        DChain c = sc.chains[m.chain];
+        chain_ray(sc, c.first_op, c.n_ops, o, d);
+        rec.p = o + best.t * d;
+        rec.front_face = false;
+        rec.normal = mk(1.0, 0.0, 0.0);
+        rec.material = m.material;
+        rec.node = m.node;
+        rec.face = 0;
+        chain_post(sc, m.chain, world, rec);
+        return;
+    }
+    const DPrim &p = sc.prims[best.prim];
+    V3 o = world.o, d = world.d;
+    DChain c = sc.chains[p.chain];
+    chain_ray(sc, c.first_op, c.n_ops, o, d);
+    rec.p = o + best.t * d;  // r.at(t) in the primitive's own space
+    rec.material = p.material;
+    rec.node = p.node;
+    rec.face = best.face;
+    bool want_uv = WANT_UV || sc.materials[p.material].needs_uv;
+    switch (p.kind) {
+        case PRIM_SPHERE:
+        case PRIM_MSPHERE: {  // sphere.rs:75-94
+            V3 center = p.kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
+            double radius = p.kind == PRIM_SPHERE ? p.d[3] : p.d[8];
+            V3 outward_normal = (rec.p - center) / radius;
+            set_face_normal(rec, d, outward_normal);
+            if (want_uv) get_sphere_uv(outward_normal, rec.u, rec.v);
+            break;
+        }
+        case PRIM_RECT:
+        case PRIM_BOX: {  // rect.rs:59-78
+            uint32_t plane = p.axis;
+            double a0 = p.d[0], a1 = p.d[1], b0 = p.d[2], b1 = p.d[3], k = p.d[4];
+            if (p.kind == PRIM_BOX) box_face(p.d, best.face, plane, a0, a1, b0, b1, k);
+            int ki, ai, bi;
+            rect_axes(plane, ki, ai, bi);
+            if (want_uv) {
+                double a = comp(o, ai) + best.t * comp(d, ai);
+                double b = comp(o, bi) + best.t * comp(d, bi);
+                rec.u = (a - a0) / (a1 - a0);
+                rec.v = (b - b0) / (b1 - b0);
+            }
+            V3 normal = mk(0.0, 0.0, 0.0);
+            set_comp(normal, ki, 1.0);
+            set_face_normal(rec, d, normal);
+            break;
+        }
+        default: {  // tri.rs:40-54
+            if (want_uv) {
+                double t, b1, b2;
+                tri_t(o, d, p.d, -DBL_MAX, DBL_MAX, t, b1, b2);
+                rec.u = b1;
+                rec.v = b2;
+            }
+            set_face_normal(rec, d, ld3(p.d + 9));
+            break;
+        }
+    }
+    chain_post(sc, p.chain, world, rec);
+}
+
+// world.hit(ray, 0.00001, inf) (main.rs:48)
+template <bool WITH_MEDIA>
+RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, Best &best) {
+    best.t = DBL_MAX;  // stands for +inf: every accepted t is finite or the reference's own inf corner
+    best.prim = kNoPrim;
+    best.rank = 0;
+    best.face = 0;
+    best.t = __longlong_as_double(0x7FF0000000000000ll);  // f64::INFINITY
+    trace_groups(sc, 0, sc.n_world_groups, r, kTMin, best);
+    if (WITH_MEDIA && sc.n_media) trace_media(sc, r, rng, kTMin, best);
+    return best.prim != kNoPrim;
+}
+
+// ---------------------------------------------------------------------------
+// Textures (texture.rs, perlin.rs)
+// ---------------------------------------------------------------------------
+RT_DEV unsigned long long as_usize(double x) {  // Rust `as usize`: saturating, NaN -> 0
+    if (!(x == x) || x <= 0.0) return 0ull;
+    if (x >= 18446744073709551615.0) return 0xFFFFFFFFFFFFFFFFull;
+    return (unsigned long long)x;
+}
+RT_DEV double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+RT_DEV double perlin_noise(const DPerlin &t, V3 p, double scale) {  // perlin.rs:77-109 + :39-56 (§Q15)
+    double fx = floor(scale * p.x), fy = floor(scale * p.y), fz = floor(scale * p.z);
+    double u = scale * p.x - fx, v = scale * p.y - fy, w = scale * p.z - fz;
+    u = u * u * (3.0 - 2.0 * u);
+    v = v * v * (3.0 - 2.0 * v);
+    w = w * w * (3.0 - 2.0 * w);
+    unsigned long long i = as_usize(fx), j = as_usize(fy), k = as_usize(fz);
+    double uu = u * u * (3.0 - 2.0 * u);
+    double vv = v * v * (3.0 - 2.0 * v);
+    double ww = w * w * (3.0 - 2.0 * w);
+    double accum = 0.0;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                uint32_t idx = (t.perm_x[(i + di) & 255] ^ t.perm_y[(j + dj) & 255] ^ t.perm_z[(k + dk) & 255]) & 255u;
+                V3 c = ld3(t.ranvec + 3 * idx);
+                V3 weight = mk(u - (double)di, v - (double)dj, w - (double)dk);
+                accum += ((double)di * uu + (double)(1 - di) * (1.0 - uu)) * ((double)dj * vv + (double)(1 - dj) * (1.0 - vv)) *
+                         ((double)dk * ww + (double)(1 - dk) * (1.0 - ww)) * dot(c, weight);
+            }
+    return accum;
+}
+RT_DEV double perlin_turb(const DPerlin &t, V3 p, double scale, int depth) {  // perlin.rs:111-121
+    double accum = 0.0;
+    V3 temp_p = p;
+    double weight = 1.0;
+    for (int i = 0; i < depth; ++i) {
+        accum += weight * perlin_noise(t, temp_p, scale);
+        weight *= 0.5;
+        temp_p = temp_p * 2.0;
+    }
+    return fabs(accum);
+}
+RT_DEV V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
+    for (int guard = 0; guard < 16; ++guard) {
+        const DTexture &t = sc.textures[id];
+        if (t.kind == RT_TEX_CHECKER) {  // texture.rs:45-54
+            double sines = sin(10.0 * p.x) * sin(10.0 * p.y) * sin(10.0 * p.z);
+            id = sines < 0.0 ? t.a : t.b;
+            continue;
+        }
+        if (t.kind == RT_TEX_CONSTANT) return ld3(t.color);  // texture.rs:23-27
+        if (t.kind == RT_TEX_NOISE) {                         // texture.rs:71-79
+            double s = 1.0 + sin(t.scale * p.z + 10.0 * perlin_turb(sc.perlin[t.a], p, t.scale, 7));
+            return (mk(1.0, 1.0, 1.0) * 0.5) * s;
+        }
+        // texture.rs:99-121
+        DImage im = sc.images[t.a];
+        unsigned long long width = im.width, height = im.height;
+        unsigned long long i = as_usize(clampd(u, 0.0, 1.0) * (double)width);
+        unsigned long long j = as_usize(clampd(1.0 - v, 0.0, 1.0) * (double)height);
+        if (i > width - 1) i = width - 1;
+        if (j > height - 1) j = height - 1;
+        const uint8_t *px = sc.texels + im.offset + 3 * i + 3 * width * j;
+        return mk((double)px[0] / 255.0, (double)px[1] / 255.0, (double)px[2] / 255.0);
+    }
+    return mk(0.0, 0.0, 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// Lights: PDF::Hittable over the light list (pdf.rs:140-142,164-166; hit.rs:90-96)
+// ---------------------------------------------------------------------------
+RT_DEV double light_pdf_one(const DLight &l, V3 o, V3 v) {
+    if (l.kind == LIGHT_RECT) {  // rect.rs:91-101
+        double t;
+        if (!rect_t(o, v, l.axis, l.d[0], l.d[1], l.d[2], l.d[3], l.d[4], 0.001, __longlong_as_double(0x7FF0000000000000ll), t))
+            return 0.0;
+        int ki, ai, bi;
+        rect_axes(l.axis, ki, ai, bi);
+        double area = (l.d[1] - l.d[0]) * (l.d[3] - l.d[2]);
+        double distance_squared = powi2(t) * powi2(length(v));
+        // rec.normal is +-axis_k after set_face_normal: |v . normal| = |v_k|
+        double vk = comp(v, ki);
+        double nk = (vk * 1.0 < 0.0) ? 1.0 : -1.0;  // front_face ? outward : -outward, outward = +axis
+        double cosine = fabs(vk * nk) / length(v);
+        return cosine != 0.0 ? distance_squared / (cosine * area) : 0.0;
+    }
+    if (l.kind == LIGHT_SPHERE) {  // sphere.rs:104-112
+        double root;
+        V3 center = ld3(l.d);
+        if (!sphere_root(o, v, center, l.d[3], 0.001, DBL_MAX, root)) return 0.0;
+        double cos_theta_max = sqrt(1.0 - powi2(l.d[3]) / powi2(length(center - o)));
+        double solid_angle = 2.0 * kPi * (1.0 - cos_theta_max);
+        return 1.0 / solid_angle;
+    }
+    return 0.0;  // hit.rs:29
+}
+RT_DEV double lights_pdf_value(const DScene &sc, V3 o, V3 v) {  // hit.rs:90-92
+    double sum = 0.0;
+    for (uint32_t i = 0; i < sc.n_lights; ++i) sum += light_pdf_one(sc.lights[i], o, v);
+    return sum / (double)sc.n_lights;
+}
+RT_DEV V3 lights_random(const DScene &sc, V3 o, const Draw &dr) {  // hit.rs:94-96
+    uint32_t idx = (dr.bits_b * sc.n_lights) >> 11;
+    const DLight &l = sc.lights[idx];
+    if (l.kind == LIGHT_RECT) {  // rect.rs:103-111
+        int ki, ai, bi;
+        rect_axes(l.axis, ki, ai, bi);
+        V3 random_point = mk(0.0, 0.0, 0.0);
+        set_comp(random_point, ai, gen_range(l.d[0], l.d[1], dr.a));
+        set_comp(random_point, bi, gen_range(l.d[2], l.d[3], dr.b));
+        set_comp(random_point, ki, l.d[4]);
+        return random_point - o;
+    }
+    if (l.kind == LIGHT_SPHERE) {  // sphere.rs:114-119 + :27-36
+        V3 direction = ld3(l.d) - o;
+        double distance_squared = powi2(length(direction));
+        ONB uvw = onb_from_w(direction);
+        double r1 = dr.a, r2 = dr.b, radius = l.d[3];
+        double z = 1.0 + r2 * (sqrt(1.0 - powi2(radius) / distance_squared) - 1.0);
+        double phi = 2.0 * kPi * r1;
+        double x = cos(phi) * sqrt(1.0 - powi2(z));
+        double y = sin(phi) * sqrt(1.0 - powi2(z));
+        return onb_local(uvw, mk(x, y, z));
+    }
+    return mk(1.0, 0.0, 0.0);  // hit.rs:30
+}
+
+// ---------------------------------------------------------------------------
+// Materials (mat.rs:199-422) and the integrator (main.rs:41-120), iteratively
+// ---------------------------------------------------------------------------
+RT_DEV double reflectance(double cosine, double index_of_refraction) {  // mat.rs:303-307
+    double r0 = powi2((1.0 - index_of_refraction) / (1.0 + index_of_refraction));
+    return r0 + (1.0 - r0) * powi5(1.0 - cosine);
+}
+RT_DEV V3 dielectric_direction(const DMaterial &m, V3 r_in_dir, const HitRec &rec, const Rng &rng) {  // mat.rs:343-366
+    double refraction_ratio = rec.front_face ? 1.0 / m.ir : m.ir;
+    V3 unit_direction = normalized(r_in_dir);
+    double cos_theta = fmin(dot((-1.0) * unit_direction, rec.normal), 1.0);
+    double sin_theta = sqrt(1.0 - powi2(cos_theta));
+    bool cannot_refract = refraction_ratio * sin_theta > 1.0;
+    Draw d = draw(rng, SLOT_SCATTER, 0);
+    bool will_reflect = d.a < reflectance(cos_theta, refraction_ratio);
+    if (cannot_refract || will_reflect) return reflect(unit_direction, rec.normal);
+    return refract(unit_direction, rec.normal, refraction_ratio);
+}
+RT_DEV V3 random_cosine_direction(double r1, double r2) {  // pdf.rs:8-18
+    double z = sqrt(1.0 - r2);
+    double phi = 2.0 * kPi * r1;
+    double s, c;
+    sincos(phi, &s, &c);
+    double x = c * sqrt(r2);
+    double y = s * sqrt(r2);
+    return mk(x, y, z);
+}
+
+struct PathState {
+    Ray ray;
+    V3 beta;      // product of the factors the recursion multiplies on the way back up
+    V3 radiance;  // what ray_color returns for the camera ray, accumulated front to back
+    Rng rng;
+    uint32_t depth_left;
+    uint32_t segments;
+};
+
+// One call of ray_color (one segment).  Returns false when the path ended.
+//   recursion:  L = emitted + f * L_next      iteration:  radiance += beta*emitted ; beta *= f
+RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint32_t flags) {
+    if (ps.depth_left == 0) return false;  // main.rs:42-45: contributes black
+    Best best;
+    ps.segments += 1;
+    if (!world_hit<true>(sc, ps.ray, ps.rng, best)) {  // main.rs:48,118
+        ps.radiance = ps.radiance + ps.beta * ld3(sc.background);
+        return false;
+    }
+    HitRec rec;
+    resolve_hit<false>(sc, ps.ray, best, rec);
+    const DMaterial &m = sc.materials[rec.material];
+    // Material::emitted (mat.rs:70-72, :395-401)
+    if (m.kind == RT_MAT_DIFFUSE_LIGHT) {
+        // DiffuseLight never scatters (mat.rs:391-393 / default scatter_mc_method): return emitted
+        if (rec.front_face) ps.radiance = ps.radiance + ps.beta * texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+        return false;
+    }
+    V3 new_dir;
+    V3 factor;
+    if (m.kind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
+        V3 reflected = normalized(reflect(ps.ray.d, rec.normal));
+        // random_in_unit_sphere is drawn even for fuzz == 0 (§Q12); with slot addressing the
+        // draw can be skipped when its product with fuzz is exactly zero.
+        new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * random_in_unit_sphere(ps.rng) : reflected;
+        if (!(dot(new_dir, rec.normal) > 0.0)) return false;  // None -> emitted (black)
+        factor = ld3(m.albedo);
+    } else if (m.kind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
+        new_dir = dielectric_direction(m, ps.ray.d, rec, ps.rng);
+        factor = mk(1.0, 1.0, 1.0);
+    } else if (integrator == RT_INTEGRATOR_LEGACY) {
+        if (m.kind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
+            new_dir = rec.normal + normalized(random_in_unit_sphere(ps.rng));
+            if (near_zero(new_dir)) new_dir = rec.normal;
+        } else {  // Isotropic, mat.rs:418-421
+            new_dir = random_in_unit_sphere(ps.rng);
+        }
+        factor = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+    } else {
+        if (m.kind != RT_MAT_LAMBERTIAN) return false;  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
+        // main.rs:92-98
+        V3 attenuation = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+        ONB uvw = onb_from_w(rec.normal);  // PDF::cosine_pdf (pdf.rs:83-87)
+        Draw d = draw(ps.rng, SLOT_SCATTER, 0);
+        if (d.bits_a & 1u)  // pdf.rs:169
+            new_dir = lights_random(sc, rec.p, d);
+        else
+            new_dir = onb_local(uvw, random_cosine_direction(d.a, d.b));
+        double light_pdf = lights_pdf_value(sc, rec.p, new_dir);
+        V3 unit = normalized(new_dir);
+        double cosine = dot(unit, uvw.w);  // pdf.rs:131-139
+        double cosine_pdf = cosine > 0.0 ? cosine / kPi : 0.0;
+        double pdf_value = 0.5 * light_pdf + 0.5 * cosine_pdf;        // pdf.rs:143-145
+        double spdf = fmax(dot(rec.normal, unit), 0.0) / kPi;          // mat.rs:246-249
+        factor = (attenuation * spdf) / pdf_value;                     // main.rs:97
+    }
+    ps.beta = ps.beta * factor;
+    ps.ray.o = rec.p;
+    ps.ray.d = new_dir;  // time is inherited (main.rs:95, mat.rs:219,270,368)
+    ps.depth_left -= 1;
+    ps.rng.bounce += 1;
+    if (!(flags & RT_FLAG_TRACE_ZERO_THROUGHPUT) && ps.beta.x == 0.0 && ps.beta.y == 0.0 && ps.beta.z == 0.0)
+        return false;  // §Q11: the reference keeps tracing; the contribution is zero either way
+    return ps.depth_left != 0;
+}
+
+// The sample closure of main.rs:811-829: pixel jitter + Camera::get_ray (camera.rs:51-59)
+RT_DEV Ray camera_ray(const RtCamera &c, uint32_t width, uint32_t height, uint32_t i, uint32_t j, Rng rng) {
+    rng.bounce = 0;
+    Draw dj = draw(rng, SLOT_PIXEL, 0);
+    double u = ((double)i + dj.a) / (double)(width - 1);
+    double v = ((double)j + dj.b) / (double)(height - 1);
+    V3 origin = ld3(c.origin), llc = ld3(c.lower_left_corner);
+    V3 horizontal = ld3(c.horizontal), vertical = ld3(c.vertical);
+    V3 rd = c.lens_radius * random_in_unit_disk(rng);
+    V3 offset = ld3(c.cu) * rd.x + ld3(c.cv) * rd.y;
+    Draw dt = draw(rng, SLOT_TIME, 0);
+    Ray r;
+    r.time = c.time0 + dt.a * (c.time1 - c.time0);
+    r.o = origin + offset;
+    r.d = llc + u * horizontal + v * vertical - (origin + offset);
+    return r;
+}
+
+RT_DEV void path_begin(PathState &ps, const RtCamera &cam, uint32_t width, uint32_t height, uint32_t i, uint32_t j,
+                       uint32_t sample, uint32_t seed, uint32_t max_depth) {
+    ps.rng = Rng{seed, j * width + i, sample, 0};
+    ps.ray = camera_ray(cam, width, height, i, j, ps.rng);
+    ps.beta = mk(1.0, 1.0, 1.0);
+    ps.radiance = mk(0.0, 0.0, 0.0);
+    ps.depth_left = max_depth;
+    ps.segments = 0;
+}
+
+}  // namespace rtb200dev
