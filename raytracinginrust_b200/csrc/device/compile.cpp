@@ -347,6 +347,140 @@ bool same_ops(const std::vector<DOp> &a, const std::vector<DOp> &b) {
     return true;
 }
 
+
+// ---------------------------------------------------------------------------
+// The reference's own traversal order.  On an exact-t tie the reference keeps the
+// object it visits LAST (hit.rs:64-66, bvh.rs:81-84), and coincident
+// faces (the touching ground boxes of final_scene) make such ties common for rays
+// inside a box.  Ranks must therefore follow the reference's BVH leaf order, which
+// depends on its build: bounding_box() of every child (with the reference's quirks),
+// widest axis, sort by min+max, split in halves (bvh.rs:18-73).
+// ---------------------------------------------------------------------------
+struct RefBox {
+    double lo[3], hi[3];
+};
+bool ref_bbox(const RtSceneDesc &d, uint32_t id, double t0, double t1, RefBox &out, uint32_t depth) {
+    if (id >= d.n_nodes || depth > d.n_nodes + 1) return false;
+    const RtNode &n = d.nodes[id];
+    switch (n.kind) {
+        case RT_NODE_SPHERE:  // sphere.rs:97-102
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] = n.v[a] - n.v[3];
+                out.hi[a] = n.v[a] + n.v[3];
+            }
+            return true;
+        case RT_NODE_MOVING_SPHERE:  // sphere.rs:191-201
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] = std::fmin(n.v[a] - n.v[8], n.v[3 + a] - n.v[8]);
+                out.hi[a] = std::fmax(n.v[a] + n.v[8], n.v[3 + a] + n.v[8]);
+            }
+            return true;
+        case RT_NODE_RECT:  // rect.rs:83-89 (§Q5: always (a0,b0,k-1e-4)..(a1,b1,k+1e-4))
+            out.lo[0] = n.v[0]; out.lo[1] = n.v[2]; out.lo[2] = n.v[4] - 0.0001;
+            out.hi[0] = n.v[1]; out.hi[1] = n.v[3]; out.hi[2] = n.v[4] + 0.0001;
+            return true;
+        case RT_NODE_TRIANGLE:  // tri.rs:59-70
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] = std::fmin(n.v[a], std::fmin(n.v[3 + a], n.v[6 + a]));
+                out.hi[a] = std::fmax(n.v[a], std::fmax(n.v[3 + a], n.v[6 + a]));
+            }
+            return true;
+        case RT_NODE_CUBE:  // cube.rs:39-46
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] = n.v[a];
+                out.hi[a] = n.v[3 + a];
+            }
+            return true;
+        case RT_NODE_LIST:   // hit.rs:73-88
+        case RT_NODE_BVH: {  // bvh.rs:93-95: surrounding boxes all the way up = the union
+            if (n.count == 0 || (uint64_t)n.child + n.count > d.n_child_index) return false;
+            for (uint32_t i = 0; i < n.count; ++i) {
+                RefBox b;
+                if (!ref_bbox(d, d.child_index[n.child + i], t0, t1, b, depth + 1)) return false;
+                if (i == 0) out = b;
+                else
+                    for (int a = 0; a < 3; ++a) {
+                        out.lo[a] = std::fmin(out.lo[a], b.lo[a]);
+                        out.hi[a] = std::fmax(out.hi[a], b.hi[a]);
+                    }
+            }
+            return true;
+        }
+        case RT_NODE_TRANSLATE:  // translate.rs:32-40
+            if (!ref_bbox(d, n.child, t0, t1, out, depth + 1)) return false;
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] += n.v[a];
+                out.hi[a] += n.v[a];
+            }
+            return true;
+        case RT_NODE_ROTATE: {  // rotate.rs:40-57 (§Q4): the box comes out as [f64::MIN, f64::MAX]^3
+            RefBox b;
+            if (!ref_bbox(d, n.child, 0.0, 1.0, b, depth + 1)) return false;
+            for (int a = 0; a < 3; ++a) {
+                out.lo[a] = -DBL_MAX;
+                out.hi[a] = DBL_MAX;
+            }
+            return true;
+        }
+        case RT_NODE_FLIP:    // hit.rs:122-124
+        case RT_NODE_MEDIUM:  // medium.rs:63-65
+            return ref_bbox(d, n.child, t0, t1, out, depth + 1);
+        default:
+            return false;
+    }
+}
+
+// Leaf order of BVH::new(hit, t0, t1): left subtree first, then right (bvh.rs:64-70,79-84).
+bool ref_bvh_order(const RtSceneDesc &d, std::vector<uint32_t> hit, double t0, double t1, std::vector<uint32_t> &out,
+                   std::string &err) {
+    if (hit.empty()) {
+        err = "no object in the scene";  // bvh.rs:55
+        return false;
+    }
+    std::vector<RefBox> boxes(hit.size());
+    for (size_t i = 0; i < hit.size(); ++i)
+        if (!ref_bbox(d, hit[i], t0, t1, boxes[i], 0)) {
+            err = "no bounding box in bvh node";  // bvh.rs:28,61
+            return false;
+        }
+    if (hit.size() == 1) {
+        out.push_back(hit[0]);
+        return true;
+    }
+    int axis = 0;
+    double range[3];
+    for (int a = 0; a < 3; ++a) {  // bvh.rs:33-48
+        double bmin = DBL_MAX, bmax = -DBL_MAX;
+        for (const RefBox &b : boxes) {
+            bmin = std::fmin(bmin, b.lo[a]);
+            bmax = std::fmax(bmax, b.hi[a]);
+        }
+        range[a] = bmax - bmin;
+        if (range[a] != range[a]) {
+            err = "NaN extent in BVH build";  // partial_cmp().unwrap(), bvh.rs:47
+            return false;
+        }
+    }
+    if (range[1] > range[axis]) axis = 1;
+    if (range[2] > range[axis]) axis = 2;
+    std::vector<uint32_t> idx(hit.size());
+    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
+    for (const RefBox &b : boxes)
+        if (b.lo[axis] + b.hi[axis] != b.lo[axis] + b.hi[axis]) {
+            err = "NaN centroid in BVH build";  // partial_cmp().unwrap(), bvh.rs:26
+            return false;
+        }
+    // bvh.rs:51 sort_unstable_by: the order of equal keys is unspecified in the reference;
+    // a stable sort fixes it (same choice as the oracle)
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+        return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis];
+    });
+    size_t half = hit.size() / 2;
+    std::vector<uint32_t> left, right;
+    for (size_t i = 0; i < idx.size(); ++i) (i < half ? left : right).push_back(hit[idx[i]]);
+    return ref_bvh_order(d, std::move(left), t0, t1, out, err) && ref_bvh_order(d, std::move(right), t0, t1, out, err);
+}
+
 struct Walker {
     const RtSceneDesc &d;
     CompiledScene &out;
@@ -456,9 +590,19 @@ struct Walker {
             case RT_NODE_LIST:
             case RT_NODE_BVH: {
                 if ((uint64_t)n.child + n.count > d.n_child_index) return fail(RT_ERR_BAD_ARGUMENT, "child range out of bounds");
-                if (n.kind == RT_NODE_BVH && n.count == 0) return fail(RT_ERR_EMPTY_SCENE, "no object in the scene");  // bvh.rs:55
-                for (uint32_t i = 0; i < n.count; ++i)
-                    if (!walk(d.child_index[n.child + i], depth + 1)) return false;
+                if (n.kind == RT_NODE_BVH) {
+                    // visit the children in the reference BVH's leaf order so that ranks follow
+                    // the reference's traversal order (tie-break, §Q17)
+                    std::vector<uint32_t> kids(d.child_index + n.child, d.child_index + n.child + n.count), order;
+                    std::string e;
+                    if (!ref_bvh_order(d, kids, n.v[0], n.v[1], order, e))
+                        return fail(n.count == 0 ? RT_ERR_EMPTY_SCENE : RT_ERR_BAD_ARGUMENT, e);
+                    for (uint32_t id2 : order)
+                        if (!walk(id2, depth + 1)) return false;
+                } else {
+                    for (uint32_t i = 0; i < n.count; ++i)
+                        if (!walk(d.child_index[n.child + i], depth + 1)) return false;
+                }
                 break;
             }
             case RT_NODE_TRANSLATE: {
