@@ -279,6 +279,11 @@ RtStatus rt_camera_rays(const RtScene *scene, const RtCamera *camera, uint32_t w
                         uint32_t height, const RtRenderOpts *opts, const uint32_t *px,
                         const uint32_t *py, const uint32_t *sample, uint64_t n, RtRay *rays);
 
+/* Diagnostic: measured FP64 FMA throughput of `device` in TFLOP/s (a dependent-chain DFMA
+ * micro-kernel, best of 5).  bench.py uses it as the denominator of the FP64-issue roofline,
+ * the bound that actually applies to this path (DESIGN.md "Rooflines"). */
+RtStatus rt_measure_fp64_peak(int device, double *tflops_out);
+
 /* Thread-local description of the last error returned on this thread. */
 const char *rt_last_error(void);
 

@@ -64,6 +64,7 @@ _dev.rt_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C
                                   C.c_void_p]
 _dev.rt_camera_rays.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+_dev.rt_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
 _dev.rt_last_error.restype = C.c_char_p
 _dev.rt_version.restype = C.c_char_p
 
@@ -100,6 +101,13 @@ def _check_host(status):
 
 def device_count():
     return int(_dev.rt_device_count())
+
+
+def measure_fp64_peak(device=0):
+    """Measured FP64 FMA throughput in TFLOP/s (the roofline denominator for this path)."""
+    v = C.c_double()
+    _check(_dev.rt_measure_fp64_peak(device, C.byref(v)))
+    return float(v.value)
 
 
 def version():

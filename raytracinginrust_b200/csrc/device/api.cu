@@ -191,6 +191,16 @@ int rt_device_count(void) {
     return n;
 }
 
+RtStatus rt_measure_fp64_peak(int device, double *tflops_out) {
+    if (!tflops_out) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    int n = rt_device_count();
+    if (n == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    CU(measure_fp64_peak(device, tflops_out));
+    return RT_OK;
+}
+
 RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
     if (!desc || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     *out_scene = nullptr;
