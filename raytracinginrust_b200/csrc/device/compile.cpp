@@ -687,8 +687,18 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
             dg.bmin[a] = wb.lo[a];
             dg.bmax[a] = wb.hi[a];
         }
-        dg.bvh_root = -1;
-        if (dg.n_prims > LINEAR_MAX) dg.bvh_root = build_group_bvh(out, dg.first_prim, dg.n_prims);
+        bool has_bvh = dg.n_prims > LINEAR_MAX;
+        if (has_bvh) {
+            dg.bvh_root = build_group_bvh(out, dg.first_prim, dg.n_prims);
+        } else {
+            // a small group is one leaf: same encoding as a BVH leaf (LINEAR_MAX <= 8)
+            dg.bvh_root = (int32_t) ~((dg.first_prim << 3) | (dg.n_prims - 1));
+        }
+        // one or two primitives are cheaper to test than to cull; a BVH culls with its own root boxes
+        if (dg.n_prims > 2 && !has_bvh) dg.flags |= GROUP_CULL;
+        if (has_bvh && !g.xform.empty()) dg.flags |= GROUP_CULL;
+        for (const DOp &op : g.xform)
+            if (op.kind == OP_ROTATE) dg.flags |= GROUP_ROTATED;
         out.groups.push_back(dg);
     }
     return true;

@@ -100,9 +100,9 @@ __global__ void first_hit_kernel(const __grid_constant__ DScene sc, const RtRay 
     r.d = ld3(rays[k].direction);
     r.time = rays[k].time;
     Rng rng{0, 0, 0, 0};
-    Best best;
+    HitRec rec;
     RtHit h;
-    if (!world_hit<false>(sc, r, rng, best)) {
+    if (!world_hit<false, true>(sc, r, rng, rec)) {
         h.node = -1;
         h.face = 0;
         h.material = -1;
@@ -111,8 +111,6 @@ __global__ void first_hit_kernel(const __grid_constant__ DScene sc, const RtRay 
         h.u = h.v = 0.0;
         for (int a = 0; a < 3; ++a) h.position[a] = h.normal[a] = 0.0;
     } else {
-        HitRec rec;
-        resolve_hit<true>(sc, r, best, rec);
         h.node = rec.node;
         h.face = rec.face;
         h.material = (int32_t)rec.material;

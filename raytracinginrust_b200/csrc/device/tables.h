@@ -48,11 +48,18 @@ struct DChain {
     uint32_t first_op, n_ops;
 };
 
+enum GroupFlags : uint32_t {
+    GROUP_CULL = 1,     // test the group's outer-space bounds before transforming the ray
+    GROUP_ROTATED = 2,  // the chain rotates: the reciprocal direction must be recomputed
+};
+
 struct alignas(16) DGroup {
     uint32_t chain;       // ray transform of this group (flips are skipped when transforming)
     uint32_t first_prim;  // into prims
     uint32_t n_prims;
     int32_t bvh_root;     // node index, or -1: scan the primitives linearly
+    uint32_t flags;       // GroupFlags
+    uint32_t pad0, pad1, pad2;
     double bmin[3], bmax[3];  // conservative bounds in the space the ray is given in (culling only)
 };
 

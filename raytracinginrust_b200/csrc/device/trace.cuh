@@ -1,9 +1,21 @@
 // trace.cuh — device code of the path-tracing hot path (sm_100a, f64).
 //
-// Everything the reference's ray_color (src/main.rs:41-120) calls, as inlined
-// device functions over the flat tables of tables.h.  Arithmetic is f64 with the
-// reference's operation order; every value-producing expression cites the
-// reference line it restates.  Only culling (group bounds, BVH boxes) is new.
+// Everything the reference's ray_color (src/main.rs:41-120) calls, as inlined device
+// functions over the flat tables of tables.h.
+//
+// Two kinds of arithmetic live here, and they are kept apart on purpose:
+//
+//  * SEARCH (s_* functions, slab tests, BVH traversal): finds WHICH primitive a ray hits
+//    first.  Plain f64 with reciprocal multiplies, positive-logic accepts and a slab test
+//    for cubes.  It only has to order candidates; like the BVH boxes it never produces a
+//    number that reaches the image.
+//  * RESOLVE / SHADE (exact_t, resolve_hit, materials, pdfs, camera): every value that
+//    reaches the image — t, hit point, normal, uv, directions, pdfs, throughput — is
+//    computed with the reference's own expressions in the reference's operation order
+//    (true IEEE divisions included), each citing the line it restates.
+//
+// A different winner can only come out of SEARCH when two candidates lie within a couple
+// of ulps of each other or of an interval end (DESIGN.md "Precision policy").
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -14,12 +26,14 @@
 namespace rtb200dev {
 
 #define RT_DEV __device__ __forceinline__
+#define RT_DEV_COLD __device__ __noinline__
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
 constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
 constexpr uint32_t kMediumFlag = 0x80000000u;
 constexpr int kStackSize = 64;
+#define RT_INF (__longlong_as_double(0x7FF0000000000000ll))
 
 // ---------------------------------------------------------------------------
 // Vec3 (src/vec.rs)
@@ -33,24 +47,31 @@ RT_DEV V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
 RT_DEV V3 operator*(V3 a, double s) { return mk(a.x * s, a.y * s, a.z * s); }
 RT_DEV V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
 RT_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
-RT_DEV V3 operator/(V3 a, double s) { return mk(a.x / s, a.y / s, a.z / s); }
+// IEEE a/b.  nvcc's inline division sequence leaves its fast path for a zero numerator and
+// calls a ~70-instruction subroutine; 0/b is +-0 = 0*b for finite non-zero b, so take it directly.
+RT_DEV double ddiv(double a, double b) {
+    if (a == 0.0) {
+        double z = a * b;
+        if (z == 0.0 && b != 0.0) return z;
+    }
+    return a / b;
+}
+RT_DEV V3 operator/(V3 a, double s) { return mk(ddiv(a.x, s), ddiv(a.y, s), ddiv(a.z, s)); }
 RT_DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // vec.rs:38-40
 RT_DEV double length(V3 a) { return sqrt(dot(a, a)); }                        // vec.rs:42-44
 RT_DEV V3 cross(V3 a, V3 b) {                                                 // vec.rs:46-54
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
-RT_DEV V3 normalized(V3 a) { return a / length(a); }  // vec.rs:56-58
+RT_DEV V3 normalized(V3 a) {  // vec.rs:56-58: self / self.length(); x/1.0 == x exactly
+    double l = length(a);
+    if (l == 1.0) return a;
+    return a / l;
+}
 RT_DEV double powi2(double x) { return x * x; }
 RT_DEV double powi5(double x) {
     double x2 = x * x;
     double x4 = x2 * x2;
     return x4 * x;
-}
-RT_DEV double comp(V3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
-RT_DEV void set_comp(V3 &v, int i, double s) {
-    if (i == 0) v.x = s;
-    else if (i == 1) v.y = s;
-    else v.z = s;
 }
 RT_DEV V3 ld3(const double *p) { return mk(p[0], p[1], p[2]); }
 RT_DEV bool near_zero(V3 a) {  // vec.rs:107-110
@@ -63,6 +84,17 @@ RT_DEV V3 refract(V3 v, V3 n, double etai_over_etat) {                  // vec.r
     V3 r_out_perp = etai_over_etat * (v + cos_theta * n);
     V3 r_out_para = ((-1.0) * sqrt(fabs(1.0 - powi2(length(r_out_perp))))) * n;
     return r_out_perp + r_out_para;
+}
+// SEARCH-grade reciprocal: MUFU.RCP64H + two Newton steps (full precision; 1/+-0 = +-inf so that
+// axis-parallel rays order correctly in the slab tests; infinities and NaN only ever reject).
+RT_DEV double rcp_fast(double x) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double r = fma(r0, e, r0);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return x == 0.0 ? r0 : r;  // 1/+-0 = +-inf (the Newton step would turn it into NaN)
 }
 
 // ---------------------------------------------------------------------------
@@ -132,7 +164,6 @@ struct Ray {
     V3 o, d;
     double time;
 };
-RT_DEV V3 ray_at(const Ray &r, double t) { return r.o + t * r.d; }  // ray.rs:26-28
 
 struct ONB {
     V3 u, v, w;
@@ -150,35 +181,19 @@ RT_DEV V3 onb_local(const ONB &o, V3 a) { return a.x * o.u + a.y * o.v + a.z * o
 // ---------------------------------------------------------------------------
 // Wrapper chains: Translate (translate.rs:22-30), Rotate (rotate.rs:77-106), FlipNormal (hit.rs:113-120)
 // ---------------------------------------------------------------------------
-RT_DEV void rect_axes(uint32_t plane, int &k, int &a, int &b) {  // rect.rs:26-32
-    if (plane == RT_PLANE_YZ) { k = 0; a = 1; b = 2; }
-    else if (plane == RT_PLANE_XZ) { k = 1; a = 0; b = 2; }
-    else { k = 2; a = 0; b = 1; }
-}
-RT_DEV void rotate_axes(uint32_t axis, int &a, int &b) {  // rotate.rs:15-21
-    if (axis == RT_AXIS_X) { a = 1; b = 2; }
-    else if (axis == RT_AXIS_Y) { a = 0; b = 2; }
-    else { a = 0; b = 1; }
-}
-// rotate.rs:82-86: into the rotated (object) frame
+// rotate.rs:82-86: into the rotated (object) frame; (a,b) axes per rotate.rs:15-21
 RT_DEV V3 rot_fwd(const DOp &op, V3 v) {
-    int a, b;
-    rotate_axes(op.axis, a, b);
-    double va = comp(v, a), vb = comp(v, b);
-    V3 r = v;
-    set_comp(r, a, op.cos_theta * va - op.sin_theta * vb);
-    set_comp(r, b, op.sin_theta * va + op.cos_theta * vb);
-    return r;
+    double c = op.cos_theta, s = op.sin_theta;
+    if (op.axis == RT_AXIS_Y) return mk(c * v.x - s * v.z, v.y, s * v.x + c * v.z);
+    if (op.axis == RT_AXIS_X) return mk(v.x, c * v.y - s * v.z, s * v.y + c * v.z);
+    return mk(c * v.x - s * v.y, s * v.x + c * v.y, v.z);
 }
 // rotate.rs:94-98: back out of the rotated frame
 RT_DEV V3 rot_back(const DOp &op, V3 v) {
-    int a, b;
-    rotate_axes(op.axis, a, b);
-    double va = comp(v, a), vb = comp(v, b);
-    V3 r = v;
-    set_comp(r, a, op.cos_theta * va + op.sin_theta * vb);
-    set_comp(r, b, -op.sin_theta * va + op.cos_theta * vb);
-    return r;
+    double c = op.cos_theta, s = op.sin_theta;
+    if (op.axis == RT_AXIS_Y) return mk(c * v.x + s * v.z, v.y, -s * v.x + c * v.z);
+    if (op.axis == RT_AXIS_X) return mk(v.x, c * v.y + s * v.z, -s * v.y + c * v.z);
+    return mk(c * v.x + s * v.y, -s * v.x + c * v.y, v.z);
 }
 // Ray as seen below ops [first, first+n) of a chain (flips do not touch the ray).
 RT_DEV void chain_ray(const DScene &sc, uint32_t first, uint32_t n, V3 &o, V3 &d) {
@@ -193,125 +208,115 @@ RT_DEV void chain_ray(const DScene &sc, uint32_t first, uint32_t n, V3 &o, V3 &d
     }
 }
 
-// ---------------------------------------------------------------------------
-// Primitive tests.  During the closest-hit search only t (and the cube face) is
-// produced; the full HitRecord is resolved once, for the winner.
-// ---------------------------------------------------------------------------
-// Sphere::hit / MovingSphere::hit root search (sphere.rs:56-73 == :150-167)
-RT_DEV bool sphere_root(V3 o, V3 d, V3 center, double radius, double t_min, double t_max, double &root_out) {
-    V3 oc = o - center;
-    double a = powi2(length(d));
-    double half_b = dot(oc, d);
-    double c = powi2(length(oc)) - powi2(radius);
-    double discriminant = powi2(half_b) - a * c;
-    if (discriminant < 0.0) return false;
-    double sqrt_d = sqrt(discriminant);
-    double root = (-half_b - sqrt_d) / a;
-    if (root < t_min || root > t_max) {
-        root = (-half_b + sqrt_d) / a;
-        if (root < t_min || root > t_max) return false;
-    }
-    root_out = root;
-    return true;
-}
-RT_DEV V3 msphere_center(const double *pd, double time) {  // sphere.rs:144-146
-    V3 c0 = ld3(pd), c1 = ld3(pd + 3);
-    return c0 + ((time - pd[6]) / (pd[7] - pd[6])) * (c1 - c0);
-}
-// AARect::hit up to the bounds test (rect.rs:49-58)
-RT_DEV bool rect_t(V3 o, V3 d, uint32_t plane, double a0, double a1, double b0, double b1, double k, double t_min,
-                   double t_max, double &t_out) {
-    int ki, ai, bi;
-    rect_axes(plane, ki, ai, bi);
-    double t = (k - comp(o, ki)) / comp(d, ki);
-    if (t < t_min || t > t_max) return false;
-    double a = comp(o, ai) + t * comp(d, ai);
-    double b = comp(o, bi) + t * comp(d, bi);
-    if (a < a0 || a > a1 || b < b0 || b > b1) return false;
-    t_out = t;
-    return true;
-}
-// The six sides of a Cube in the order of cube.rs:17-25.
-RT_DEV void box_face(const double *pd, int face, uint32_t &plane, double &a0, double &a1, double &b0, double &b1, double &k) {
-    // pd = minx miny minz maxx maxy maxz
-    if (face < 2) {
-        plane = RT_PLANE_XY; a0 = pd[0]; a1 = pd[3]; b0 = pd[1]; b1 = pd[4]; k = face == 0 ? pd[5] : pd[2];
-    } else if (face < 4) {
-        plane = RT_PLANE_XZ; a0 = pd[0]; a1 = pd[3]; b0 = pd[2]; b1 = pd[5]; k = face == 2 ? pd[4] : pd[1];
-    } else {
-        plane = RT_PLANE_YZ; a0 = pd[1]; a1 = pd[4]; b0 = pd[2]; b1 = pd[5]; k = face == 4 ? pd[3] : pd[0];
-    }
-}
-// Cube::hit = HittableList::hit over the six rects (cube.rs:35-37, hit.rs:59-71)
-RT_DEV bool box_t(V3 o, V3 d, const double *pd, double t_min, double t_max, double &t_out, int &face_out) {
-    bool any = false;
-    double closest = t_max;
-#pragma unroll
-    for (int f = 0; f < 6; ++f) {
-        uint32_t plane;
-        double a0, a1, b0, b1, k, t;
-        box_face(pd, f, plane, a0, a1, b0, b1, k);
-        if (rect_t(o, d, plane, a0, a1, b0, b1, k, t_min, closest, t)) {
-            closest = t;
-            face_out = f;
-            any = true;
-        }
-    }
-    t_out = closest;
-    return any;
-}
-// Triangle::hit up to the barycentric test (tri.rs:24-39); pd = v0 e1 e2 n
-RT_DEV bool tri_t(V3 o, V3 d, const double *pd, double t_min, double t_max, double &t_out, double &b1_out, double &b2_out) {
-    V3 s = o - ld3(pd);
-    V3 e1 = ld3(pd + 3), e2 = ld3(pd + 6);
-    V3 s1 = cross(d, e2);
-    V3 s2 = cross(s, e1);
-    double s1_e1 = dot(s1, e1);
-    double t = dot(s2, e2) / s1_e1;
-    double b1 = dot(s1, s) / s1_e1;
-    double b2 = dot(s2, d) / s1_e1;
-    if (t < t_min || t > t_max) return false;
-    if (b1 < 0.0 || b2 < 0.0 || (1.0 - b1 - b2) < 0.0) return false;
-    t_out = t;
-    b1_out = b1;
-    b2_out = b2;
-    return true;
-}
-
+// ===========================================================================
+// SEARCH: which primitive is hit first
+// ===========================================================================
+struct SRay {  // a ray in some group's space with its reciprocal direction
+    V3 o, d, inv;
+    double time;
+};
 struct Best {
-    double t;
+    double t;       // search-grade t of the current winner (upper end of the search interval)
     uint32_t prim;  // index into prims, kMediumFlag|index into media, or kNoPrim
     uint32_t rank;
-    int face;
+    int face;       // BOX: which of the six sides (cube.rs:17-25 order)
 };
 
-RT_DEV void test_prim(const DScene &sc, uint32_t pi, V3 o, V3 d, double time, double t_min, Best &best) {
-    const DPrim &p = sc.prims[pi];
-    double t;
-    int face = 0;
-    bool h = false;
-    switch (p.kind) {
-        case PRIM_SPHERE: h = sphere_root(o, d, ld3(p.d), p.d[3], t_min, best.t, t); break;
-        case PRIM_MSPHERE: h = sphere_root(o, d, msphere_center(p.d, time), p.d[8], t_min, best.t, t); break;
-        case PRIM_RECT: h = rect_t(o, d, p.axis, p.d[0], p.d[1], p.d[2], p.d[3], p.d[4], t_min, best.t, t); break;
-        case PRIM_TRI: {
-            double b1, b2;
-            h = tri_t(o, d, p.d, t_min, best.t, t, b1, b2);
-            break;
-        }
-        default: h = box_t(o, d, p.d, t_min, best.t, t, face); break;
-    }
-    // Every test accepts t == t_max, and lists / BVH nodes keep the later object on an
-    // exact tie (hit.rs:64-66, bvh.rs:81-84; §Q17): later = higher rank.
-    if (h && (t < best.t || best.prim == kNoPrim || p.rank > best.rank)) {
+// Every reference test accepts t == t_max, and lists / BVH nodes keep the object visited
+// last (hit.rs:64-66, bvh.rs:81-84; §Q17): an equal t only wins with a higher rank.
+RT_DEV void accept(bool h, double t, uint32_t pi, uint32_t rank, int face, Best &best) {
+    if (h && (t < best.t || rank > best.rank)) {
         best.t = t;
         best.prim = pi;
-        best.rank = p.rank;
+        best.rank = rank;
         best.face = face;
     }
 }
 
-// Conservative slab test against [t_min, t_max] (culling only).
+RT_DEV V3 msphere_center(const double *pd, double time) {  // sphere.rs:144-146
+    V3 c0 = ld3(pd), c1 = ld3(pd + 3);
+    return c0 + ddiv(time - pd[6], pd[7] - pd[6]) * (c1 - c0);
+}
+
+RT_DEV void s_sphere(const SRay &r, V3 center, double radius, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    V3 oc = r.o - center;
+    double a = dot(r.d, r.d);
+    double half_b = dot(oc, r.d);
+    double c = dot(oc, oc) - radius * radius;
+    double disc = half_b * half_b - a * c;
+    if (!(disc >= 0.0)) return;
+    double sq = sqrt(disc);
+    double ia = rcp_fast(a);
+    double t = (-half_b - sq) * ia;
+    if (!(t >= t_min && t <= best.t)) t = (-half_b + sq) * ia;
+    accept(t >= t_min && t <= best.t, t, pi, rank, 0, best);
+}
+RT_DEV void s_rect(const SRay &r, uint32_t plane, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    double a0 = pd[0], a1 = pd[1], b0 = pd[2], b1 = pd[3], k = pd[4];
+    double t, a, b;
+    if (plane == RT_PLANE_XZ) {
+        t = (k - r.o.y) * r.inv.y;
+        a = fma(t, r.d.x, r.o.x);
+        b = fma(t, r.d.z, r.o.z);
+    } else if (plane == RT_PLANE_YZ) {
+        t = (k - r.o.x) * r.inv.x;
+        a = fma(t, r.d.y, r.o.y);
+        b = fma(t, r.d.z, r.o.z);
+    } else {
+        t = (k - r.o.z) * r.inv.z;
+        a = fma(t, r.d.x, r.o.x);
+        b = fma(t, r.d.y, r.o.y);
+    }
+    accept(t >= t_min && t <= best.t && a >= a0 && a <= a1 && b >= b0 && b <= b1, t, pi, rank, 0, best);
+}
+// Cube = six AARects in a list (cube.rs:17-25,35-37).  For a convex box the closest accepted
+// side is the entry point if it lies in the interval, else the exit point: a slab test.
+RT_DEV void s_box(const SRay &r, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    double x0 = (pd[0] - r.o.x) * r.inv.x, x1 = (pd[3] - r.o.x) * r.inv.x;
+    double y0 = (pd[1] - r.o.y) * r.inv.y, y1 = (pd[4] - r.o.y) * r.inv.y;
+    double z0 = (pd[2] - r.o.z) * r.inv.z, z1 = (pd[5] - r.o.z) * r.inv.z;
+    // near/far per axis and the side index it belongs to (cube.rs order: +z 0, -z 1, +y 2, -y 3, +x 4, -x 5)
+    bool sx = x0 <= x1, sy = y0 <= y1, sz = z0 <= z1;
+    double nx = sx ? x0 : x1, fx = sx ? x1 : x0;
+    double ny = sy ? y0 : y1, fy = sy ? y1 : y0;
+    double nz = sz ? z0 : z1, fz = sz ? z1 : z0;
+    double t_in = nx;
+    int f_in = sx ? 5 : 4;
+    if (ny > t_in) { t_in = ny; f_in = sy ? 3 : 2; }
+    if (nz > t_in) { t_in = nz; f_in = sz ? 1 : 0; }
+    double t_out = fx;
+    int f_out = sx ? 4 : 5;
+    if (fy < t_out) { t_out = fy; f_out = sy ? 2 : 3; }
+    if (fz < t_out) { t_out = fz; f_out = sz ? 0 : 1; }
+    if (!(t_in <= t_out)) return;  // misses the box (NaN: a ray parallel to a slab on its plane -> no hit)
+    bool in_ok = t_in >= t_min && t_in <= best.t;
+    double t = in_ok ? t_in : t_out;
+    int f = in_ok ? f_in : f_out;
+    accept(t >= t_min && t <= best.t, t, pi, rank, f, best);
+}
+RT_DEV void s_tri(const SRay &r, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    V3 s = r.o - ld3(pd);
+    V3 e1 = ld3(pd + 3), e2 = ld3(pd + 6);
+    V3 s1 = cross(r.d, e2);
+    V3 s2 = cross(s, e1);
+    double inv = rcp_fast(dot(s1, e1));
+    double t = dot(s2, e2) * inv;
+    double b1 = dot(s1, s) * inv;
+    double b2 = dot(s2, r.d) * inv;
+    accept(t >= t_min && t <= best.t && b1 >= 0.0 && b2 >= 0.0 && (1.0 - b1 - b2) >= 0.0, t, pi, rank, 0, best);
+}
+
+RT_DEV void s_prim(const DScene &sc, uint32_t pi, const SRay &r, double t_min, Best &best) {
+    const DPrim &p = sc.prims[pi];
+    uint32_t kind = p.kind, rank = p.rank;
+    if (kind == PRIM_RECT) s_rect(r, p.axis, p.d, t_min, pi, rank, best);
+    else if (kind == PRIM_BOX) s_box(r, p.d, t_min, pi, rank, best);
+    else if (kind == PRIM_SPHERE) s_sphere(r, ld3(p.d), p.d[3], t_min, pi, rank, best);
+    else if (kind == PRIM_TRI) s_tri(r, p.d, t_min, pi, rank, best);
+    else s_sphere(r, msphere_center(p.d, r.time), p.d[8], t_min, pi, rank, best);
+}
+
+// Conservative slab test against [t_min, t_max] (culling only; NaN operands are ignored by fmin/fmax).
 RT_DEV bool slab(V3 o, V3 inv, const double *lo, const double *hi, double t_min, double t_max, double &t_entry) {
     double tx0 = (lo[0] - o.x) * inv.x, tx1 = (hi[0] - o.x) * inv.x;
     double ty0 = (lo[1] - o.y) * inv.y, ty1 = (hi[1] - o.y) * inv.y;
@@ -322,13 +327,8 @@ RT_DEV bool slab(V3 o, V3 inv, const double *lo, const double *hi, double t_min,
     return tin <= tout;
 }
 
-// Closest hit of one group given the ray already in the group's space.
-RT_DEV void trace_group(const DScene &sc, const DGroup &g, V3 o, V3 d, double time, double t_min, Best &best) {
-    if (g.bvh_root < 0) {
-        for (uint32_t i = 0; i < g.n_prims; ++i) test_prim(sc, g.first_prim + i, o, d, time, t_min, best);
-        return;
-    }
-    V3 inv = mk(1.0 / d.x, 1.0 / d.y, 1.0 / d.z);
+// g.bvh_root >= 0: a BVH node; < 0: the whole (small) group encoded as one leaf — one code path.
+RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double t_min, Best &best) {
     int stack[kStackSize];
     int sp = 0;
     int node = g.bvh_root;
@@ -336,8 +336,8 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, V3 o, V3 d, double ti
         if (node >= 0) {
             const DBvhNode &n = sc.nodes[node];
             double e0, e1;
-            bool h0 = slab(o, inv, n.lo0, n.hi0, t_min, best.t, e0);
-            bool h1 = slab(o, inv, n.lo1, n.hi1, t_min, best.t, e1);
+            bool h0 = slab(r.o, r.inv, n.lo0, n.hi0, t_min, best.t, e0);
+            bool h1 = slab(r.o, r.inv, n.lo1, n.hi1, t_min, best.t, e1);
             if (h0 && h1) {
                 int near_c = n.child0, far_c = n.child1;
                 if (e1 < e0) {
@@ -359,7 +359,7 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, V3 o, V3 d, double ti
         } else {
             uint32_t code = ~(uint32_t)node;
             uint32_t first = code >> 3, count = (code & 7u) + 1u;
-            for (uint32_t i = 0; i < count; ++i) test_prim(sc, first + i, o, d, time, t_min, best);
+            for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, best);
         }
         if (sp == 0) break;
         node = stack[--sp];
@@ -367,55 +367,30 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, V3 o, V3 d, double ti
 }
 
 // Closest hit over a sub-scene (a range of groups) for the ray given in the outermost space.
-RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &r, double t_min, Best &best) {
-    V3 inv = mk(1.0 / r.d.x, 1.0 / r.d.y, 1.0 / r.d.z);
+RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
+                         Best &best) {
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const DGroup &g = sc.groups[first_group + gi];
         double e;
-        if (!slab(r.o, inv, g.bmin, g.bmax, t_min, best.t, e)) continue;
-        V3 o = r.o, d = r.d;
+        // a one- or two-primitive group is cheaper to test than to cull
+        if ((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, t_min, best.t, e)) continue;
+        SRay r;
+        r.o = ray.o;
+        r.d = ray.d;
+        r.time = ray.time;
+        r.inv = inv;
         DChain c = sc.chains[g.chain];
-        chain_ray(sc, c.first_op, c.n_ops, o, d);
-        trace_group(sc, g, o, d, r.time, t_min, best);
-    }
-}
-
-// ConstantMedium::hit (medium.rs:27-61) for every medium of the world, after the
-// surfaces: with slot-addressed draws the outcome does not depend on list order.
-RT_DEV void trace_media(const DScene &sc, const Ray &r, const Rng &rng, double t_min, Best &best) {
-    for (uint32_t mi = 0; mi < sc.n_media; ++mi) {
-        const DMedium &m = sc.media[mi];
-        Best b1{DBL_MAX, kNoPrim, 0, 0};
-        trace_groups(sc, m.first_group, m.n_groups, r, -DBL_MAX, b1);  // boundary.hit(r, -MAX, MAX)
-        if (b1.prim == kNoPrim) continue;
-        Best b2{DBL_MAX, kNoPrim, 0, 0};
-        trace_groups(sc, m.first_group, m.n_groups, r, b1.t + 0.0001, b2);  // boundary.hit(r, hit1.t + 0.0001, MAX)
-        if (b2.prim == kNoPrim) continue;
-        double t1 = b1.t, t2 = b2.t;
-        if (t1 < t_min) t1 = t_min;
-        if (t2 > best.t) t2 = best.t;
-        if (t1 < t2) {
-            // r.direction().length() of the ray the medium sees (below its own wrappers)
-            V3 o = r.o, d = r.d;
-            DChain c = sc.chains[m.chain];
-            chain_ray(sc, c.first_op, c.n_ops, o, d);
-            double len = length(d);
-            double distance_inside_boundary = (t2 - t1) * len;
-            Draw dr = draw(rng, SLOT_MEDIUM, (uint32_t)m.node);
-            double hit_distance = -(1.0 / m.density) * log(dr.a);
-            if (hit_distance < distance_inside_boundary) {
-                best.t = t1 + hit_distance / len;
-                best.prim = kMediumFlag | mi;
-                best.rank = m.rank;
-                best.face = 0;
-            }
+        if (c.n_ops) {
+            chain_ray(sc, c.first_op, c.n_ops, r.o, r.d);
+            if (g.flags & GROUP_ROTATED) r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
         }
+        trace_group(sc, g, r, t_min, best);
     }
 }
 
-// ---------------------------------------------------------------------------
-// HitRecord (hit.rs:9-24) of the winning primitive
-// ---------------------------------------------------------------------------
+// ===========================================================================
+// RESOLVE: the winner's HitRecord (hit.rs:9-24) in reference arithmetic
+// ===========================================================================
 struct HitRec {
     V3 p, normal;
     double t, u, v;
@@ -434,7 +409,29 @@ RT_DEV void get_sphere_uv(V3 p, double &u, double &v) {  // sphere.rs:11-25
     u = phi / (2.0 * kPi);
     v = theta / kPi;
 }
-
+// The six sides of a Cube in the order of cube.rs:17-25; pd = minx miny minz maxx maxy maxz
+RT_DEV void box_face(const double *pd, int face, uint32_t &plane, double &a0, double &a1, double &b0, double &b1, double &k) {
+    if (face < 2) {
+        plane = RT_PLANE_XY; a0 = pd[0]; a1 = pd[3]; b0 = pd[1]; b1 = pd[4]; k = face == 0 ? pd[5] : pd[2];
+    } else if (face < 4) {
+        plane = RT_PLANE_XZ; a0 = pd[0]; a1 = pd[3]; b0 = pd[2]; b1 = pd[5]; k = face == 2 ? pd[4] : pd[1];
+    } else {
+        plane = RT_PLANE_YZ; a0 = pd[1]; a1 = pd[4]; b0 = pd[2]; b1 = pd[5]; k = face == 4 ? pd[3] : pd[0];
+    }
+}
+// The nearest root in [t_min, inf) exactly as Sphere::hit computes it (sphere.rs:56-73 == :150-167).
+// For the winner of a search the reference's t_max test cannot have rejected the chosen root.
+RT_DEV double sphere_root_exact(V3 o, V3 d, V3 center, double radius, double t_min) {
+    V3 oc = o - center;
+    double a = powi2(length(d));
+    double half_b = dot(oc, d);
+    double c = powi2(length(oc)) - powi2(radius);
+    double discriminant = powi2(half_b) - a * c;
+    double sqrt_d = sqrt(fmax(discriminant, 0.0));  // search said "hit": a last-ulp negative stays a graze
+    double root = (-half_b - sqrt_d) / a;
+    if (root < t_min) root = (-half_b + sqrt_d) / a;
+    return root;
+}
 // Wrapper post-processing, innermost first (translate.rs:26, rotate.rs:88-104, hit.rs:116)
 RT_DEV void chain_post(const DScene &sc, uint32_t chain, const Ray &world, HitRec &rec) {
     DChain c = sc.chains[chain];
@@ -455,87 +452,172 @@ RT_DEV void chain_post(const DScene &sc, uint32_t chain, const Ray &world, HitRe
     }
 }
 
+// t: the winner's reference-arithmetic t (exact_t).
 template <bool WANT_UV>
-RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, HitRec &rec) {
-    rec.t = best.t;
+RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, double t, HitRec &rec) {
+    rec.t = t;
     rec.u = 0.0;
     rec.v = 0.0;
-    if (best.prim & kMediumFlag) {  // medium.rs:46-56
-        const DMedium &m = sc.media[best.prim & ~kMediumFlag];
-        V3 o = world.o, d = world.d;
-        DChain c = sc.chains[m.chain];
-        chain_ray(sc, c.first_op, c.n_ops, o, d);
-        rec.p = o + best.t * d;
-        rec.front_face = false;
-        rec.normal = mk(1.0, 0.0, 0.0);
-        rec.material = m.material;
-        rec.node = m.node;
-        rec.face = 0;
-        chain_post(sc, m.chain, world, rec);
-        return;
-    }
     const DPrim &p = sc.prims[best.prim];
     V3 o = world.o, d = world.d;
     DChain c = sc.chains[p.chain];
     chain_ray(sc, c.first_op, c.n_ops, o, d);
-    rec.p = o + best.t * d;  // r.at(t) in the primitive's own space
     rec.material = p.material;
     rec.node = p.node;
     rec.face = best.face;
     bool want_uv = WANT_UV || sc.materials[p.material].needs_uv;
-    switch (p.kind) {
-        case PRIM_SPHERE:
-        case PRIM_MSPHERE: {  // sphere.rs:75-94
-            V3 center = p.kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
-            double radius = p.kind == PRIM_SPHERE ? p.d[3] : p.d[8];
-            V3 outward_normal = (rec.p - center) / radius;
-            set_face_normal(rec, d, outward_normal);
-            if (want_uv) get_sphere_uv(outward_normal, rec.u, rec.v);
-            break;
+    uint32_t kind = p.kind;
+    if (kind == PRIM_RECT || kind == PRIM_BOX) {  // rect.rs:49-78
+        uint32_t plane = p.axis;
+        double a0 = p.d[0], a1 = p.d[1], b0 = p.d[2], b1 = p.d[3], k = p.d[4];
+        if (kind == PRIM_BOX) box_face(p.d, best.face, plane, a0, a1, b0, b1, k);
+        double ok, dk, oa, da, ob, db;
+        V3 normal;
+        if (plane == RT_PLANE_XZ) { ok = o.y; dk = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; normal = mk(0.0, 1.0, 0.0); }
+        else if (plane == RT_PLANE_YZ) { ok = o.x; dk = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; normal = mk(1.0, 0.0, 0.0); }
+        else { ok = o.z; dk = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; normal = mk(0.0, 0.0, 1.0); }
+        if (want_uv) {
+            double a = oa + t * da;
+            double b = ob + t * db;
+            rec.u = (a - a0) / (a1 - a0);
+            rec.v = (b - b0) / (b1 - b0);
         }
-        case PRIM_RECT:
-        case PRIM_BOX: {  // rect.rs:59-78
-            uint32_t plane = p.axis;
-            double a0 = p.d[0], a1 = p.d[1], b0 = p.d[2], b1 = p.d[3], k = p.d[4];
-            if (p.kind == PRIM_BOX) box_face(p.d, best.face, plane, a0, a1, b0, b1, k);
-            int ki, ai, bi;
-            rect_axes(plane, ki, ai, bi);
-            if (want_uv) {
-                double a = comp(o, ai) + best.t * comp(d, ai);
-                double b = comp(o, bi) + best.t * comp(d, bi);
-                rec.u = (a - a0) / (a1 - a0);
-                rec.v = (b - b0) / (b1 - b0);
-            }
-            V3 normal = mk(0.0, 0.0, 0.0);
-            set_comp(normal, ki, 1.0);
-            set_face_normal(rec, d, normal);
-            break;
+        rec.p = o + t * d;  // r.at(t), ray.rs:26-28
+        set_face_normal(rec, d, normal);
+    } else if (kind == PRIM_TRI) {  // tri.rs:24-54; p.d = v0 e1 e2 n
+        V3 s = o - ld3(p.d);
+        V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
+        V3 s1 = cross(d, e2);
+        V3 s2 = cross(s, e1);
+        if (want_uv) {
+            double s1_e1 = dot(s1, e1);
+            rec.u = dot(s1, s) / s1_e1;
+            rec.v = dot(s2, d) / s1_e1;
         }
-        default: {  // tri.rs:40-54
-            if (want_uv) {
-                double t, b1, b2;
-                tri_t(o, d, p.d, -DBL_MAX, DBL_MAX, t, b1, b2);
-                rec.u = b1;
-                rec.v = b2;
-            }
-            set_face_normal(rec, d, ld3(p.d + 9));
-            break;
-        }
+        rec.p = o + t * d;
+        set_face_normal(rec, d, ld3(p.d + 9));
+    } else {  // sphere.rs:56-94, :150-188
+        V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
+        double radius = kind == PRIM_SPHERE ? p.d[3] : p.d[8];
+        rec.p = o + t * d;
+        V3 outward_normal = (rec.p - center) / radius;
+        set_face_normal(rec, d, outward_normal);
+        if (want_uv) get_sphere_uv(outward_normal, rec.u, rec.v);
     }
     chain_post(sc, p.chain, world, rec);
 }
 
-// world.hit(ray, 0.00001, inf) (main.rs:48)
-template <bool WITH_MEDIA>
-RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, Best &best) {
-    best.t = DBL_MAX;  // stands for +inf: every accepted t is finite or the reference's own inf corner
-    best.prim = kNoPrim;
-    best.rank = 0;
-    best.face = 0;
-    best.t = __longlong_as_double(0x7FF0000000000000ll);  // f64::INFINITY
-    trace_groups(sc, 0, sc.n_world_groups, r, kTMin, best);
-    if (WITH_MEDIA && sc.n_media) trace_media(sc, r, rng, kTMin, best);
-    return best.prim != kNoPrim;
+// The reference-arithmetic t of a search winner (the part of resolve_hit that produces rec.t).
+// t_min: the lower end of the interval the search ran with.
+RT_DEV double exact_t(const DScene &sc, const Ray &world, const Best &best, double t_min) {
+    const DPrim &p = sc.prims[best.prim];
+    V3 o = world.o, d = world.d;
+    DChain c = sc.chains[p.chain];
+    chain_ray(sc, c.first_op, c.n_ops, o, d);
+    uint32_t kind = p.kind;
+    if (kind == PRIM_RECT || kind == PRIM_BOX) {  // rect.rs:51
+        uint32_t plane = p.axis;
+        double k = p.d[4];
+        if (kind == PRIM_BOX) {
+            double a0, a1, b0, b1;
+            box_face(p.d, best.face, plane, a0, a1, b0, b1, k);
+        }
+        double ok = plane == RT_PLANE_XZ ? o.y : (plane == RT_PLANE_YZ ? o.x : o.z);
+        double dk = plane == RT_PLANE_XZ ? d.y : (plane == RT_PLANE_YZ ? d.x : d.z);
+        return (k - ok) / dk;
+    }
+    if (kind == PRIM_TRI) {  // tri.rs:26-33
+        V3 s = o - ld3(p.d);
+        V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
+        V3 s1 = cross(d, e2);
+        V3 s2 = cross(s, e1);
+        return dot(s2, e2) / dot(s1, e1);
+    }
+    V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
+    return sphere_root_exact(o, d, center, kind == PRIM_SPHERE ? p.d[3] : p.d[8], t_min);
+}
+
+RT_DEV void resolve_medium(const DScene &sc, const Ray &world, const Best &best, double t, HitRec &rec) {  // medium.rs:46-56
+    const DMedium &m = sc.media[best.prim & ~kMediumFlag];
+    V3 o = world.o, d = world.d;
+    DChain c = sc.chains[m.chain];
+    chain_ray(sc, c.first_op, c.n_ops, o, d);
+    rec.t = t;
+    rec.u = 0.0;
+    rec.v = 0.0;
+    rec.p = o + t * d;
+    rec.front_face = false;
+    rec.normal = mk(1.0, 0.0, 0.0);
+    rec.material = m.material;
+    rec.node = m.node;
+    rec.face = 0;
+    chain_post(sc, m.chain, world, rec);
+}
+
+// world.hit(ray, 0.00001, inf) (main.rs:48).  One query loop with a single search call site:
+// query 0 is the world's surfaces; then, per ConstantMedium, the two boundary queries of
+// medium.rs:29-30.  Media are visited after the surfaces: with slot-addressed draws the outcome
+// does not depend on list order.  `closest` is closest_so_far (hit.rs:61-66) in reference arithmetic.
+template <bool WITH_MEDIA, bool WANT_UV>
+RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &rec) {
+    V3 inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
+    Best win{RT_INF, kNoPrim, 0, 0};
+    double closest = RT_INF;
+    double t1 = 0.0;
+    bool have_t1 = false;
+    const uint32_t nq = 1u + (WITH_MEDIA ? 2u * sc.n_media : 0u);
+    for (uint32_t q = 0; q < nq; ++q) {
+        uint32_t fg = 0, ng = sc.n_world_groups, mi = 0;
+        double t_min = kTMin;
+        Best b{RT_INF, kNoPrim, 0, 0};
+        bool second = false;
+        if (q > 0) {
+            mi = (q - 1u) >> 1;
+            second = ((q - 1u) & 1u) != 0u;
+            if (second && !have_t1) continue;
+            const DMedium &m = sc.media[mi];
+            fg = m.first_group;
+            ng = m.n_groups;
+            t_min = second ? t1 + 0.0001 : -DBL_MAX;  // boundary.hit(r, -MAX, MAX) ; boundary.hit(r, hit1.t + 0.0001, MAX)
+            b.t = DBL_MAX;
+        }
+        trace_groups(sc, fg, ng, r, inv, t_min, b);
+        bool found = b.prim != kNoPrim;
+        if (q > 0 && !second) have_t1 = found;
+        if (!found) continue;
+        double te = exact_t(sc, r, b, t_min);
+        if (q == 0) {
+            win = b;
+            closest = te;
+        } else if (!second) {
+            t1 = te;
+        } else {  // medium.rs:32-58
+            const DMedium &m = sc.media[mi];
+            double h1 = t1, h2 = te;
+            if (h1 < kTMin) h1 = kTMin;
+            if (h2 > closest) h2 = closest;
+            if (h1 < h2) {
+                // r.direction().length() of the ray the medium sees (below its own wrappers)
+                V3 o = r.o, d = r.d;
+                DChain c = sc.chains[m.chain];
+                chain_ray(sc, c.first_op, c.n_ops, o, d);
+                double len = length(d);
+                double distance_inside_boundary = (h2 - h1) * len;
+                Draw dr = draw(rng, SLOT_MEDIUM, (uint32_t)m.node);
+                double hit_distance = -(1.0 / m.density) * log(dr.a);
+                if (hit_distance < distance_inside_boundary) {
+                    closest = h1 + hit_distance / len;
+                    win.prim = kMediumFlag | mi;
+                    win.rank = m.rank;
+                    win.face = 0;
+                }
+            }
+        }
+    }
+    if (win.prim == kNoPrim) return false;
+    if (win.prim & kMediumFlag) resolve_medium(sc, r, win, closest, rec);
+    else resolve_hit<WANT_UV>(sc, r, win, closest, rec);
+    return true;
 }
 
 // ---------------------------------------------------------------------------
@@ -573,39 +655,47 @@ RT_DEV double perlin_noise(const DPerlin &t, V3 p, double scale) {  // perlin.rs
             }
     return accum;
 }
-RT_DEV double perlin_turb(const DPerlin &t, V3 p, double scale, int depth) {  // perlin.rs:111-121
+// Cold: only textured scenes reach these; keeping them out of line keeps the hot loop small.
+RT_DEV_COLD double perlin_turb(const DPerlin *t, double px, double py, double pz, double scale, int depth) {  // perlin.rs:111-121
     double accum = 0.0;
-    V3 temp_p = p;
+    V3 temp_p = mk(px, py, pz);
     double weight = 1.0;
     for (int i = 0; i < depth; ++i) {
-        accum += weight * perlin_noise(t, temp_p, scale);
+        accum += weight * perlin_noise(*t, temp_p, scale);
         weight *= 0.5;
         temp_p = temp_p * 2.0;
     }
     return fabs(accum);
 }
+RT_DEV_COLD void image_texel(const DImage *images, const uint8_t *texels, uint32_t id, double u, double v, double *rgb) {  // texture.rs:99-121
+    DImage im = images[id];
+    unsigned long long width = im.width, height = im.height;
+    unsigned long long i = as_usize(clampd(u, 0.0, 1.0) * (double)width);
+    unsigned long long j = as_usize(clampd(1.0 - v, 0.0, 1.0) * (double)height);
+    if (i > width - 1) i = width - 1;
+    if (j > height - 1) j = height - 1;
+    const uint8_t *px = texels + im.offset + 3 * i + 3 * width * j;
+    rgb[0] = (double)px[0] / 255.0;
+    rgb[1] = (double)px[1] / 255.0;
+    rgb[2] = (double)px[2] / 255.0;
+}
 RT_DEV V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p) {
     for (int guard = 0; guard < 16; ++guard) {
         const DTexture &t = sc.textures[id];
-        if (t.kind == RT_TEX_CHECKER) {  // texture.rs:45-54
+        uint32_t kind = t.kind;
+        if (kind == RT_TEX_CONSTANT) return ld3(t.color);  // texture.rs:23-27
+        if (kind == RT_TEX_CHECKER) {                       // texture.rs:45-54
             double sines = sin(10.0 * p.x) * sin(10.0 * p.y) * sin(10.0 * p.z);
             id = sines < 0.0 ? t.a : t.b;
             continue;
         }
-        if (t.kind == RT_TEX_CONSTANT) return ld3(t.color);  // texture.rs:23-27
-        if (t.kind == RT_TEX_NOISE) {                         // texture.rs:71-79
-            double s = 1.0 + sin(t.scale * p.z + 10.0 * perlin_turb(sc.perlin[t.a], p, t.scale, 7));
+        if (kind == RT_TEX_NOISE) {  // texture.rs:71-79
+            double s = 1.0 + sin(t.scale * p.z + 10.0 * perlin_turb(&sc.perlin[t.a], p.x, p.y, p.z, t.scale, 7));
             return (mk(1.0, 1.0, 1.0) * 0.5) * s;
         }
-        // texture.rs:99-121
-        DImage im = sc.images[t.a];
-        unsigned long long width = im.width, height = im.height;
-        unsigned long long i = as_usize(clampd(u, 0.0, 1.0) * (double)width);
-        unsigned long long j = as_usize(clampd(1.0 - v, 0.0, 1.0) * (double)height);
-        if (i > width - 1) i = width - 1;
-        if (j > height - 1) j = height - 1;
-        const uint8_t *px = sc.texels + im.offset + 3 * i + 3 * width * j;
-        return mk((double)px[0] / 255.0, (double)px[1] / 255.0, (double)px[2] / 255.0);
+        double rgb[3];
+        image_texel(sc.images, sc.texels, t.a, u, v, rgb);
+        return mk(rgb[0], rgb[1], rgb[2]);
     }
     return mk(0.0, 0.0, 0.0);
 }
@@ -614,24 +704,38 @@ RT_DEV V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p)
 // Lights: PDF::Hittable over the light list (pdf.rs:140-142,164-166; hit.rs:90-96)
 // ---------------------------------------------------------------------------
 RT_DEV double light_pdf_one(const DLight &l, V3 o, V3 v) {
-    if (l.kind == LIGHT_RECT) {  // rect.rs:91-101
-        double t;
-        if (!rect_t(o, v, l.axis, l.d[0], l.d[1], l.d[2], l.d[3], l.d[4], 0.001, __longlong_as_double(0x7FF0000000000000ll), t))
-            return 0.0;
-        int ki, ai, bi;
-        rect_axes(l.axis, ki, ai, bi);
-        double area = (l.d[1] - l.d[0]) * (l.d[3] - l.d[2]);
-        double distance_squared = powi2(t) * powi2(length(v));
-        // rec.normal is +-axis_k after set_face_normal: |v . normal| = |v_k|
-        double vk = comp(v, ki);
-        double nk = (vk * 1.0 < 0.0) ? 1.0 : -1.0;  // front_face ? outward : -outward, outward = +axis
-        double cosine = fabs(vk * nk) / length(v);
+    if (l.kind == LIGHT_RECT) {  // rect.rs:91-101 -> AARect::hit(Ray(o,v), 0.001, inf), rect.rs:49-58
+        double a0 = l.d[0], a1 = l.d[1], b0 = l.d[2], b1 = l.d[3], k = l.d[4];
+        double ok, vk, oa, va, ob, vb;
+        if (l.axis == RT_PLANE_XZ) { ok = o.y; vk = v.y; oa = o.x; va = v.x; ob = o.z; vb = v.z; }
+        else if (l.axis == RT_PLANE_YZ) { ok = o.x; vk = v.x; oa = o.y; va = v.y; ob = o.z; vb = v.z; }
+        else { ok = o.z; vk = v.z; oa = o.x; va = v.x; ob = o.y; vb = v.y; }
+        double t = (k - ok) / vk;
+        if (t < 0.001 || t > RT_INF) return 0.0;
+        double a = oa + t * va;
+        double b = ob + t * vb;
+        if (a < a0 || a > a1 || b < b0 || b > b1) return 0.0;
+        double area = (a1 - a0) * (b1 - b0);
+        double len = length(v);
+        double distance_squared = powi2(t) * powi2(len);
+        // rec.normal is +-axis_k after set_face_normal, so |v . normal| = |v_k| exactly
+        double cosine = fabs(vk) / len;
         return cosine != 0.0 ? distance_squared / (cosine * area) : 0.0;
     }
     if (l.kind == LIGHT_SPHERE) {  // sphere.rs:104-112
-        double root;
         V3 center = ld3(l.d);
-        if (!sphere_root(o, v, center, l.d[3], 0.001, DBL_MAX, root)) return 0.0;
+        V3 oc = o - center;
+        double a = powi2(length(v));
+        double half_b = dot(oc, v);
+        double c = powi2(length(oc)) - powi2(l.d[3]);
+        double discriminant = powi2(half_b) - a * c;
+        if (discriminant < 0.0) return 0.0;
+        double sqrt_d = sqrt(discriminant);
+        double root = (-half_b - sqrt_d) / a;
+        if (root < 0.001 || root > DBL_MAX) {
+            root = (-half_b + sqrt_d) / a;
+            if (root < 0.001 || root > DBL_MAX) return 0.0;
+        }
         double cos_theta_max = sqrt(1.0 - powi2(l.d[3]) / powi2(length(center - o)));
         double solid_angle = 2.0 * kPi * (1.0 - cos_theta_max);
         return 1.0 / solid_angle;
@@ -647,12 +751,13 @@ RT_DEV V3 lights_random(const DScene &sc, V3 o, const Draw &dr) {  // hit.rs:94-
     uint32_t idx = (dr.bits_b * sc.n_lights) >> 11;
     const DLight &l = sc.lights[idx];
     if (l.kind == LIGHT_RECT) {  // rect.rs:103-111
-        int ki, ai, bi;
-        rect_axes(l.axis, ki, ai, bi);
-        V3 random_point = mk(0.0, 0.0, 0.0);
-        set_comp(random_point, ai, gen_range(l.d[0], l.d[1], dr.a));
-        set_comp(random_point, bi, gen_range(l.d[2], l.d[3], dr.b));
-        set_comp(random_point, ki, l.d[4]);
+        double a = gen_range(l.d[0], l.d[1], dr.a);
+        double b = gen_range(l.d[2], l.d[3], dr.b);
+        double k = l.d[4];
+        V3 random_point;
+        if (l.axis == RT_PLANE_XZ) random_point = mk(a, k, b);
+        else if (l.axis == RT_PLANE_YZ) random_point = mk(k, a, b);
+        else random_point = mk(a, b, k);
         return random_point - o;
     }
     if (l.kind == LIGHT_SPHERE) {  // sphere.rs:114-119 + :27-36
@@ -710,35 +815,34 @@ struct PathState {
 //   recursion:  L = emitted + f * L_next      iteration:  radiance += beta*emitted ; beta *= f
 RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint32_t flags) {
     if (ps.depth_left == 0) return false;  // main.rs:42-45: contributes black
-    Best best;
+    HitRec rec;
     ps.segments += 1;
-    if (!world_hit<true>(sc, ps.ray, ps.rng, best)) {  // main.rs:48,118
+    if (!world_hit<true, false>(sc, ps.ray, ps.rng, rec)) {  // main.rs:48,118
         ps.radiance = ps.radiance + ps.beta * ld3(sc.background);
         return false;
     }
-    HitRec rec;
-    resolve_hit<false>(sc, ps.ray, best, rec);
     const DMaterial &m = sc.materials[rec.material];
+    uint32_t mkind = m.kind;
     // Material::emitted (mat.rs:70-72, :395-401)
-    if (m.kind == RT_MAT_DIFFUSE_LIGHT) {
+    if (mkind == RT_MAT_DIFFUSE_LIGHT) {
         // DiffuseLight never scatters (mat.rs:391-393 / default scatter_mc_method): return emitted
         if (rec.front_face) ps.radiance = ps.radiance + ps.beta * texture_value(sc, m.texture, rec.u, rec.v, rec.p);
         return false;
     }
     V3 new_dir;
     V3 factor;
-    if (m.kind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
+    if (mkind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
         V3 reflected = normalized(reflect(ps.ray.d, rec.normal));
         // random_in_unit_sphere is drawn even for fuzz == 0 (§Q12); with slot addressing the
         // draw can be skipped when its product with fuzz is exactly zero.
         new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * random_in_unit_sphere(ps.rng) : reflected;
         if (!(dot(new_dir, rec.normal) > 0.0)) return false;  // None -> emitted (black)
         factor = ld3(m.albedo);
-    } else if (m.kind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
+    } else if (mkind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
         new_dir = dielectric_direction(m, ps.ray.d, rec, ps.rng);
         factor = mk(1.0, 1.0, 1.0);
     } else if (integrator == RT_INTEGRATOR_LEGACY) {
-        if (m.kind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
+        if (mkind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
             new_dir = rec.normal + normalized(random_in_unit_sphere(ps.rng));
             if (near_zero(new_dir)) new_dir = rec.normal;
         } else {  // Isotropic, mat.rs:418-421
@@ -746,7 +850,7 @@ RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint
         }
         factor = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
     } else {
-        if (m.kind != RT_MAT_LAMBERTIAN) return false;  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
+        if (mkind != RT_MAT_LAMBERTIAN) return false;  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
         // main.rs:92-98
         V3 attenuation = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
         ONB uvw = onb_from_w(rec.normal);  // PDF::cosine_pdf (pdf.rs:83-87)
@@ -759,9 +863,9 @@ RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint
         V3 unit = normalized(new_dir);
         double cosine = dot(unit, uvw.w);  // pdf.rs:131-139
         double cosine_pdf = cosine > 0.0 ? cosine / kPi : 0.0;
-        double pdf_value = 0.5 * light_pdf + 0.5 * cosine_pdf;        // pdf.rs:143-145
-        double spdf = fmax(dot(rec.normal, unit), 0.0) / kPi;          // mat.rs:246-249
-        factor = (attenuation * spdf) / pdf_value;                     // main.rs:97
+        double pdf_value = 0.5 * light_pdf + 0.5 * cosine_pdf;  // pdf.rs:143-145
+        double spdf = fmax(dot(rec.normal, unit), 0.0) / kPi;    // mat.rs:246-249
+        factor = (attenuation * spdf) / pdf_value;               // main.rs:97
     }
     ps.beta = ps.beta * factor;
     ps.ray.o = rec.p;
