@@ -267,6 +267,18 @@ struct Builder {
     }
 };
 
+// f64 -> f32 rounded toward -inf / +inf (the node boxes may only grow)
+float f32_down(double x) {
+    float f = (float)x;
+    if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+    return f;
+}
+float f32_up(double x) {
+    float f = (float)x;
+    if ((double)f < x) f = std::nextafterf(f, INFINITY);
+    return f;
+}
+
 // Builds the BVH of prims[first, first+count) (reordering them) and appends the
 // nodes, breadth-first, to out.nodes.  Returns the root node index.
 int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
@@ -312,10 +324,10 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
         DBvhNode &dn = out.nodes[base + h];
         const Box &b0 = b.nodes[n.left].box, &b1 = b.nodes[n.right].box;
         for (int a = 0; a < 3; ++a) {
-            dn.lo0[a] = b0.lo[a];
-            dn.hi0[a] = b0.hi[a];
-            dn.lo1[a] = b1.lo[a];
-            dn.hi1[a] = b1.hi[a];
+            dn.lo0[a] = f32_down(b0.lo[a]);
+            dn.hi0[a] = f32_up(b0.hi[a]);
+            dn.lo1[a] = f32_down(b1.lo[a]);
+            dn.hi1[a] = f32_up(b1.hi[a]);
         }
         dn.child0 = encode(n.left);
         dn.child1 = encode(n.right);

@@ -24,7 +24,10 @@ __device__ __forceinline__ bool item_pixel(const RenderParams &P, uint64_t lin, 
     return i < P.width && row < P.height;
 }
 
-__global__ void __launch_bounds__(kRenderBlock)
+#ifndef RT_MIN_BLOCKS
+#define RT_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(kRenderBlock, RT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
               const __grid_constant__ RenderParams P, double *__restrict__ planes,
               unsigned long long *__restrict__ counters) {

@@ -8,7 +8,10 @@
 
 namespace rtb200dev {
 
-constexpr int kRenderBlock = 128;
+#ifndef RT_RENDER_BLOCK
+#define RT_RENDER_BLOCK 128
+#endif
+constexpr int kRenderBlock = RT_RENDER_BLOCK;
 
 enum Counter : int { kCounterWork = 0, kCounterPaths = 1, kCounterRays = 2, kCounterNonFinite = 3, kNumCounters = 4 };
 

@@ -63,10 +63,14 @@ struct alignas(16) DGroup {
     double bmin[3], bmax[3];  // conservative bounds in the space the ray is given in (culling only)
 };
 
-// Two child boxes per node.  child >= 0: inner node; child < 0: leaf, ~child = (first_prim << 3) | (count-1).
+// Two child boxes per node, 64 bytes = four 128-bit loads.  child >= 0: inner node; child < 0:
+// leaf, ~child = (first_prim << 3) | (count-1).  The boxes only cull, so they are fp32: each
+// bound is the f64 bound rounded OUTWARD, which together with the traversal's rounded-up /
+// rounded-down ray origin and its relative slack on the slab distances (trace.cuh slab2f) can
+// only make a box larger than the f64 box, never smaller.
 struct alignas(16) DBvhNode {
-    double lo0[3], hi0[3];
-    double lo1[3], hi1[3];
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
     int32_t child0, child1;
     int32_t pad0, pad1;
 };

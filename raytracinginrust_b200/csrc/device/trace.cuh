@@ -327,48 +327,88 @@ RT_DEV bool slab(V3 o, V3 inv, const double *lo, const double *hi, double t_min,
     return tin <= tout;
 }
 
-// g.bvh_root >= 0: a BVH node; < 0: the whole (small) group encoded as one leaf — one code path.
+// ---- fp32 node boxes: conservative by construction --------------------------------------
+// The f64 ray is carried as o_up = round_up(o), o_dn = round_down(o) and inv ~ 1/d:
+//   (lo' - o_up) <= lo - o   and   (hi' - o_dn) >= hi - o      (lo', hi' are rounded outward),
+// so whichever of the two products is the near/far plane for the sign of d, the near distance is
+// under- and the far distance over-estimated up to the rounding of the subtraction, of inv and of
+// the product (a few 2^-24 relative), which the 2^-19 relative slack below dominates.
+struct FRay {
+    float oux, ouy, ouz, odx, ody, odz, ix, iy, iz;
+};
+RT_DEV FRay make_fray(const SRay &r) {
+    FRay f;
+    f.oux = __double2float_ru(r.o.x); f.ouy = __double2float_ru(r.o.y); f.ouz = __double2float_ru(r.o.z);
+    f.odx = __double2float_rd(r.o.x); f.ody = __double2float_rd(r.o.y); f.odz = __double2float_rd(r.o.z);
+    // 1/d in fp32 (d == 0 -> +-inf: that axis then only rejects rays that start outside its slab)
+    f.ix = __frcp_rn(__double2float_rn(r.d.x)); f.iy = __frcp_rn(__double2float_rn(r.d.y)); f.iz = __frcp_rn(__double2float_rn(r.d.z));
+    return f;
+}
+RT_DEV bool slab2f(const FRay &f, float lx, float ly, float lz, float hx, float hy, float hz, float t_min, float t_max,
+                   float &t_entry) {
+    const float kSlack = 1.9073486328125e-06f;  // 2^-19
+    float ax = (lx - f.oux) * f.ix, bx = (hx - f.odx) * f.ix;
+    float ay = (ly - f.ouy) * f.iy, by = (hy - f.ody) * f.iy;
+    float az = (lz - f.ouz) * f.iz, bz = (hz - f.odz) * f.iz;
+    float tin = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+    float tout = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+    tin = fmaxf(fmaf(-fabsf(tin), kSlack, tin), t_min);
+    tout = fminf(fmaf(fabsf(tout), kSlack, tout), t_max);
+    t_entry = tin;
+    return tin <= tout;
+}
+
+// g.bvh_root >= 0: a BVH node; < 0: a leaf code (a small group is a single leaf).  "while-while"
+// traversal: every lane first descends inner nodes until it holds a leaf (or is done), then the
+// leaves are tested together, which keeps the warp together in both phases.
 RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double t_min, Best &best) {
+    const int kDone = (int)0x80000000;
     int stack[kStackSize];
     int sp = 0;
     int node = g.bvh_root;
-    for (;;) {
-        if (node >= 0) {
-            const DBvhNode &n = sc.nodes[node];
-            double e0, e1;
-            bool h0 = slab(r.o, r.inv, n.lo0, n.hi0, t_min, best.t, e0);
-            bool h1 = slab(r.o, r.inv, n.lo1, n.hi1, t_min, best.t, e1);
+    FRay f;
+    float t_min_f = 0.f, t_max_f = 0.f;
+    if (node >= 0) {
+        f = make_fray(r);
+        t_min_f = __double2float_rd(t_min);
+        t_max_f = __double2float_ru(best.t);
+    }
+    while (node != kDone) {
+        while (node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+            float e0, e1;
+            bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
+            bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
             if (h0 && h1) {
-                int near_c = n.child0, far_c = n.child1;
-                if (e1 < e0) {
-                    near_c = n.child1;
-                    far_c = n.child0;
-                }
+                bool swap = e1 < e0;
+                int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
                 if (sp < kStackSize) stack[sp++] = far_c;
                 node = near_c;
-                continue;
+            } else if (h0) {
+                node = ch.x;
+            } else if (h1) {
+                node = ch.y;
+            } else {
+                node = sp ? stack[--sp] : kDone;
             }
-            if (h0) {
-                node = n.child0;
-                continue;
-            }
-            if (h1) {
-                node = n.child1;
-                continue;
-            }
-        } else {
+        }
+        if (node != kDone) {
             uint32_t code = ~(uint32_t)node;
             uint32_t first = code >> 3, count = (code & 7u) + 1u;
+            double before = best.t;
             for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, best);
+            if (best.t != before) t_max_f = __double2float_ru(best.t);
+            node = sp ? stack[--sp] : kDone;
         }
-        if (sp == 0) break;
-        node = stack[--sp];
     }
 }
 
 // Closest hit over a sub-scene (a range of groups) for the ray given in the outermost space.
 RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
                          Best &best) {
+#pragma unroll 1
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const DGroup &g = sc.groups[first_group + gi];
         double e;
@@ -566,6 +606,7 @@ RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &re
     double t1 = 0.0;
     bool have_t1 = false;
     const uint32_t nq = 1u + (WITH_MEDIA ? 2u * sc.n_media : 0u);
+#pragma unroll 1
     for (uint32_t q = 0; q < nq; ++q) {
         uint32_t fg = 0, ng = sc.n_world_groups, mi = 0;
         double t_min = kTMin;
