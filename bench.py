@@ -70,9 +70,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -82,7 +82,10 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for ts, r in self.rows if (t_begin is None or ts >= t_begin) and (t_end is None or ts <= t_end + 0.15)]
+        if not rows:  # window shorter than the sampling period: use everything collected while the GPU was busy
+            rows = [r for _, r in self.rows]
+        for r in rows:
             if len(r) < 7:
                 continue
             try:
@@ -215,6 +218,7 @@ def main():
         if dist is not None:
             dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi takes ~1 s to come up
     for _ in range(args.warmup):
         flush.fill_(1)
         step()
@@ -222,7 +226,7 @@ def main():
             scene.render_wait()
     barrier()
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_begin = time.time()
     step_ms, kern_ms, paths, rays = [], [], 0, 0
     for _ in range(args.steps):
         flush.fill_(0)  # L2 flush between timed steps
@@ -239,7 +243,10 @@ def main():
             paths += st.paths
             rays += st.rays
     barrier()
-    clocks = sampler.stop() if sampler else None
+    t_end = time.time()
+    if sampler and t_end - t_begin < 1.0:
+        time.sleep(0.3)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
 
     t = torch.tensor(step_ms, dtype=torch.float64, device="cuda")
     cnt = torch.tensor([paths, rays], dtype=torch.float64, device="cuda")

@@ -5,6 +5,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -48,6 +49,7 @@ struct RtScene {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int render_blocks = 0;
+    int render_variant = 0;
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
     size_t planes_bytes = 0;
@@ -149,7 +151,7 @@ RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
 RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, float *out_dev, cudaStream_t st) {
     CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * kNumCounters, st));
     CU(cudaEventRecord(s.ev0, st));
-    CU(launch_render(s.ds, cam, P, s.render_blocks, s.planes, s.counters, st));
+    CU(launch_render(s.ds, cam, P, s.render_variant, s.render_blocks, s.planes, s.counters, st));
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaMemcpyAsync(s.counters_host, s.counters, sizeof(unsigned long long) * kNumCounters, cudaMemcpyDeviceToHost, st));
@@ -244,7 +246,10 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
     CU(cudaEventCreate(&s->ev1));
     CU(cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * kNumCounters));
     CU(cudaMallocHost((void **)&s->counters_host, sizeof(unsigned long long) * kNumCounters));
-    CU(render_grid_size(device, &s->render_blocks));
+    // BVH and media scenes are latency-bound in the search: run them with the 64-register build (more warps)
+    s->render_variant = (cs.nodes.empty() && cs.media.empty()) ? 0 : 1;
+    if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) s->render_variant = std::atoi(v) ? 1 : 0;
+    CU(render_grid_size(device, s->render_variant, &s->render_blocks));
     *out_scene = s.release();
     return RT_OK;
 }

@@ -709,8 +709,29 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
         // one or two primitives are cheaper to test than to cull; a BVH culls with its own root boxes
         if (dg.n_prims > 2 && !has_bvh) dg.flags |= GROUP_CULL;
         if (has_bvh && !g.xform.empty()) dg.flags |= GROUP_CULL;
-        for (const DOp &op : g.xform)
-            if (op.kind == OP_ROTATE) dg.flags |= GROUP_ROTATED;
+        double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0};
+        for (const DOp &op : g.xform) {
+            dg.flags |= GROUP_XFORM;
+            if (op.kind == OP_TRANSLATE) {  // p' = p - offset (translate.rs:23)
+                for (int a = 0; a < 3; ++a) T[a] -= op.offset[a];
+            } else if (op.kind == OP_ROTATE) {  // p' = R p (rotate.rs:82-86)
+                dg.flags |= GROUP_ROTATED;
+                int r, a, b;
+                rotate_axes(op.axis, r, a, b);
+                double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+                R[a * 3 + a] = op.cos_theta; R[a * 3 + b] = -op.sin_theta;
+                R[b * 3 + a] = op.sin_theta; R[b * 3 + b] = op.cos_theta;
+                double M2[9], T2[3];
+                for (int i = 0; i < 3; ++i) {
+                    T2[i] = R[i * 3] * T[0] + R[i * 3 + 1] * T[1] + R[i * 3 + 2] * T[2];
+                    for (int j = 0; j < 3; ++j) M2[i * 3 + j] = R[i * 3] * M[j] + R[i * 3 + 1] * M[3 + j] + R[i * 3 + 2] * M[6 + j];
+                }
+                std::memcpy(M, M2, sizeof(M));
+                std::memcpy(T, T2, sizeof(T));
+            }
+        }
+        std::memcpy(dg.m, M, sizeof(M));
+        std::memcpy(dg.t, T, sizeof(T));
         out.groups.push_back(dg);
     }
     return true;

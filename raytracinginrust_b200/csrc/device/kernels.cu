@@ -24,10 +24,11 @@ __device__ __forceinline__ bool item_pixel(const RenderParams &P, uint64_t lin, 
     return i < P.width && row < P.height;
 }
 
-#ifndef RT_MIN_BLOCKS
-#define RT_MIN_BLOCKS 4
-#endif
-__global__ void __launch_bounds__(kRenderBlock, RT_MIN_BLOCKS)
+// Two register budgets of the same kernel (a launch bound is a compile-time property): flat
+// scenes run best at 128 registers / 4 blocks per SM, BVH scenes at 64 / 8 — the traversal is
+// latency-bound and more resident warps hide more of it (profiles/r1 sweep).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kRenderBlock, MIN_BLOCKS)
 render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
               const __grid_constant__ RenderParams P, double *__restrict__ planes,
               unsigned long long *__restrict__ counters) {
@@ -198,20 +199,23 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-cudaError_t render_grid_size(int device, int *blocks_out) {
+// variant 0: 128 registers (4 blocks/SM); variant 1: 64 registers (8 blocks/SM)
+cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
     int sms = 0, per_sm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel, kRenderBlock, 0);
+    if (variant == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<4>, kRenderBlock, 0);
+    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<8>, kRenderBlock, 0);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     *blocks_out = sms * per_sm;  // persistent: exactly one resident wave
     return cudaSuccess;
 }
 
-cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int blocks, double *planes,
-                          unsigned long long *counters, cudaStream_t stream) {
-    render_kernel<<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
+cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int variant, int blocks,
+                          double *planes, unsigned long long *counters, cudaStream_t stream) {
+    if (variant == 0) render_kernel<4><<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
+    else render_kernel<8><<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
     return cudaGetLastError();
 }
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,

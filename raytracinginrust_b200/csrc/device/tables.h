@@ -51,6 +51,7 @@ struct DChain {
 enum GroupFlags : uint32_t {
     GROUP_CULL = 1,     // test the group's outer-space bounds before transforming the ray
     GROUP_ROTATED = 2,  // the chain rotates: the reciprocal direction must be recomputed
+    GROUP_XFORM = 4,    // the chain moves the ray at all (else the group lives in the outer space)
 };
 
 struct alignas(16) DGroup {
@@ -61,6 +62,9 @@ struct alignas(16) DGroup {
     uint32_t flags;       // GroupFlags
     uint32_t pad0, pad1, pad2;
     double bmin[3], bmax[3];  // conservative bounds in the space the ray is given in (culling only)
+    // SEARCH only: the chain composed into one affine map, object = m * outer + t (row-major m).
+    // The winner is re-derived op by op in reference arithmetic (chain_ray).
+    double m[9], t[3];
 };
 
 // Two child boxes per node, 64 bytes = four 128-bit loads.  child >= 0: inner node; child < 0:

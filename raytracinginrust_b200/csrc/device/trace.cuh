@@ -419,10 +419,16 @@ RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_grou
         r.d = ray.d;
         r.time = ray.time;
         r.inv = inv;
-        DChain c = sc.chains[g.chain];
-        if (c.n_ops) {
-            chain_ray(sc, c.first_op, c.n_ops, r.o, r.d);
-            if (g.flags & GROUP_ROTATED) r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
+        if (g.flags & GROUP_XFORM) {  // search-grade: one composed affine map instead of the op chain
+            const double *m = g.m;
+            V3 o = ray.o, d = ray.d;
+            r.o = mk(fma(m[0], o.x, fma(m[1], o.y, fma(m[2], o.z, g.t[0]))), fma(m[3], o.x, fma(m[4], o.y, fma(m[5], o.z, g.t[1]))),
+                     fma(m[6], o.x, fma(m[7], o.y, fma(m[8], o.z, g.t[2]))));
+            if (g.flags & GROUP_ROTATED) {
+                r.d = mk(fma(m[0], d.x, fma(m[1], d.y, m[2] * d.z)), fma(m[3], d.x, fma(m[4], d.y, m[5] * d.z)),
+                         fma(m[6], d.x, fma(m[7], d.y, m[8] * d.z)));
+                r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
+            }
         }
         trace_group(sc, g, r, t_min, best);
     }
