@@ -315,10 +315,17 @@ def main():
     kern_s = (sum(kern_ms) / len(kern_ms)) * 1e-3 if kern_ms else None
     segs_per_launch = (rays / len(kern_ms)) if kern_ms else 0.0
     roofline = roofline64 = None
+    traffic = None  # dram__bytes_read+write of render_kernel per launch, from the committed ncu capture of this command
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["render_kernel"]
+        if tr["scene"] == args.workload and tr["spp"] == spp and tr["n_gpus"] == world:
+            traffic = tr["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     if kern_s and bytes_seg is not None:
         achieved = bytes_seg * segs_per_launch / kern_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": None, "peak_source": hbm_src, "kernel": "render_kernel",
+                    "traffic": traffic, "peak_source": hbm_src, "kernel": "render_kernel",
                     "algorithmic_bytes_per_segment": bytes_seg, "segments_per_launch": segs_per_launch,
                     "kernel_ms": kern_s * 1e3,
                     "note": "megakernel: no ray queues (Q=0); the scene tables are cache-resident, so measured DRAM "
