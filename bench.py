@@ -193,6 +193,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     hs = rt.HostScene(args.workload)
