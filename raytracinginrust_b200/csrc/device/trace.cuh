@@ -860,11 +860,19 @@ struct PathState {
 
 // One call of ray_color (one segment).  Returns false when the path ended.
 //   recursion:  L = emitted + f * L_next      iteration:  radiance += beta*emitted ; beta *= f
+RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags);
+
 RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint32_t flags) {
     if (ps.depth_left == 0) return false;  // main.rs:42-45: contributes black
     HitRec rec;
     ps.segments += 1;
-    if (!world_hit<true, false>(sc, ps.ray, ps.rng, rec)) {  // main.rs:48,118
+    bool hit = world_hit<true, false>(sc, ps.ray, ps.rng, rec);  // main.rs:48
+    return path_shade(sc, ps, hit, rec, integrator, flags);
+}
+
+// Everything ray_color does after world.hit returned (main.rs:62-119).
+RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags) {
+    if (!hit) {  // main.rs:118
         ps.radiance = ps.radiance + ps.beta * ld3(sc.background);
         return false;
     }
