@@ -189,6 +189,12 @@ typedef struct RtRenderOpts {
  * (src/main.rs:97 evaluates the recursive call even when scattering_pdf == 0).
  * Off by default: the contribution is zero either way. */
 #define RT_FLAG_TRACE_ZERO_THROUGHPUT 1u
+/* Pipeline choice.  Both run the same device arithmetic and give bit-identical images:
+ *   wavefront  - generate / extend / shade stages over HBM-resident ray queues
+ *   megakernel - one persistent kernel, one path per lane, the path state in registers
+ * With neither flag the library picks per scene (DESIGN.md "Kernels"). */
+#define RT_FLAG_WAVEFRONT 2u
+#define RT_FLAG_MEGAKERNEL 4u
 
 typedef struct RtStats {
     uint64_t paths;             /* (pixel, sample) paths started                        */

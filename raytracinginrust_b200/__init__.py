@@ -22,7 +22,7 @@ from ._abi import (RtCamera, RtHit, RtImage, RtMaterial, RtNode, RtPerlin, RtRay
                    RtTexture, HIT_DTYPE, RAY_DTYPE, INTEGRATOR_HEAD, INTEGRATOR_LEGACY)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+LIB_DIR = os.environ.get("RTB200_LIB_DIR") or os.path.join(_HERE, "lib")  # override: tuning sweeps over prebuilt variants
 REPO_ROOT = os.path.dirname(_HERE)
 ASSETS_DIR = os.path.join(REPO_ROOT, "assets")
 

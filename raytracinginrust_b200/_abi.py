@@ -23,6 +23,8 @@ MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = ra
 TEX_CONSTANT, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 INTEGRATOR_HEAD, INTEGRATOR_LEGACY = 0, 1
 FLAG_TRACE_ZERO_THROUGHPUT = 1
+FLAG_WAVEFRONT = 2   # generate / extend / shade stages over HBM-resident ray queues
+FLAG_MEGAKERNEL = 4  # one persistent kernel, path state in registers
 
 
 class RtNode(C.Structure):

@@ -14,6 +14,7 @@
 #include "../../../include/rtb200.h"
 #include "compile.h"
 #include "kernels.h"
+#include "wavefront.h"
 
 using namespace rtb200dev;
 
@@ -57,6 +58,13 @@ struct RtScene {
     size_t out_bytes = 0;
     unsigned long long *counters = nullptr;
     unsigned long long *counters_host = nullptr;  // pinned
+    // wavefront pipeline: path pool + queues, allocated on first use
+    WfPool wf{};
+    std::vector<void *> wf_allocations;
+    unsigned *wf_status_host = nullptr;  // pinned
+    int sms = 148;
+    bool has_media = false;
+    bool wavefront_default = false;
     // last async render
     bool pending = false;
     cudaStream_t pending_stream = nullptr;
@@ -70,6 +78,8 @@ struct RtScene {
         if (out_dev) cudaFree(out_dev);
         if (counters) cudaFree(counters);
         if (counters_host) cudaFreeHost(counters_host);
+        for (void *p : wf_allocations) cudaFree(p);
+        if (wf_status_host) cudaFreeHost(wf_status_host);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -90,13 +100,35 @@ RtStatus upload(RtScene &s, const std::vector<T> &v, const T *&dev) {
     return RT_OK;
 }
 
+uint32_t wf_pool_capacity() {
+    if (const char *v = std::getenv("RTB200_WF_POOL")) {
+        long long n = std::atoll(v);
+        if (n >= 1024 && n <= (1ll << 26)) return (uint32_t)n;
+    }
+    return 1u << 22;  // 4 Mi slots (640 MB): per-round fixed costs and the extend tail amortise; measured best of 128 Ki..4 Mi
+}
+
+// Which pipeline a render runs: the flags win, then RTB200_PIPELINE, then the scene's default.
+bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_depth) {
+    if (max_depth == 0) return false;  // nothing to trace: the megakernel returns black
+    uint32_t flags = opts ? opts->flags : 0u;
+    if (flags & RT_FLAG_WAVEFRONT) return true;
+    if (flags & RT_FLAG_MEGAKERNEL) return false;
+    if (const char *v = std::getenv("RTB200_PIPELINE")) {
+        if (!std::strcmp(v, "wavefront")) return true;
+        if (!std::strcmp(v, "megakernel")) return false;
+    }
+    return s.wavefront_default;
+}
+
 RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-                     const RtRenderOpts *opts, RenderParams &P) {
+                     const RtRenderOpts *opts, bool wavefront, RenderParams &P) {
     if (width < 2 || height < 2) return fail(RT_ERR_BAD_ARGUMENT, "width and height must be at least 2 (main.rs:817-818 divides by W-1, H-1)");
     if ((uint64_t)width * height > (1ull << 31)) return fail(RT_ERR_BAD_ARGUMENT, "image too large");
     RtRenderOpts o{};
     if (opts) o = *opts;
     if (o.integrator > RT_INTEGRATOR_LEGACY) return fail(RT_ERR_BAD_ARGUMENT, "unknown integrator");
+    if ((o.flags & RT_FLAG_WAVEFRONT) && (o.flags & RT_FLAG_MEGAKERNEL)) return fail(RT_ERR_BAD_ARGUMENT, "RT_FLAG_WAVEFRONT and RT_FLAG_MEGAKERNEL exclude each other");
     if (o.integrator == RT_INTEGRATOR_HEAD && s.n_lights == 0)
         return fail(RT_ERR_NO_LIGHTS, "HEAD integrator needs a non-empty light list (reference: unwrap() panic at hit.rs:94-96)");
     uint32_t begin = o.sample_begin;
@@ -115,10 +147,14 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.tiles_x = (width + 7) / 8;
     P.tiles_y = (height + 3) / 4;
     P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
-    // enough items that the tail of the persistent grid is a small fraction of the run
-    uint64_t resident = (uint64_t)(s.render_blocks > 0 ? s.render_blocks : 148) * kRenderBlock;
-    uint64_t target_items = resident * 64ull;
+    // Enough (chunk, pixel) items that the tail of the persistent grid / of the wavefront pool is a
+    // small fraction of the run.  The partition depends only on the image and the sample range, not
+    // on the pipeline or the GPU, so the f64 summation order - and with it every bit of the image -
+    // is the same whichever way it is rendered.
+    uint64_t target_items = 1ull << 26;
     uint64_t chunks = (target_items + P.items_per_chunk - 1) / P.items_per_chunk;
+    uint64_t plane_cap = (4ull << 30) / ((uint64_t)width * height * 3 * sizeof(double));  // at most 4 GiB of planes
+    if (chunks > plane_cap) chunks = plane_cap;
     if (chunks < 1) chunks = 1;
     if (chunks > count) chunks = count;
     if (chunks > 256) chunks = 256;
@@ -148,14 +184,71 @@ RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
     return RT_OK;
 }
 
-RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, float *out_dev, cudaStream_t st) {
+template <class T>
+RtStatus wf_alloc(RtScene &s, T *&ptr, size_t count) {
+    void *p = nullptr;
+    CU(cudaMalloc(&p, count * sizeof(T)));
+    s.wf_allocations.push_back(p);
+    ptr = (T *)p;
+    return RT_OK;
+}
+
+RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
+    const uint32_t cap = wf_pool_capacity();
+    if (s.wf.capacity != cap) {
+        for (void *p : s.wf_allocations) cudaFree(p);
+        s.wf_allocations.clear();
+        s.wf = WfPool{};
+        WfPool w{};
+#define WA(field, count)                              \
+    do {                                              \
+        RtStatus a__ = wf_alloc(s, w.field, (count)); \
+        if (a__ != RT_OK) return a__;                 \
+    } while (0)
+        WA(slots, cap); WA(sum, cap); WA(ctl, 1);
+#undef WA
+        w.capacity = cap;
+        s.wf = w;
+        if (!s.wf_status_host) CU(cudaMallocHost((void **)&s.wf_status_host, sizeof(unsigned)));
+    }
+    // never more slots than there are work items
+    uint64_t items = (uint64_t)P.width * P.height * P.n_chunks;
+    s.wf.n_slots = (uint32_t)(items < cap ? items : cap);
+    return RT_OK;
+}
+
+// The wavefront pipeline: rounds of shade / generate / extend / control until no path is alive.
+// The number of rounds depends on the paths, so the host reads the live count back every few
+// rounds (an empty round is four kernels that find nothing to do).
+RtStatus run_wavefront(RtScene &s, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
+    const int kRoundsPerCheck = 8;
+    CU(wf_launch_init(s.wf, st));
+    s.pending_launches += 1;
+    for (;;) {
+        for (int k = 0; k < kRoundsPerCheck; ++k) CU(wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, st));
+        s.pending_launches += (uint64_t)kRoundsPerCheck * kWfLaunchesPerRound;
+        CU(cudaMemcpyAsync(s.wf_status_host, &s.wf.ctl->status_live, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*s.wf_status_host == 0u) break;
+    }
+    return RT_OK;
+}
+
+RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, bool wavefront, float *out_dev, cudaStream_t st) {
     CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * kNumCounters, st));
     CU(cudaEventRecord(s.ev0, st));
-    CU(launch_render(s.ds, cam, P, s.render_variant, s.render_blocks, s.planes, s.counters, st));
+    s.pending_launches = 0;
+    if (wavefront) {
+        RtStatus w = run_wavefront(s, cam, P, st);
+        if (w != RT_OK) return w;
+    } else {
+        CU(launch_render(s.ds, cam, P, s.render_variant, s.render_blocks, s.planes, s.counters, st));
+        s.pending_launches += 1;
+    }
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaMemcpyAsync(s.counters_host, s.counters, sizeof(unsigned long long) * kNumCounters, cudaMemcpyDeviceToHost, st));
-    s.pending_launches = 2;
+    s.pending_launches += 1;
     return RT_OK;
 }
 
@@ -250,6 +343,12 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
     s->render_variant = (cs.nodes.empty() && cs.media.empty()) ? 0 : 1;
     if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) s->render_variant = std::atoi(v) ? 1 : 0;
     CU(render_grid_size(device, s->render_variant, &s->render_blocks));
+    CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
+    s->has_media = !cs.media.empty();
+    // Measured per scene class (profiles/r1_e_pipeline_ab.md): the wavefront stages beat the megakernel
+    // only where world.hit is a long chain of queries - media over BVH scenes (the Next Week final
+    // scene, +21 %); flat scenes and plain BVH scenes run faster with the path state in registers.
+    s->wavefront_default = !cs.media.empty() && !cs.nodes.empty();
     *out_scene = s.release();
     return RT_OK;
 }
@@ -265,11 +364,13 @@ RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t
     s.t_call0 = now_ms();
     CU(cudaSetDevice(s.device));
     RenderParams P;
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    const bool wavefront = use_wavefront(s, opts, max_depth);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, wavefront, P);
     if (st != RT_OK) return st;
     st = ensure_scratch(s, P, false);
+    if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
     if (st != RT_OK) return st;
-    st = enqueue_render(s, *camera, P, out_rgb_sum_device, (cudaStream_t)cuda_stream);
+    st = enqueue_render(s, *camera, P, wavefront, out_rgb_sum_device, (cudaStream_t)cuda_stream);
     if (st != RT_OK) return st;
     s.pending = true;
     s.pending_stream = (cudaStream_t)cuda_stream;
@@ -292,11 +393,13 @@ RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width,
     s.t_call0 = now_ms();
     CU(cudaSetDevice(s.device));
     RenderParams P;
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    const bool wavefront = use_wavefront(s, opts, max_depth);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, wavefront, P);
     if (st != RT_OK) return st;
     st = ensure_scratch(s, P, true);
+    if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
     if (st != RT_OK) return st;
-    st = enqueue_render(s, *camera, P, s.out_dev, s.stream);
+    st = enqueue_render(s, *camera, P, wavefront, s.out_dev, s.stream);
     if (st != RT_OK) return st;
     size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
     CU(cudaMemcpyAsync(out_rgb_sum, s.out_dev, out_bytes, cudaMemcpyDeviceToHost, s.stream));

@@ -14,16 +14,6 @@
 
 namespace rtb200dev {
 
-// pixel order inside the item space: 8x4 tiles so that the 32 lanes of a warp start
-// on neighbouring pixels (coherent primary rays and BVH paths)
-__device__ __forceinline__ bool item_pixel(const RenderParams &P, uint64_t lin, uint32_t &i, uint32_t &row) {
-    uint32_t tile = (uint32_t)(lin >> 5), within = (uint32_t)(lin & 31u);
-    uint32_t tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-    i = tx * 8u + (within & 7u);
-    row = ty * 4u + (within >> 3);
-    return i < P.width && row < P.height;
-}
-
 // Two register budgets of the same kernel (a launch bound is a compile-time property): flat
 // scenes run best at 128 registers / 4 blocks per SM, BVH scenes at 64 / 8 — the traversal is
 // latency-bound and more resident warps hide more of it (profiles/r1 sweep).
@@ -54,7 +44,7 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
                     if (item >= P.n_items) break;
                     uint32_t chunk = (uint32_t)(item / P.items_per_chunk);
                     uint64_t lin = item - (uint64_t)chunk * P.items_per_chunk;
-                    if (!item_pixel(P, lin, i, row)) continue;
+                    if (!item_pixel(P.tiles_x, P.width, P.height, lin, i, row)) continue;
                     s = P.sample_begin + chunk * P.chunk_size;
                     s_end = min(s + P.chunk_size, P.sample_end);
                     slot = (uint64_t)chunk * P.width * P.height + (uint64_t)row * P.width + i;

@@ -26,7 +26,7 @@
 namespace rtb200dev {
 
 #define RT_DEV __device__ __forceinline__
-#define RT_DEV_COLD __device__ __noinline__
+#define RT_DEV_COLD static __device__ __noinline__
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
@@ -958,6 +958,16 @@ RT_DEV void path_begin(PathState &ps, const RtCamera &cam, uint32_t width, uint3
     ps.radiance = mk(0.0, 0.0, 0.0);
     ps.depth_left = max_depth;
     ps.segments = 0;
+}
+
+// pixel order inside the item space: 8x4 tiles so that the 32 lanes of a warp start
+// on neighbouring pixels (coherent primary rays and BVH paths)
+__device__ __forceinline__ bool item_pixel(uint32_t tiles_x, uint32_t width, uint32_t height, uint64_t lin, uint32_t &i, uint32_t &row) {
+    uint32_t tile = (uint32_t)(lin >> 5), within = (uint32_t)(lin & 31u);
+    uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
+    i = tx * 8u + (within & 7u);
+    row = ty * 4u + (within >> 3);
+    return i < width && row < height;
 }
 
 }  // namespace rtb200dev

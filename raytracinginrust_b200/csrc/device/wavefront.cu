@@ -1,0 +1,544 @@
+// wavefront.cu — the sample loop of src/main.rs:772-834 as a wavefront pipeline (sm_100a).
+//
+// The recursion of ray_color (src/main.rs:41-120) is cut at its one recursive call: a path is a
+// slot of an HBM-resident pool (wavefront.h), and a round moves every live path forward by one
+// segment with three stage kernels:
+//
+//   shade     (main.rs:62-119)  reads the slot's ray + what extend found, resolves the hit record,
+//                               evaluates the material, writes the next ray or ends the path
+//   generate  (main.rs:811-820) gives every slot whose path ended its next sample (or its next
+//                               (chunk, pixel) work item) and writes the camera ray
+//   extend    (main.rs:48)      world.hit for every live slot: persistent warps that pull slots
+//                               from a cursor and REPLACE a finished ray by the next slot while the
+//                               other lanes are still traversing (idle lanes are compacted onto the
+//                               reserved range with __ballot_sync/__popc)
+//   control                     one thread: round bookkeeping, loop condition
+//
+// All arithmetic is the device code of trace.cuh, shared with the megakernel; a slot runs the
+// samples of its item in sample order into an f64 sum of its own, so the image is bit-identical
+// to the megakernel's and to itself run after run.
+#include <cuda_runtime.h>
+
+#include "trace.cuh"
+#include "wavefront.h"
+
+namespace rtb200dev {
+
+#ifndef RT_WF_REFILL_THRESHOLD
+#define RT_WF_REFILL_THRESHOLD 24
+#endif
+#ifndef RT_WF_INNER_THRESHOLD
+#define RT_WF_INNER_THRESHOLD 12
+#endif
+#ifndef RT_WF_EXTEND_MIN_BLOCKS
+#define RT_WF_EXTEND_MIN_BLOCKS 4
+#endif
+#ifndef RT_WF_SHADE_MIN_BLOCKS
+#define RT_WF_SHADE_MIN_BLOCKS 4
+#endif
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+size_t wf_bytes_per_slot() { return sizeof(WfSlot) + sizeof(double4); }
+
+// 128-bit views of a slot record
+__device__ __forceinline__ const double2 *slot_d2(const WfPool &pool, uint32_t slot) { return reinterpret_cast<const double2 *>(pool.slots + slot); }
+__device__ __forceinline__ double2 *slot_d2w(const WfPool &pool, uint32_t slot) { return reinterpret_cast<double2 *>(pool.slots + slot); }
+__device__ __forceinline__ uint4 ld_u4(const double2 *p) { return *reinterpret_cast<const uint4 *>(p); }
+__device__ __forceinline__ void st_u4(double2 *p, uint4 v) { *reinterpret_cast<uint4 *>(p) = v; }
+__device__ __forceinline__ uint4 pack_time_state(double time, uint32_t state, uint32_t depth_left) {
+    return make_uint4((uint32_t)__double2loint(time), (uint32_t)__double2hiint(time), state, depth_left);
+}
+__device__ __forceinline__ uint4 pack_bz_keys(double bz, uint32_t rng_pixel, uint32_t sample) {
+    return make_uint4((uint32_t)__double2loint(bz), (uint32_t)__double2hiint(bz), rng_pixel, sample);
+}
+__device__ __forceinline__ double unpack_lo_double(uint4 v) { return __hiloint2double((int)v.y, (int)v.x); }
+
+// Block-wide sum of a per-thread count, then ONE fire-and-forget atomic per block.
+__device__ __forceinline__ void block_count_add(unsigned *dst, unsigned mine, unsigned long long *dst64 = nullptr) {
+    __shared__ unsigned s_total;
+    if (threadIdx.x == 0) s_total = 0u;
+    __syncthreads();
+    const unsigned w = __reduce_add_sync(kFull, mine);
+    if ((threadIdx.x & 31u) == 0u && w) atomicAdd(&s_total, w);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_total) {
+        atomicAdd(dst, s_total);
+        if (dst64) atomicAdd(dst64, (unsigned long long)s_total);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// init: every slot is empty and asks generate for an item
+// ---------------------------------------------------------------------------
+__global__ void wf_init_kernel(const __grid_constant__ WfPool pool) {
+    unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned stride = gridDim.x * blockDim.x;
+    if (k == 0) {
+        WfCtl c{};
+        c.status_live = 1;
+        *pool.ctl = c;
+    }
+    for (; k < pool.n_slots; k += stride) {
+        double2 *u = slot_d2w(pool, k);
+        st_u4(u + 3, pack_time_state(0.0, WF_REGEN, 0u));
+        st_u4(u + 5, pack_bz_keys(0.0, 0u, 0u));
+        st_u4(u + 7, make_uint4(0u, 0u, kWfNoItem, 0u));  // no item: sample + 1 >= s_end
+        pool.sum[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// shade: everything ray_color does after world.hit returned (main.rs:62-119)
+// ---------------------------------------------------------------------------
+// One slot per thread: the stage's cost is the latency of the slot record, which only
+// parallelism hides.
+__global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
+wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams P,
+                const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
+    const unsigned cur = pool.ctl->round & 1u;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false, bad = false;
+    if (slot < pool.n_slots) {
+        const double2 *u = slot_d2(pool, slot);
+        const uint4 u3 = ld_u4(u + 3);
+        if (u3.z == WF_LIVE) {
+            const double2 u0 = u[0], u1 = u[1], u2 = u[2], u4 = u[4];
+            const uint4 u5 = ld_u4(u + 5), u6 = ld_u4(u + 6);
+            PathState ps;
+            ps.ray.o = mk(u0.x, u0.y, u1.x);
+            ps.ray.d = mk(u1.y, u2.x, u2.y);
+            ps.ray.time = unpack_lo_double(u3);
+            ps.beta = mk(u4.x, u4.y, unpack_lo_double(u5));
+            ps.radiance = mk(0.0, 0.0, 0.0);  // non-zero only at the segment that ends the path
+            ps.rng = Rng{P.seed, u5.z, u5.w, P.max_depth - u3.w};
+            ps.depth_left = u3.w;
+            ps.segments = 0;
+            const uint32_t prim = u6.x;
+            const double t = __hiloint2double((int)u6.w, (int)u6.z);
+            HitRec rec;
+            const bool hit = prim != kNoPrim;
+            if (hit) {
+                Best win{t, prim, 0u, (int)u6.y};
+                if (prim & kMediumFlag) resolve_medium(sc, ps.ray, win, t, rec);
+                else resolve_hit<false>(sc, ps.ray, win, t, rec);
+            }
+            alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
+            double2 *w = slot_d2w(pool, slot);
+            if (alive) {
+                w[0] = make_double2(ps.ray.o.x, ps.ray.o.y);
+                w[1] = make_double2(ps.ray.o.z, ps.ray.d.x);
+                w[2] = make_double2(ps.ray.d.y, ps.ray.d.z);
+                st_u4(w + 3, make_uint4(u3.x, u3.y, WF_LIVE, ps.depth_left));  // time is inherited (main.rs:95, mat.rs:219,270,368)
+                w[4] = make_double2(ps.beta.x, ps.beta.y);
+                st_u4(w + 5, pack_bz_keys(ps.beta.z, u5.z, u5.w));
+            } else {
+                st_u4(w + 3, make_uint4(u3.x, u3.y, WF_REGEN, 0u));
+                // vec.rs:253-260 Sum, in sample order (the slot runs its samples one after the other)
+                const V3 L = ps.radiance;
+                bad = !(isfinite(L.x) && isfinite(L.y) && isfinite(L.z));  // §Q10: counted, not guarded
+                if (L.x != 0.0 || L.y != 0.0 || L.z != 0.0) {              // x + 0 == x
+                    double4 s = pool.sum[slot];
+                    s.x += L.x;
+                    s.y += L.y;
+                    s.z += L.z;
+                    pool.sum[slot] = s;
+                }
+            }
+        }
+    }
+    block_count_add(&pool.ctl->live[cur], alive ? 1u : 0u);
+    if (__syncthreads_or(bad)) {
+        const unsigned nb = __popc(__ballot_sync(kFull, bad));
+        if ((threadIdx.x & 31u) == 0u && nb) atomicAdd(&counters[kCounterNonFinite], (unsigned long long)nb);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// generate: the sample closure of main.rs:811-820 for every slot whose path ended
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWfBlock, 4)
+wf_generate_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__ RenderParams P,
+                   const __grid_constant__ WfPool pool, double *__restrict__ planes,
+                   unsigned long long *__restrict__ counters) {
+    __shared__ unsigned s_need;
+    __shared__ unsigned long long s_first;
+    const unsigned cur = pool.ctl->round & 1u;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t n_pixels = (uint64_t)P.width * P.height;
+    uint32_t rng_pixel = 0, out_pixel = 0, sample = 0, s_end = 0, chunk = kWfNoItem;
+    bool regen = false, have = false, need_item = false;
+    if (threadIdx.x == 0) s_need = 0u;
+    if (slot < pool.n_slots) {
+        const double2 *u = slot_d2(pool, slot);
+        const uint4 u3 = ld_u4(u + 3);
+        regen = u3.z == WF_REGEN;
+        if (regen) {
+            const uint4 u5 = ld_u4(u + 5), u7 = ld_u4(u + 7);
+            rng_pixel = u5.z;
+            sample = u5.w + 1u;
+            out_pixel = u7.x;
+            s_end = u7.y;
+            chunk = u7.z;
+            have = chunk != kWfNoItem && sample < s_end;
+            need_item = !have;
+            if (need_item && chunk != kWfNoItem) {  // the item is complete: its sum goes to its plane slot
+                const double4 s = pool.sum[slot];
+                double *dst = planes + 3 * ((uint64_t)chunk * n_pixels + out_pixel);
+                dst[0] = s.x;
+                dst[1] = s.y;
+                dst[2] = s.z;
+                pool.sum[slot] = make_double4(0.0, 0.0, 0.0, 0.0);
+                chunk = kWfNoItem;
+            }
+        }
+    }
+    // Next (chunk, pixel) items.  First try: one atomic for the whole block - threads that ask
+    // together get consecutive items, i.e. neighbouring pixels of 8x4 tiles.  Items that fall into
+    // the padding of partial tiles are skipped and asked for again, warp by warp.
+    __syncthreads();
+    unsigned my_rank = 0;
+    {
+        const unsigned m = __ballot_sync(kFull, need_item);
+        unsigned wbase = 0;
+        if (lane == 0 && m) wbase = atomicAdd(&s_need, (unsigned)__popc(m));
+        wbase = __shfl_sync(kFull, wbase, 0);
+        my_rank = wbase + __popc(m & ((1u << lane) - 1u));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_need) s_first = atomicAdd(&counters[kCounterWork], (unsigned long long)s_need);
+    __syncthreads();
+    unsigned long long item = s_first + my_rank;
+    for (bool first_try = true;; first_try = false) {
+        if (!first_try) {
+            const unsigned m = __ballot_sync(kFull, need_item);
+            if (m == 0u) break;
+            unsigned long long f = 0;
+            if (lane == 0) f = atomicAdd(&counters[kCounterWork], (unsigned long long)__popc(m));
+            f = __shfl_sync(kFull, f, 0);
+            item = f + __popc(m & ((1u << lane) - 1u));
+        }
+        if (need_item) {
+            if (item >= P.n_items) {
+                need_item = false;  // no work left: the slot retires
+            } else {
+                const uint32_t c = (uint32_t)(item / P.items_per_chunk);
+                const uint64_t lin = item - (uint64_t)c * P.items_per_chunk;
+                uint32_t i, row;
+                if (item_pixel(P.tiles_x, P.width, P.height, lin, i, row)) {
+                    chunk = c;
+                    sample = P.sample_begin + c * P.chunk_size;
+                    s_end = min(sample + P.chunk_size, P.sample_end);
+                    out_pixel = row * P.width + i;
+                    rng_pixel = (P.height - 1u - row) * P.width + i;  // row 0 of the image is j = H-1 (main.rs:772)
+                    have = true;
+                    need_item = false;
+                }
+            }
+        }
+    }
+    if (regen) {
+        double2 *w = slot_d2w(pool, slot);
+        if (have) {
+            const uint32_t row = out_pixel / P.width, i = out_pixel - row * P.width;
+            Rng rng{P.seed, rng_pixel, sample, 0};
+            const Ray r = camera_ray(cam, P.width, P.height, i, P.height - 1u - row, rng);
+            w[0] = make_double2(r.o.x, r.o.y);
+            w[1] = make_double2(r.o.z, r.d.x);
+            w[2] = make_double2(r.d.y, r.d.z);
+            st_u4(w + 3, pack_time_state(r.time, WF_LIVE, P.max_depth));
+            w[4] = make_double2(1.0, 1.0);
+            st_u4(w + 5, pack_bz_keys(1.0, rng_pixel, sample));
+            st_u4(w + 7, make_uint4(out_pixel, s_end, chunk, 0u));
+        } else {
+            st_u4(w + 3, pack_time_state(0.0, WF_EMPTY, 0u));
+            st_u4(w + 7, make_uint4(0u, 0u, kWfNoItem, 0u));
+        }
+    }
+    block_count_add(&pool.ctl->live[cur], have ? 1u : 0u, &counters[kCounterPaths]);
+}
+
+// ---------------------------------------------------------------------------
+// extend: world.hit(ray, 0.00001, inf) (main.rs:48) for every live slot
+// ---------------------------------------------------------------------------
+// The control flow of world_hit / trace_groups / trace_group (trace.cuh) unrolled into a per-lane
+// state machine, so that a lane whose ray is finished takes the next slot instead of waiting for
+// the slowest ray of its warp:
+//   A  refill      idle lanes take the next slots of the warp's reserved range (one global atomic
+//                  per kWfReserve slots; idle lanes are ranked with __ballot_sync/__popc)
+//   B  transition  lanes without a BVH node run world_hit's bookkeeping until they need one:
+//                  next group of the query (cull, transform; a group that is a single leaf is
+//                  scanned right here), query complete (exact_t; medium.rs:32-58), next query,
+//                  result
+//   C  traverse    while-while over BVH nodes and leaves, with votes: stop descending when few
+//                  lanes still hold an inner node, leave when a quarter of the rays wait for B
+#ifndef RT_WF_RESERVE
+#define RT_WF_RESERVE 64
+#endif
+constexpr unsigned kWfReserve = RT_WF_RESERVE;  // slots a warp reserves per global atomic
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(kWfBlock, RT_WF_EXTEND_MIN_BLOCKS)
+wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth) {
+    const int kDone = (int)0x80000000;
+    const unsigned n = pool.n_slots;
+    unsigned *cursor = &pool.ctl->ext_cursor;
+    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    const uint32_t nq = 1u + (MEDIA ? 2u * sc.n_media : 0u);
+
+    unsigned wbase = 0, wend = 0;  // the warp's reserved range of slots
+    bool exhausted = false;
+    bool has_ray = false;
+    uint32_t slot = 0;
+    Ray ray;
+    V3 inv;
+    Rng rng{seed, 0u, 0u, 0u};
+    uint32_t q = 0, gi = 0, g_end = 0;
+    double t_min = kTMin, closest = RT_INF, t1 = 0.0;
+    bool have_t1 = false;
+    Best b{RT_INF, kNoPrim, 0u, 0}, win{RT_INF, kNoPrim, 0u, 0};
+    SRay r;
+    FRay f;
+    float t_min_f = 0.f, t_max_f = 0.f;
+    int node = kDone, sp = 0;
+    int stack[kStackSize];
+    ray.o = ray.d = inv = r.o = r.d = r.inv = mk(0.0, 0.0, 0.0);
+    ray.time = r.time = 0.0;
+    f = FRay{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+
+    for (;;) {
+        // ---- A: refill ----------------------------------------------------------------------
+        const unsigned want = __ballot_sync(kFull, !has_ray);
+        if (want != 0u && !exhausted) {
+            if (wbase == wend) {
+                unsigned got = 0;
+                if (lane == 0) got = atomicAdd(cursor, kWfReserve);
+                got = __shfl_sync(kFull, got, 0);
+                wbase = min(got, n);
+                wend = min(got + kWfReserve, n);
+                exhausted = wbase == wend;
+            }
+            const unsigned avail = wend - wbase;
+            const unsigned rank = __popc(want & lt);
+            if (!has_ray && rank < avail) {
+                const uint32_t cand = wbase + rank;
+                const double2 *u = slot_d2(pool, cand);
+                const uint4 u3 = ld_u4(u + 3);
+                if (u3.z == WF_LIVE) {  // not LIVE only in the tail of a render, when items have run out
+                    slot = cand;
+                    const double2 r0 = u[0], r1 = u[1], r2 = u[2];
+                    ray.o = mk(r0.x, r0.y, r1.x);
+                    ray.d = mk(r1.y, r2.x, r2.y);
+                    ray.time = unpack_lo_double(u3);
+                    if (MEDIA) {
+                        const uint4 u5 = ld_u4(u + 5);
+                        rng.pixel = u5.z;
+                        rng.sample = u5.w;
+                        rng.bounce = max_depth - u3.w;
+                    }
+                    inv = mk(rcp_fast(ray.d.x), rcp_fast(ray.d.y), rcp_fast(ray.d.z));
+                    q = 0;
+                    gi = 0;
+                    g_end = sc.n_world_groups;
+                    t_min = kTMin;
+                    b = Best{RT_INF, kNoPrim, 0u, 0};
+                    win = b;
+                    closest = RT_INF;
+                    have_t1 = false;
+                    node = kDone;
+                    sp = 0;
+                    has_ray = true;
+                }
+            }
+            wbase += min(avail, (unsigned)__popc(want));
+        }
+        const unsigned n_has = __popc(__ballot_sync(kFull, has_ray));
+        if (n_has == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+        // leave the traversal loop once a quarter of the rays in flight wait for a transition
+        const unsigned leave_below = (n_has * (unsigned)RT_WF_REFILL_THRESHOLD) >> 5;
+        const unsigned inner_below = (n_has * (unsigned)RT_WF_INNER_THRESHOLD) >> 5;
+
+        // ---- B: transition ------------------------------------------------------------------
+        if (has_ray && node == kDone) {
+            for (;;) {
+                if (gi < g_end) {  // trace_groups: next group of this query
+                    const DGroup &g = sc.groups[gi++];
+                    double e;
+                    if ((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, t_min, b.t, e)) continue;
+                    r.o = ray.o;
+                    r.d = ray.d;
+                    r.time = ray.time;
+                    r.inv = inv;
+                    if (g.flags & GROUP_XFORM) {
+                        const double *m = g.m;
+                        const V3 o = ray.o, d = ray.d;
+                        r.o = mk(fma(m[0], o.x, fma(m[1], o.y, fma(m[2], o.z, g.t[0]))), fma(m[3], o.x, fma(m[4], o.y, fma(m[5], o.z, g.t[1]))),
+                                 fma(m[6], o.x, fma(m[7], o.y, fma(m[8], o.z, g.t[2]))));
+                        if (g.flags & GROUP_ROTATED) {
+                            r.d = mk(fma(m[0], d.x, fma(m[1], d.y, m[2] * d.z)), fma(m[3], d.x, fma(m[4], d.y, m[5] * d.z)),
+                                     fma(m[6], d.x, fma(m[7], d.y, m[8] * d.z)));
+                            r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
+                        }
+                    }
+                    const int root = g.bvh_root;
+                    if (root < 0) {  // the whole group is one leaf: scan it here, no trip through C
+                        const uint32_t code = ~(uint32_t)root;
+                        const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+                        for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, b);
+                        continue;
+                    }
+                    node = root;
+                    sp = 0;
+                    f = make_fray(r);
+                    t_min_f = __double2float_rd(t_min);
+                    t_max_f = __double2float_ru(b.t);
+                    break;
+                }
+                // world_hit: the query is complete
+                const bool found = b.prim != kNoPrim;
+                const bool second = MEDIA && q > 0u && ((q - 1u) & 1u) != 0u;
+                if (MEDIA && q > 0u && !second) have_t1 = found;
+                if (found) {
+                    const double te = exact_t(sc, ray, b, t_min);
+                    if (q == 0u) {
+                        win = b;
+                        closest = te;
+                    } else if (!second) {
+                        t1 = te;
+                    } else {  // medium.rs:32-58
+                        const uint32_t mi = (q - 1u) >> 1;
+                        const DMedium &m = sc.media[mi];
+                        double h1 = t1, h2 = te;
+                        if (h1 < kTMin) h1 = kTMin;
+                        if (h2 > closest) h2 = closest;
+                        if (h1 < h2) {
+                            V3 o = ray.o, d = ray.d;
+                            DChain c = sc.chains[m.chain];
+                            chain_ray(sc, c.first_op, c.n_ops, o, d);
+                            const double len = length(d);
+                            const double distance_inside_boundary = (h2 - h1) * len;
+                            const Draw dr = draw(rng, SLOT_MEDIUM, (uint32_t)m.node);
+                            const double hit_distance = -(1.0 / m.density) * log(dr.a);
+                            if (hit_distance < distance_inside_boundary) {
+                                closest = h1 + hit_distance / len;
+                                win.prim = kMediumFlag | mi;
+                                win.rank = m.rank;
+                                win.face = 0;
+                            }
+                        }
+                    }
+                }
+                ++q;
+                if (MEDIA && q < nq && ((q - 1u) & 1u) != 0u && !have_t1) ++q;  // no first boundary hit: skip the second query
+                if (q >= nq) {
+                    st_u4(slot_d2w(pool, slot) + 6, make_uint4(win.prim, (uint32_t)win.face, (uint32_t)__double2loint(closest), (uint32_t)__double2hiint(closest)));
+                    has_ray = false;
+                    break;
+                }
+                if (MEDIA) {  // open a boundary query of medium (q-1)/2 (medium.rs:29-30)
+                    const uint32_t mi = (q - 1u) >> 1;
+                    const bool sec = ((q - 1u) & 1u) != 0u;
+                    const DMedium &m = sc.media[mi];
+                    gi = m.first_group;
+                    g_end = gi + m.n_groups;
+                    t_min = sec ? t1 + 0.0001 : -DBL_MAX;
+                    b = Best{DBL_MAX, kNoPrim, 0u, 0};
+                }
+            }
+        }
+
+        // ---- C: traverse --------------------------------------------------------------------
+        while (node != kDone) {
+            while (node >= 0) {
+                const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+                float e0, e1;
+                const bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
+                const bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
+                if (h0 && h1) {
+                    const bool swap = e1 < e0;
+                    const int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
+                    if (sp < kStackSize) stack[sp++] = far_c;
+                    node = near_c;
+                } else if (h0) {
+                    node = ch.x;
+                } else if (h1) {
+                    node = ch.y;
+                } else {
+                    node = sp ? stack[--sp] : kDone;
+                }
+                // lanes that hold a leaf wait here for the others: stop descending once few are left
+                if ((unsigned)__popc(__ballot_sync(__activemask(), node >= 0)) < inner_below) break;
+            }
+            if (node < 0 && node != kDone) {
+                const uint32_t code = ~(uint32_t)node;
+                const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+                const double before = b.t;
+                for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, b);
+                if (b.t != before) t_max_f = __double2float_ru(b.t);
+                node = sp ? stack[--sp] : kDone;
+            }
+            if ((unsigned)__popc(__ballot_sync(__activemask(), node != kDone)) < leave_below) break;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// control: end of a round
+// ---------------------------------------------------------------------------
+__global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
+    WfCtl *c = pool.ctl;
+    const unsigned cur = c->round & 1u;
+    const unsigned live = c->live[cur];
+    counters[kCounterRays] += live;  // one segment per live slot (main.rs:48)
+    c->status_live = live;
+    c->live[cur ^ 1u] = 0u;
+    c->ext_cursor = 0u;
+    c->round += 1u;
+    c->rounds_done += 1u;
+}
+
+// ---------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------
+cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
+    unsigned blocks = (pool.n_slots + 255u) / 256u;
+    if (blocks > 148u * 8u) blocks = 148u * 8u;
+    if (blocks < 1u) blocks = 1u;
+    wf_init_kernel<<<blocks, 256, 0, stream>>>(pool);
+    return cudaGetLastError();
+}
+
+cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
+                            double *planes, unsigned long long *counters, bool media, int sms, cudaStream_t stream) {
+    static int ext_per_sm[2] = {0, 0};
+    if (ext_per_sm[0] == 0) {
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_per_sm[0], wf_extend_kernel<false>, kWfBlock, 0);
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_per_sm[1], wf_extend_kernel<true>, kWfBlock, 0);
+        if (e != cudaSuccess) {
+            ext_per_sm[0] = 0;
+            return e;
+        }
+    }
+    // shade and generate: one slot per thread.  extend: one resident wave of persistent warps, but
+    // never more warps than there are reservations to hand out.
+    const unsigned per_slot = (pool.n_slots + kWfBlock - 1) / kWfBlock;
+    const unsigned per_reserve = (pool.n_slots + kWfReserve - 1) / kWfReserve;
+    const int occ = ext_per_sm[media ? 1 : 0];
+    unsigned ext_grid = (unsigned)(sms * (occ > 0 ? occ : 1));
+    const unsigned ext_want = (per_reserve + (kWfBlock / 32) - 1) / (kWfBlock / 32);
+    if (ext_grid > ext_want) ext_grid = ext_want ? ext_want : 1u;
+    wf_shade_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);
+    wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
+    if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+    else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+    wf_control_kernel<<<1, 1, 0, stream>>>(pool, counters);
+    return cudaGetLastError();
+}
+
+}  // namespace rtb200dev

@@ -202,3 +202,36 @@ def test_mesh_config_reduced(rt, orc):
     err = rel_err(img, ref, floor=1e-6).max(axis=2)
     print("mesh %dx%dx%d: 8-bit RMSE %.6f, pixels within 1e-4 rel %.6f" % (W, H, spp, rmse, (err <= 1e-4).mean()))
     assert rmse <= 0.01 and (err <= 1e-4).mean() >= 0.999
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_wavefront_equals_megakernel(rt, orc, name):
+    """The two pipelines run the same device arithmetic with the same summation order: the
+    wavefront stages (generate / extend / shade over ray queues) must reproduce the megakernel's
+    image bit for bit, and count the same paths and segments."""
+    hs, dev, _ = scenes(rt, orc, name)
+    W, H, spp, depth = 97, 61, 20, 100  # ragged: partial 8x4 tiles, a pool larger than the image
+    abi = rt._abi
+    a, sa = dev.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=3, integrator=hs.integrator, flags=abi.FLAG_MEGAKERNEL))
+    b, sb = dev.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=3, integrator=hs.integrator, flags=abi.FLAG_WAVEFRONT))
+    assert sa.paths == sb.paths == W * H * spp
+    assert sa.rays == sb.rays
+    assert sa.nonfinite_samples == sb.nonfinite_samples
+    assert np.array_equal(a, b, equal_nan=True)
+    # a sample sub-range (the multi-GPU partition) and a depth cut
+    o = dict(seed=3, integrator=hs.integrator, sample_begin=5, sample_count=9)
+    a, _ = dev.render(hs.camera, W, H, spp, 7, rt.render_opts(flags=abi.FLAG_MEGAKERNEL, **o))
+    b, _ = dev.render(hs.camera, W, H, spp, 7, rt.render_opts(flags=abi.FLAG_WAVEFRONT, **o))
+    assert np.array_equal(a, b, equal_nan=True)
+
+
+def test_wavefront_matches_oracle_image(rt, orc):
+    """Check 3 through the wavefront pipeline on the scene with media, BVHs, textures and motion blur."""
+    hs, dev, osc = scenes(rt, orc, "final")
+    W, H, spp, depth = 61, 45, 24, 100
+    opts = rt.render_opts(seed=8, integrator=hs.integrator, flags=rt._abi.FLAG_WAVEFRONT)
+    img, stats = dev.render(hs.camera, W, H, spp, depth, opts)
+    ref, _ = osc.render(hs.camera, W, H, spp, depth, opts)
+    err = rel_err(img, ref, floor=1e-6).max(axis=2)
+    assert float((err <= 1e-4).mean()) >= 0.995
+    assert stats.kernel_launches > 4
