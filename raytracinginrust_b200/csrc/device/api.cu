@@ -340,8 +340,8 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
     CU(cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * kNumCounters));
     CU(cudaMallocHost((void **)&s->counters_host, sizeof(unsigned long long) * kNumCounters));
     // BVH and media scenes are latency-bound in the search: run them with the 64-register build (more warps)
-    s->render_variant = (cs.nodes.empty() && cs.media.empty()) ? 0 : 1;
-    if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) s->render_variant = std::atoi(v) ? 1 : 0;
+    s->render_variant = ((cs.nodes.empty() && cs.media.empty()) ? 0 : 1) | (cs.media.empty() ? 0 : 2);
+    if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) s->render_variant = (std::atoi(v) ? 1 : 0) | (cs.media.empty() ? 0 : 2);
     CU(render_grid_size(device, s->render_variant, &s->render_blocks));
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();

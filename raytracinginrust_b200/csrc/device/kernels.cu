@@ -17,7 +17,7 @@ namespace rtb200dev {
 // Two register budgets of the same kernel (a launch bound is a compile-time property): flat
 // scenes run best at 128 registers / 4 blocks per SM, BVH scenes at 64 / 8 — the traversal is
 // latency-bound and more resident warps hide more of it (profiles/r1 sweep).
-template <int MIN_BLOCKS>
+template <int MIN_BLOCKS, bool MEDIA>
 __global__ void __launch_bounds__(kRenderBlock, MIN_BLOCKS)
 render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
               const __grid_constant__ RenderParams P, double *__restrict__ planes,
@@ -60,7 +60,7 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
             ++n_paths;
             alive = true;
         }
-        alive = path_step(sc, ps, P.integrator, P.flags);
+        alive = path_step<MEDIA>(sc, ps, P.integrator, P.flags);
         if (!alive) {
             n_rays += ps.segments;
             // no NaN guard, like the reference (§Q10); only counted
@@ -126,7 +126,7 @@ __global__ void path_radiance_kernel(const __grid_constant__ DScene sc, const __
     if (k >= n) return;
     PathState ps;
     path_begin(ps, cam, P.width, P.height, px[k], py[k], sample[k], P.seed, P.max_depth);
-    while (path_step(sc, ps, P.integrator, P.flags)) {
+    while (path_step<true>(sc, ps, P.integrator, P.flags)) {
     }
     rgb[3 * k] = ps.radiance.x;
     rgb[3 * k + 1] = ps.radiance.y;
@@ -189,13 +189,22 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-// variant 0: 128 registers (4 blocks/SM); variant 1: 64 registers (8 blocks/SM)
+// variant bit 0: 0 = 128 registers (4 blocks/SM), 1 = 64 registers (8 blocks/SM);
+// variant bit 1: the scene has media (the kernel carries the boundary-query loop of medium.rs)
+template <class F>
+static cudaError_t with_render_kernel(int variant, F f) {
+    switch (variant & 3) {
+        case 0: return f(render_kernel<4, false>);
+        case 1: return f(render_kernel<8, false>);
+        case 2: return f(render_kernel<4, true>);
+        default: return f(render_kernel<8, true>);
+    }
+}
 cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
     int sms = 0, per_sm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    if (variant == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<4>, kRenderBlock, 0);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, render_kernel<8>, kRenderBlock, 0);
+    e = with_render_kernel(variant, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRenderBlock, 0); });
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     *blocks_out = sms * per_sm;  // persistent: exactly one resident wave
@@ -204,9 +213,10 @@ cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
 
 cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int variant, int blocks,
                           double *planes, unsigned long long *counters, cudaStream_t stream) {
-    if (variant == 0) render_kernel<4><<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
-    else render_kernel<8><<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
-    return cudaGetLastError();
+    return with_render_kernel(variant, [&](auto k) {
+        k<<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
+        return cudaGetLastError();
+    });
 }
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
                                  cudaStream_t stream) {

@@ -478,36 +478,49 @@ RT_DEV double sphere_root_exact(V3 o, V3 d, V3 center, double radius, double t_m
     if (root < t_min) root = (-half_b + sqrt_d) / a;
     return root;
 }
-// Wrapper post-processing, innermost first (translate.rs:26, rotate.rs:88-104, hit.rs:116)
-RT_DEV void chain_post(const DScene &sc, uint32_t chain, const Ray &world, HitRec &rec) {
+// Wrapper post-processing, innermost first (translate.rs:26, rotate.rs:88-104, hit.rs:116).
+// d_obj: the ray direction below the WHOLE chain (what chain_ray gives for all n_ops ops).
+RT_DEV void chain_post(const DScene &sc, uint32_t chain, const Ray &world, V3 d_obj, HitRec &rec) {
     DChain c = sc.chains[chain];
+    bool inner_only_flips = true;  // no Translate/Rotate below op i: its object-space ray is the chain's
     for (uint32_t i = c.n_ops; i-- > 0;) {
         const DOp &op = sc.ops[c.first_op + i];
         if (op.kind == OP_FLIP) {
             rec.front_face = !rec.front_face;
         } else if (op.kind == OP_TRANSLATE) {
             rec.p = rec.p + ld3(op.offset);
+            inner_only_flips = false;
         } else {
             rec.p = rot_back(op, rec.p);
             V3 n = rot_back(op, rec.normal);
             // §Q3: face orientation is recomputed with the ray of THIS Rotate's object space
-            V3 o = world.o, d = world.d;
-            chain_ray(sc, c.first_op, i + 1, o, d);
+            V3 d = d_obj;
+            if (!inner_only_flips) {
+                V3 o = world.o;
+                d = world.d;
+                chain_ray(sc, c.first_op, i + 1, o, d);
+            }
             set_face_normal(rec, d, n);
+            inner_only_flips = false;
         }
     }
 }
 
-// t: the winner's reference-arithmetic t (exact_t).
+// The ray as the primitive's own hit() sees it: below every wrapper of its chain.
+RT_DEV void object_ray(const DScene &sc, uint32_t chain, const Ray &world, V3 &o, V3 &d) {
+    o = world.o;
+    d = world.d;
+    DChain c = sc.chains[chain];
+    chain_ray(sc, c.first_op, c.n_ops, o, d);
+}
+
+// t: the winner's reference-arithmetic t (exact_t); (o, d): object_ray of the winner's chain.
 template <bool WANT_UV>
-RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, double t, HitRec &rec) {
+RT_DEV void resolve_hit_obj(const DScene &sc, const Ray &world, const Best &best, double t, V3 o, V3 d, HitRec &rec) {
     rec.t = t;
     rec.u = 0.0;
     rec.v = 0.0;
     const DPrim &p = sc.prims[best.prim];
-    V3 o = world.o, d = world.d;
-    DChain c = sc.chains[p.chain];
-    chain_ray(sc, c.first_op, c.n_ops, o, d);
     rec.material = p.material;
     rec.node = p.node;
     rec.face = best.face;
@@ -517,11 +530,11 @@ RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, do
         uint32_t plane = p.axis;
         double a0 = p.d[0], a1 = p.d[1], b0 = p.d[2], b1 = p.d[3], k = p.d[4];
         if (kind == PRIM_BOX) box_face(p.d, best.face, plane, a0, a1, b0, b1, k);
-        double ok, dk, oa, da, ob, db;
+        double oa, da, ob, db;
         V3 normal;
-        if (plane == RT_PLANE_XZ) { ok = o.y; dk = d.y; oa = o.x; da = d.x; ob = o.z; db = d.z; normal = mk(0.0, 1.0, 0.0); }
-        else if (plane == RT_PLANE_YZ) { ok = o.x; dk = d.x; oa = o.y; da = d.y; ob = o.z; db = d.z; normal = mk(1.0, 0.0, 0.0); }
-        else { ok = o.z; dk = d.z; oa = o.x; da = d.x; ob = o.y; db = d.y; normal = mk(0.0, 0.0, 1.0); }
+        if (plane == RT_PLANE_XZ) { oa = o.x; da = d.x; ob = o.z; db = d.z; normal = mk(0.0, 1.0, 0.0); }
+        else if (plane == RT_PLANE_YZ) { oa = o.y; da = d.y; ob = o.z; db = d.z; normal = mk(1.0, 0.0, 0.0); }
+        else { oa = o.x; da = d.x; ob = o.y; db = d.y; normal = mk(0.0, 0.0, 1.0); }
         if (want_uv) {
             double a = oa + t * da;
             double b = ob + t * db;
@@ -531,11 +544,11 @@ RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, do
         rec.p = o + t * d;  // r.at(t), ray.rs:26-28
         set_face_normal(rec, d, normal);
     } else if (kind == PRIM_TRI) {  // tri.rs:24-54; p.d = v0 e1 e2 n
-        V3 s = o - ld3(p.d);
-        V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
-        V3 s1 = cross(d, e2);
-        V3 s2 = cross(s, e1);
         if (want_uv) {
+            V3 s = o - ld3(p.d);
+            V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
+            V3 s1 = cross(d, e2);
+            V3 s2 = cross(s, e1);
             double s1_e1 = dot(s1, e1);
             rec.u = dot(s1, s) / s1_e1;
             rec.v = dot(s2, d) / s1_e1;
@@ -550,16 +563,19 @@ RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, do
         set_face_normal(rec, d, outward_normal);
         if (want_uv) get_sphere_uv(outward_normal, rec.u, rec.v);
     }
-    chain_post(sc, p.chain, world, rec);
+    chain_post(sc, p.chain, world, d, rec);
+}
+template <bool WANT_UV>
+RT_DEV void resolve_hit(const DScene &sc, const Ray &world, const Best &best, double t, HitRec &rec) {
+    V3 o, d;
+    object_ray(sc, sc.prims[best.prim].chain, world, o, d);
+    resolve_hit_obj<WANT_UV>(sc, world, best, t, o, d, rec);
 }
 
-// The reference-arithmetic t of a search winner (the part of resolve_hit that produces rec.t).
-// t_min: the lower end of the interval the search ran with.
-RT_DEV double exact_t(const DScene &sc, const Ray &world, const Best &best, double t_min) {
+// The reference-arithmetic t of a search winner (the part of the primitive's hit() that produces
+// rec.t), for the object-space ray (o, d).  t_min: the lower end of the interval the search ran with.
+RT_DEV double exact_t_obj(const DScene &sc, const Best &best, V3 o, V3 d, double time, double t_min) {
     const DPrim &p = sc.prims[best.prim];
-    V3 o = world.o, d = world.d;
-    DChain c = sc.chains[p.chain];
-    chain_ray(sc, c.first_op, c.n_ops, o, d);
     uint32_t kind = p.kind;
     if (kind == PRIM_RECT || kind == PRIM_BOX) {  // rect.rs:51
         uint32_t plane = p.axis;
@@ -579,8 +595,13 @@ RT_DEV double exact_t(const DScene &sc, const Ray &world, const Best &best, doub
         V3 s2 = cross(s, e1);
         return dot(s2, e2) / dot(s1, e1);
     }
-    V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
+    V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, time);
     return sphere_root_exact(o, d, center, kind == PRIM_SPHERE ? p.d[3] : p.d[8], t_min);
+}
+RT_DEV double exact_t(const DScene &sc, const Ray &world, const Best &best, double t_min) {
+    V3 o, d;
+    object_ray(sc, sc.prims[best.prim].chain, world, o, d);
+    return exact_t_obj(sc, best, o, d, world.time, t_min);
 }
 
 RT_DEV void resolve_medium(const DScene &sc, const Ray &world, const Best &best, double t, HitRec &rec) {  // medium.rs:46-56
@@ -597,7 +618,7 @@ RT_DEV void resolve_medium(const DScene &sc, const Ray &world, const Best &best,
     rec.material = m.material;
     rec.node = m.node;
     rec.face = 0;
-    chain_post(sc, m.chain, world, rec);
+    chain_post(sc, m.chain, world, d, rec);
 }
 
 // world.hit(ray, 0.00001, inf) (main.rs:48).  One query loop with a single search call site:
@@ -612,6 +633,14 @@ RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &re
     double t1 = 0.0;
     bool have_t1 = false;
     const uint32_t nq = 1u + (WITH_MEDIA ? 2u * sc.n_media : 0u);
+    if (!WITH_MEDIA) {  // one query; t and the record come from one object-space ray
+        trace_groups(sc, 0, sc.n_world_groups, r, inv, kTMin, win);
+        if (win.prim == kNoPrim) return false;
+        V3 o, d;
+        object_ray(sc, sc.prims[win.prim].chain, r, o, d);
+        resolve_hit_obj<WANT_UV>(sc, r, win, exact_t_obj(sc, win, o, d, r.time, kTMin), o, d, rec);
+        return true;
+    }
 #pragma unroll 1
     for (uint32_t q = 0; q < nq; ++q) {
         uint32_t fg = 0, ng = sc.n_world_groups, mi = 0;
@@ -862,11 +891,14 @@ struct PathState {
 //   recursion:  L = emitted + f * L_next      iteration:  radiance += beta*emitted ; beta *= f
 RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags);
 
+// MEDIA: the scene has ConstantMedium objects (a compile-time property of the kernel variant, so
+// that scenes without volumes do not carry the boundary-query loop).
+template <bool MEDIA>
 RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint32_t flags) {
     if (ps.depth_left == 0) return false;  // main.rs:42-45: contributes black
     HitRec rec;
     ps.segments += 1;
-    bool hit = world_hit<true, false>(sc, ps.ray, ps.rng, rec);  // main.rs:48
+    bool hit = world_hit<MEDIA, false>(sc, ps.ray, ps.rng, rec);  // main.rs:48
     return path_shade(sc, ps, hit, rec, integrator, flags);
 }
 
