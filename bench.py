@@ -228,7 +228,7 @@ def main():
     barrier()
 
     t_begin = time.time()
-    step_ms, kern_ms, paths, rays = [], [], 0, 0
+    step_ms, kern_ms, paths, rays, launches = [], [], 0, 0, 0
     for _ in range(args.steps):
         flush.fill_(0)  # L2 flush between timed steps
         barrier()
@@ -243,6 +243,7 @@ def main():
             kern_ms.append(st.render_ms)
             paths += st.paths
             rays += st.rays
+            launches += st.kernel_launches
     barrier()
     t_end = time.time()
     if sampler and t_end - t_begin < 1.0:
@@ -315,6 +316,9 @@ def main():
     hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
     kern_s = (sum(kern_ms) / len(kern_ms)) * 1e-3 if kern_ms else None
     segs_per_launch = (rays / len(kern_ms)) if kern_ms else 0.0
+    info = scene.render_info  # which pipeline build ran: megakernel or wavefront, feature variant
+    pipeline = info.get("pipeline", "?")
+    kernel_name = "render_kernel" if pipeline == "megakernel" else "wf_extend_kernel + wf_shade_kernel + wf_generate_kernel"
     roofline = roofline64 = None
     traffic = None  # dram__bytes_read+write of render_kernel per launch, from the committed ncu capture of this command
     try:
@@ -326,11 +330,14 @@ def main():
     if kern_s and bytes_seg is not None:
         achieved = bytes_seg * segs_per_launch / kern_s / 1e9
         roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                    "traffic": traffic, "peak_source": hbm_src, "kernel": "render_kernel",
+                    "traffic": traffic, "peak_source": hbm_src, "kernel": kernel_name,
                     "algorithmic_bytes_per_segment": bytes_seg, "segments_per_launch": segs_per_launch,
                     "kernel_ms": kern_s * 1e3,
-                    "note": "megakernel: no ray queues (Q=0); the scene tables are cache-resident, so measured DRAM "
-                            "traffic is far BELOW the algorithmic bytes; the binding limit is FP64 issue (roofline_fp64)"}
+                    "note": ("megakernel: no ray queues (Q=0); the scene tables are cache-resident, so measured DRAM "
+                             "traffic is far BELOW the algorithmic bytes; the binding limit is FP64 issue (roofline_fp64)")
+                    if pipeline == "megakernel" else
+                            ("wavefront: the algorithmic bytes exclude the path-pool traffic (one 128-byte slot record "
+                             "read+written per segment and stage); the binding limit is FP64 issue (roofline_fp64)")}
         fp64_peak = rt.measure_fp64_peak(local_rank)
         ach_tf = flops_seg * segs_per_launch / kern_s / 1e12
         roofline64 = {"bound": "fp64_issue", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -345,13 +352,14 @@ def main():
         "config": {"workload": WORKLOADS[args.workload], "scene": args.workload, "width": W, "height": H, "spp": spp,
                    "max_depth": depth, "integrator": "HEAD" if hs.integrator == 0 else "LEGACY",
                    "parallelism": "sample blocks x%d + 1 ncclReduce" % world if world > 1 else "1 GPU",
-                   "l2": "256 MiB device memset between timed steps (L2 flush)", "seed": 1},
+                   "l2": "256 MiB device memset between timed steps (L2 flush)", "seed": 1,
+                   "pipeline": pipeline, "variant": info.get("variant"), "pipeline_info": info},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "Mpaths/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
                 "what": "RtSceneDesc in host memory -> rt_scene_create (compile, BVH build, upload) -> render -> "
                         "fp32 sums copied to pinned host memory"},
-        "gpu_launches": 2 * args.steps,
+        "gpu_launches": int(launches),  # this rank's render + reduce kernels inside the timed steps (RtStats.kernel_launches)
         "roofline": roofline, "roofline_fp64": roofline64, "cpu_baseline": cpu,
         "algorithmic_tests_per_segment": per_seg, "checksum": checksum,
     }

@@ -285,6 +285,11 @@ RtStatus rt_camera_rays(const RtScene *scene, const RtCamera *camera, uint32_t w
                         uint32_t height, const RtRenderOpts *opts, const uint32_t *px,
                         const uint32_t *py, const uint32_t *sample, uint64_t n, RtRay *rays);
 
+/* Diagnostic: which pipeline build the last rt_render / rt_render_device on this scene ran, e.g.
+ * "pipeline=megakernel variant=vflat blocks_per_sm=6".  The string lives until the next render
+ * on the scene.  "" before the first render. */
+const char *rt_render_info(const RtScene *scene);
+
 /* Diagnostic: measured FP64 FMA throughput of `device` in TFLOP/s (a dependent-chain DFMA
  * micro-kernel, best of 5).  bench.py uses it as the denominator of the FP64-issue roofline,
  * the bound that actually applies to this path (DESIGN.md "Rooflines"). */

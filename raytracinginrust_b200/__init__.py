@@ -53,6 +53,8 @@ _dev.rt_scene_destroy.argtypes = [C.c_void_p]
 _dev.rt_scene_destroy.restype = None
 _dev.rt_scene_device_bytes.argtypes = [C.c_void_p]
 _dev.rt_scene_device_bytes.restype = C.c_uint64
+_dev.rt_render_info.argtypes = [C.c_void_p]
+_dev.rt_render_info.restype = C.c_char_p
 _dev.rt_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                            C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(RtStats)]
 _dev.rt_render_device.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -338,6 +340,12 @@ class DeviceScene:
     @property
     def device_bytes(self):
         return int(_dev.rt_scene_device_bytes(self._h))
+
+    @property
+    def render_info(self):
+        """Which pipeline build the last render ran: {'pipeline': ..., 'variant': ..., ...}."""
+        text = (_dev.rt_render_info(self._h) or b"").decode()
+        return dict(kv.split("=", 1) for kv in text.split() if "=" in kv)
 
     def render(self, camera, width, height, spp, max_depth, opts=None):
         opts = opts or render_opts()

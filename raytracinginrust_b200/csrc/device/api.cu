@@ -14,6 +14,7 @@
 #include "../../../include/rtb200.h"
 #include "compile.h"
 #include "kernels.h"
+#include "variants.h"
 #include "wavefront.h"
 
 using namespace rtb200dev;
@@ -49,8 +50,8 @@ struct RtScene {
     uint32_t n_lights = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int render_blocks = 0;
-    int render_variant = 0;
+    uint32_t features = 0;     // Feat bits of the scene (the integrator bit is added per render)
+    int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
     size_t planes_bytes = 0;
@@ -65,6 +66,7 @@ struct RtScene {
     int sms = 148;
     bool has_media = false;
     bool wavefront_default = false;
+    std::string render_info;
     // last async render
     bool pending = false;
     cudaStream_t pending_stream = nullptr;
@@ -164,6 +166,37 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     return RT_OK;
 }
 
+uint32_t scene_features(const CompiledScene &cs) {
+    uint32_t f = 0;
+    for (const DPrim &p : cs.prims) {
+        switch (p.kind) {
+            case PRIM_SPHERE: f |= F_SPHERE; break;
+            case PRIM_MSPHERE: f |= F_MSPHERE; break;
+            case PRIM_RECT: f |= F_RECT; break;
+            case PRIM_TRI: f |= F_TRI; break;
+            default: f |= F_BOX; break;
+        }
+    }
+    if (!cs.nodes.empty()) f |= F_BVH;
+    for (const DTexture &t : cs.textures)
+        if (t.kind != RT_TEX_CONSTANT) f |= F_TEX;
+    for (const DLight &l : cs.lights)
+        if (l.kind == LIGHT_SPHERE) f |= F_SPHERE_LIGHT;
+    for (const DMaterial &m : cs.materials) {
+        if (m.kind == RT_MAT_METAL) f |= F_METAL;
+        if (m.kind == RT_MAT_DIELECTRIC) f |= F_DIELECTRIC;
+    }
+    return f;
+}
+
+// The pipeline build a render runs on: the most specific variant that covers the scene's features
+// and the integrator (RTB200_VARIANT=<name> forces one, e.g. vall for an A/B).
+const PipelineVariant *pick_variant(const RtScene &s, uint32_t integrator) {
+    if (const char *v = std::getenv("RTB200_VARIANT"))
+        if (const PipelineVariant *pv = find_variant_by_name(v)) return pv;
+    return find_variant(s.features | (integrator == RT_INTEGRATOR_LEGACY ? F_LEGACY : F_HEAD));
+}
+
 RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
     size_t plane_bytes = (size_t)P.n_chunks * P.width * P.height * 3 * sizeof(double);
     if (plane_bytes > s.planes_bytes) {
@@ -220,12 +253,12 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
 // The wavefront pipeline: rounds of shade / generate / extend / control until no path is alive.
 // The number of rounds depends on the paths, so the host reads the live count back every few
 // rounds (an empty round is four kernels that find nothing to do).
-RtStatus run_wavefront(RtScene &s, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
+RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
     const int kRoundsPerCheck = 8;
-    CU(wf_launch_init(s.wf, st));
+    CU(pv.wf_launch_init(s.wf, st));
     s.pending_launches += 1;
     for (;;) {
-        for (int k = 0; k < kRoundsPerCheck; ++k) CU(wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, st));
+        for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, st));
         s.pending_launches += (uint64_t)kRoundsPerCheck * kWfLaunchesPerRound;
         CU(cudaMemcpyAsync(s.wf_status_host, &s.wf.ctl->status_live, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
@@ -238,11 +271,16 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
     CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * kNumCounters, st));
     CU(cudaEventRecord(s.ev0, st));
     s.pending_launches = 0;
+    const PipelineVariant &pv = *pick_variant(s, P.integrator);
     if (wavefront) {
-        RtStatus w = run_wavefront(s, cam, P, st);
+        s.render_info = std::string("pipeline=wavefront variant=") + pv.name + " pool_slots=" + std::to_string(s.wf.n_slots);
+        RtStatus w = run_wavefront(s, pv, cam, P, st);
         if (w != RT_OK) return w;
     } else {
-        CU(launch_render(s.ds, cam, P, s.render_variant, s.render_blocks, s.planes, s.counters, st));
+        int blocks = 0;
+        CU(pv.render_grid_size(s.device, s.render_variant, &blocks));
+        s.render_info = std::string("pipeline=megakernel variant=") + pv.name + " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
+        CU(pv.launch_render(s.ds, cam, P, s.render_variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
@@ -339,10 +377,14 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
     CU(cudaEventCreate(&s->ev1));
     CU(cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * kNumCounters));
     CU(cudaMallocHost((void **)&s->counters_host, sizeof(unsigned long long) * kNumCounters));
-    // BVH and media scenes are latency-bound in the search: run them with the 64-register build (more warps)
-    s->render_variant = ((cs.nodes.empty() && cs.media.empty()) ? 0 : 1) | (cs.media.empty() ? 0 : 2);
-    if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) s->render_variant = (std::atoi(v) ? 1 : 0) | (cs.media.empty() ? 0 : 2);
-    CU(render_grid_size(device, s->render_variant, &s->render_blocks));
+    // register budget of the megakernel (megakernel.inl: 0 = 6 blocks/SM, 1 = 8, 2 = 12) + media bit
+    s->features = scene_features(cs);
+    {
+        const bool bvh = !cs.nodes.empty(), media = !cs.media.empty(), tris = (s->features & F_TRI) != 0u;
+        int budget = (!bvh && !media) ? 0 : ((bvh && !media && !tris) ? 2 : 1);
+        if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) budget = std::atoi(v) & 3;
+        s->render_variant = budget | (media ? 4 : 0);
+    }
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();
     // Measured per scene class (profiles/r1_e_pipeline_ab.md): the wavefront stages beat the megakernel
@@ -356,6 +398,8 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
 void rt_scene_destroy(RtScene *scene) { delete scene; }
 
 uint64_t rt_scene_device_bytes(const RtScene *scene) { return scene ? scene->device_bytes : 0; }
+
+const char *rt_render_info(const RtScene *scene) { return scene ? scene->render_info.c_str() : ""; }
 
 RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height, uint32_t spp,
                           uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream) {

@@ -1,77 +1,11 @@
-// kernels.cu — CUDA kernels of the hot path and their launchers (sm_100a).
-//
-// render_kernel replaces the nested pixel / sample loop of src/main.rs:772-834.
-// Design (DESIGN.md "Kernels"): persistent threads, one path per lane, per-lane
-// regeneration.  A work item is (sample chunk, pixel); a lane pulls items from a
-// global counter, runs the chunk's samples one after the other in sample order,
-// and writes the chunk's f64 sum to its own slot of a [chunk][pixel] plane —
-// no atomics on pixel data, so the image is bit-reproducible run to run.
-// reduce_planes_kernel then adds the planes in chunk order into the fp32 image.
+// kernels.cu — the kernels that exist once: the plane reduction, the parity hooks and the FP64
+// probe (sm_100a).  The render pipelines live in pipelines.cu, compiled once per scene feature set.
 #include <cuda_runtime.h>
 
 #include "kernels.h"
 #include "trace.cuh"
 
 namespace rtb200dev {
-
-// Two register budgets of the same kernel (a launch bound is a compile-time property): flat
-// scenes run best at 128 registers / 4 blocks per SM, BVH scenes at 64 / 8 — the traversal is
-// latency-bound and more resident warps hide more of it (profiles/r1 sweep).
-template <int MIN_BLOCKS, bool MEDIA>
-__global__ void __launch_bounds__(kRenderBlock, MIN_BLOCKS)
-render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
-              const __grid_constant__ RenderParams P, double *__restrict__ planes,
-              unsigned long long *__restrict__ counters) {
-    unsigned long long n_paths = 0, n_rays = 0, n_bad = 0;
-    PathState ps;
-    bool alive = false, have_item = false;
-    uint32_t i = 0, row = 0, s = 0, s_end = 0;
-    uint64_t slot = 0;
-    V3 sum = mk(0.0, 0.0, 0.0);
-    for (;;) {
-        if (!alive) {
-            if (!have_item || s == s_end) {
-                if (have_item) {
-                    double *dst = planes + 3 * slot;
-                    dst[0] = sum.x;
-                    dst[1] = sum.y;
-                    dst[2] = sum.z;
-                    have_item = false;
-                }
-                // next (chunk, pixel) item; skip the padding of partial tiles
-                for (;;) {
-                    unsigned long long item = atomicAdd(&counters[kCounterWork], 1ull);
-                    if (item >= P.n_items) break;
-                    uint32_t chunk = (uint32_t)(item / P.items_per_chunk);
-                    uint64_t lin = item - (uint64_t)chunk * P.items_per_chunk;
-                    if (!item_pixel(P.tiles_x, P.width, P.height, lin, i, row)) continue;
-                    s = P.sample_begin + chunk * P.chunk_size;
-                    s_end = min(s + P.chunk_size, P.sample_end);
-                    slot = (uint64_t)chunk * P.width * P.height + (uint64_t)row * P.width + i;
-                    sum = mk(0.0, 0.0, 0.0);
-                    have_item = true;
-                    break;
-                }
-                if (!have_item) break;
-            }
-            // row 0 of the image is j = H-1 (main.rs:772)
-            path_begin(ps, cam, P.width, P.height, i, P.height - 1u - row, s, P.seed, P.max_depth);
-            ++s;
-            ++n_paths;
-            alive = true;
-        }
-        alive = path_step<MEDIA>(sc, ps, P.integrator, P.flags);
-        if (!alive) {
-            n_rays += ps.segments;
-            // no NaN guard, like the reference (§Q10); only counted
-            if (!(isfinite(ps.radiance.x) && isfinite(ps.radiance.y) && isfinite(ps.radiance.z))) ++n_bad;
-            sum = sum + ps.radiance;  // vec.rs:253-260 Sum, in sample order
-        }
-    }
-    atomicAdd(&counters[kCounterPaths], n_paths);
-    atomicAdd(&counters[kCounterRays], n_rays);
-    atomicAdd(&counters[kCounterNonFinite], n_bad);
-}
 
 // out[p] (+)= sum over chunks of planes[c][p], c ascending: a fixed summation order
 __global__ void reduce_planes_kernel(const double *__restrict__ planes, float *__restrict__ out, uint64_t n_values,
@@ -189,35 +123,6 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-// variant bit 0: 0 = 128 registers (4 blocks/SM), 1 = 64 registers (8 blocks/SM);
-// variant bit 1: the scene has media (the kernel carries the boundary-query loop of medium.rs)
-template <class F>
-static cudaError_t with_render_kernel(int variant, F f) {
-    switch (variant & 3) {
-        case 0: return f(render_kernel<4, false>);
-        case 1: return f(render_kernel<8, false>);
-        case 2: return f(render_kernel<4, true>);
-        default: return f(render_kernel<8, true>);
-    }
-}
-cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
-    int sms = 0, per_sm = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    if (e != cudaSuccess) return e;
-    e = with_render_kernel(variant, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRenderBlock, 0); });
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    *blocks_out = sms * per_sm;  // persistent: exactly one resident wave
-    return cudaSuccess;
-}
-
-cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int variant, int blocks,
-                          double *planes, unsigned long long *counters, cudaStream_t stream) {
-    return with_render_kernel(variant, [&](auto k) {
-        k<<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
-        return cudaGetLastError();
-    });
-}
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
                                  cudaStream_t stream) {
     uint64_t want = (n_values + 255) / 256;

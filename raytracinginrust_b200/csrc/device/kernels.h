@@ -29,10 +29,7 @@ struct RenderParams {
     uint64_t n_items;                   // n_chunks * items_per_chunk
 };
 
-cudaError_t render_grid_size(int device, int variant, int *blocks_out);
 cudaError_t measure_fp64_peak(int device, double *tflops);
-cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int variant, int blocks,
-                          double *planes, unsigned long long *counters, cudaStream_t stream);
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
                                  cudaStream_t stream);
 cudaError_t launch_first_hit(const DScene &sc, const RtRay *rays, uint64_t n, RtHit *hits, cudaStream_t stream);

@@ -121,6 +121,19 @@ struct DPerlin {
     uint32_t perm_x[256], perm_y[256], perm_z[256];
 };
 
+// What a scene uses.  The pipelines are compiled once per feature set (variants.h): a scene runs
+// on the smallest variant that covers its features, so the Cornell box does not carry sphere,
+// triangle, BVH, Perlin or legacy-integrator code through its instruction cache and registers.
+enum Feat : uint32_t {
+    F_SPHERE = 1, F_MSPHERE = 2, F_RECT = 4, F_TRI = 8, F_BOX = 16,
+    F_BVH = 32,            // some group has a BVH
+    F_TEX = 64,            // a non-constant texture (checker, noise, image)
+    F_SPHERE_LIGHT = 128,  // a sphere in the light list
+    F_METAL = 256, F_DIELECTRIC = 512,
+    F_LEGACY = 1024, F_HEAD = 2048,  // which ray_color (a render option, added at render time)
+    F_ALL = 0xFFFFFFFFu
+};
+
 // Pointers are device pointers once uploaded.
 struct DScene {
     const DPrim *prims;

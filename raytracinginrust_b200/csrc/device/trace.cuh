@@ -23,9 +23,20 @@
 #include "../../../include/rtb200.h"
 #include "tables.h"
 
+// This header is compiled once per pipeline variant (variants.h): RT_VARIANT_NS names the variant,
+// RT_FEAT_MASK is the feature set compiled in; feat(F_X) folds the code of unused features away.
+#ifndef RT_VARIANT_NS
+#define RT_VARIANT_NS vall
+#endif
+#ifndef RT_FEAT_MASK
+#define RT_FEAT_MASK F_ALL
+#endif
+
 namespace rtb200dev {
+inline namespace RT_VARIANT_NS {
 
 #define RT_DEV __device__ __forceinline__
+__device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
 #define RT_DEV_COLD static __device__ __noinline__
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
@@ -309,11 +320,11 @@ RT_DEV void s_tri(const SRay &r, const double *pd, double t_min, uint32_t pi, ui
 RT_DEV void s_prim(const DScene &sc, uint32_t pi, const SRay &r, double t_min, Best &best) {
     const DPrim &p = sc.prims[pi];
     uint32_t kind = p.kind, rank = p.rank;
-    if (kind == PRIM_RECT) s_rect(r, p.axis, p.d, t_min, pi, rank, best);
-    else if (kind == PRIM_BOX) s_box(r, p.d, t_min, pi, rank, best);
-    else if (kind == PRIM_SPHERE) s_sphere(r, ld3(p.d), p.d[3], t_min, pi, rank, best);
-    else if (kind == PRIM_TRI) s_tri(r, p.d, t_min, pi, rank, best);
-    else s_sphere(r, msphere_center(p.d, r.time), p.d[8], t_min, pi, rank, best);
+    if (feat(F_RECT) && kind == PRIM_RECT) s_rect(r, p.axis, p.d, t_min, pi, rank, best);
+    else if (feat(F_BOX) && kind == PRIM_BOX) s_box(r, p.d, t_min, pi, rank, best);
+    else if (feat(F_SPHERE) && kind == PRIM_SPHERE) s_sphere(r, ld3(p.d), p.d[3], t_min, pi, rank, best);
+    else if (feat(F_TRI) && kind == PRIM_TRI) s_tri(r, p.d, t_min, pi, rank, best);
+    else if (feat(F_MSPHERE)) s_sphere(r, msphere_center(p.d, r.time), p.d[8], t_min, pi, rank, best);
 }
 
 // Conservative slab test against [t_min, t_max] (culling only; NaN operands are ignored by fmin/fmax).
@@ -368,13 +379,14 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double
     int node = g.bvh_root;
     FRay f;
     float t_min_f = 0.f, t_max_f = 0.f;
+    if (!feat(F_BVH)) node = node >= 0 ? kDone : node;
     if (node >= 0) {
         f = make_fray(r);
         t_min_f = __double2float_rd(t_min);
         t_max_f = __double2float_ru(best.t);
     }
     while (node != kDone) {
-        while (node >= 0) {
+        while (feat(F_BVH) && node >= 0) {
             const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
             float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
             int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
@@ -543,7 +555,7 @@ RT_DEV void resolve_hit_obj(const DScene &sc, const Ray &world, const Best &best
         }
         rec.p = o + t * d;  // r.at(t), ray.rs:26-28
         set_face_normal(rec, d, normal);
-    } else if (kind == PRIM_TRI) {  // tri.rs:24-54; p.d = v0 e1 e2 n
+    } else if (feat(F_TRI) && kind == PRIM_TRI) {  // tri.rs:24-54; p.d = v0 e1 e2 n
         if (want_uv) {
             V3 s = o - ld3(p.d);
             V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
@@ -555,7 +567,7 @@ RT_DEV void resolve_hit_obj(const DScene &sc, const Ray &world, const Best &best
         }
         rec.p = o + t * d;
         set_face_normal(rec, d, ld3(p.d + 9));
-    } else {  // sphere.rs:56-94, :150-188
+    } else if (feat(F_SPHERE | F_MSPHERE)) {  // sphere.rs:56-94, :150-188
         V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, world.time);
         double radius = kind == PRIM_SPHERE ? p.d[3] : p.d[8];
         rec.p = o + t * d;
@@ -588,13 +600,15 @@ RT_DEV double exact_t_obj(const DScene &sc, const Best &best, V3 o, V3 d, double
         double dk = plane == RT_PLANE_XZ ? d.y : (plane == RT_PLANE_YZ ? d.x : d.z);
         return (k - ok) / dk;
     }
-    if (kind == PRIM_TRI) {  // tri.rs:26-33
+    if (!feat(F_SPHERE | F_MSPHERE | F_TRI)) return 0.0;
+    if (feat(F_TRI) && kind == PRIM_TRI) {  // tri.rs:26-33
         V3 s = o - ld3(p.d);
         V3 e1 = ld3(p.d + 3), e2 = ld3(p.d + 6);
         V3 s1 = cross(d, e2);
         V3 s2 = cross(s, e1);
         return dot(s2, e2) / dot(s1, e1);
     }
+    if (!feat(F_SPHERE | F_MSPHERE)) return 0.0;
     V3 center = kind == PRIM_SPHERE ? ld3(p.d) : msphere_center(p.d, time);
     return sphere_root_exact(o, d, center, kind == PRIM_SPHERE ? p.d[3] : p.d[8], t_min);
 }
@@ -759,7 +773,7 @@ RT_DEV V3 texture_value(const DScene &sc, uint32_t id, double u, double v, V3 p)
     for (int guard = 0; guard < 16; ++guard) {
         const DTexture &t = sc.textures[id];
         uint32_t kind = t.kind;
-        if (kind == RT_TEX_CONSTANT) return ld3(t.color);  // texture.rs:23-27
+        if (!feat(F_TEX) || kind == RT_TEX_CONSTANT) return ld3(t.color);  // texture.rs:23-27
         if (kind == RT_TEX_CHECKER) {                       // texture.rs:45-54
             double sines = sin(10.0 * p.x) * sin(10.0 * p.y) * sin(10.0 * p.z);
             id = sines < 0.0 ? t.a : t.b;
@@ -798,7 +812,7 @@ RT_DEV double light_pdf_one(const DLight &l, V3 o, V3 v) {
         double cosine = fabs(vk) / len;
         return cosine != 0.0 ? distance_squared / (cosine * area) : 0.0;
     }
-    if (l.kind == LIGHT_SPHERE) {  // sphere.rs:104-112
+    if (feat(F_SPHERE_LIGHT) && l.kind == LIGHT_SPHERE) {  // sphere.rs:104-112
         V3 center = ld3(l.d);
         V3 oc = o - center;
         double a = powi2(length(v));
@@ -836,7 +850,7 @@ RT_DEV V3 lights_random(const DScene &sc, V3 o, const Draw &dr) {  // hit.rs:94-
         else random_point = mk(a, b, k);
         return random_point - o;
     }
-    if (l.kind == LIGHT_SPHERE) {  // sphere.rs:114-119 + :27-36
+    if (feat(F_SPHERE_LIGHT) && l.kind == LIGHT_SPHERE) {  // sphere.rs:114-119 + :27-36
         V3 direction = ld3(l.d) - o;
         double distance_squared = powi2(length(direction));
         ONB uvw = onb_from_w(direction);
@@ -916,19 +930,19 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
         if (rec.front_face) ps.radiance = ps.radiance + ps.beta * texture_value(sc, m.texture, rec.u, rec.v, rec.p);
         return false;
     }
-    V3 new_dir;
-    V3 factor;
-    if (mkind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
+    V3 new_dir = mk(0.0, 0.0, 0.0);
+    V3 factor = mk(0.0, 0.0, 0.0);
+    if (feat(F_METAL) && mkind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
         V3 reflected = normalized(reflect(ps.ray.d, rec.normal));
         // random_in_unit_sphere is drawn even for fuzz == 0 (§Q12); with slot addressing the
         // draw can be skipped when its product with fuzz is exactly zero.
         new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * random_in_unit_sphere(ps.rng) : reflected;
         if (!(dot(new_dir, rec.normal) > 0.0)) return false;  // None -> emitted (black)
         factor = ld3(m.albedo);
-    } else if (mkind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
+    } else if (feat(F_DIELECTRIC) && mkind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
         new_dir = dielectric_direction(m, ps.ray.d, rec, ps.rng);
         factor = mk(1.0, 1.0, 1.0);
-    } else if (integrator == RT_INTEGRATOR_LEGACY) {
+    } else if (feat(F_LEGACY) && (!feat(F_HEAD) || integrator == RT_INTEGRATOR_LEGACY)) {
         if (mkind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
             new_dir = rec.normal + normalized(random_in_unit_sphere(ps.rng));
             if (near_zero(new_dir)) new_dir = rec.normal;
@@ -936,7 +950,7 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
             new_dir = random_in_unit_sphere(ps.rng);
         }
         factor = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
-    } else {
+    } else if (feat(F_HEAD)) {
         if (mkind != RT_MAT_LAMBERTIAN) return false;  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
         // main.rs:92-98
         V3 attenuation = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
@@ -1002,4 +1016,5 @@ __device__ __forceinline__ bool item_pixel(uint32_t tiles_x, uint32_t width, uin
     return i < width && row < height;
 }
 
+}  // namespace RT_VARIANT_NS
 }  // namespace rtb200dev

@@ -62,11 +62,7 @@ struct WfPool {
     uint32_t n_slots;   // slots used by the current render (<= capacity)
 };
 
-size_t wf_bytes_per_slot();
-// Enqueue `rounds` rounds (shade, generate, extend, control) of the pipeline on `stream`.
-cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream);
-cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
-                            double *planes, unsigned long long *counters, bool media, int sms, cudaStream_t stream);
+// (launchers: per pipeline variant, see variants.h)
 constexpr int kWfLaunchesPerRound = 4;
 
 }  // namespace rtb200dev

@@ -1,4 +1,4 @@
-// wavefront.cu — the sample loop of src/main.rs:772-834 as a wavefront pipeline (sm_100a).
+// wavefront.inl — the sample loop of src/main.rs:772-834 as a wavefront pipeline (sm_100a).
 //
 // The recursion of ray_color (src/main.rs:41-120) is cut at its one recursive call: a path is a
 // slot of an HBM-resident pool (wavefront.h), and a round moves every live path forward by one
@@ -17,12 +17,7 @@
 // All arithmetic is the device code of trace.cuh, shared with the megakernel; a slot runs the
 // samples of its item in sample order into an f64 sum of its own, so the image is bit-identical
 // to the megakernel's and to itself run after run.
-#include <cuda_runtime.h>
-
-#include "trace.cuh"
-#include "wavefront.h"
-
-namespace rtb200dev {
+// (included by pipelines.cu inside the variant namespace)
 
 #ifndef RT_WF_REFILL_THRESHOLD
 #define RT_WF_REFILL_THRESHOLD 24
@@ -39,7 +34,6 @@ namespace rtb200dev {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
-size_t wf_bytes_per_slot() { return sizeof(WfSlot) + sizeof(double4); }
 
 // 128-bit views of a slot record
 __device__ __forceinline__ const double2 *slot_d2(const WfPool &pool, uint32_t slot) { return reinterpret_cast<const double2 *>(pool.slots + slot); }
@@ -506,7 +500,7 @@ __global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned 
 // ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
-cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
+static cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
     unsigned blocks = (pool.n_slots + 255u) / 256u;
     if (blocks > 148u * 8u) blocks = 148u * 8u;
     if (blocks < 1u) blocks = 1u;
@@ -514,7 +508,7 @@ cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
-cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
+static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
                             double *planes, unsigned long long *counters, bool media, int sms, cudaStream_t stream) {
     static int ext_per_sm[2] = {0, 0};
     if (ext_per_sm[0] == 0) {
@@ -541,4 +535,3 @@ cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderP
     return cudaGetLastError();
 }
 
-}  // namespace rtb200dev

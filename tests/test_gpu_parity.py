@@ -235,3 +235,20 @@ def test_wavefront_matches_oracle_image(rt, orc):
     err = rel_err(img, ref, floor=1e-6).max(axis=2)
     assert float((err <= 1e-4).mean()) >= 0.995
     assert stats.kernel_launches > 4
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_feature_variants_identical(rt, orc, name, monkeypatch):
+    """The pipelines are compiled once per scene feature set (variants.h); the build picked for a
+    scene must give the image of the build that has every feature compiled in, bit for bit."""
+    hs, dev, _ = scenes(rt, orc, name)
+    W, H, spp, depth = 80, 60, 12, 100
+    for flag in (rt._abi.FLAG_MEGAKERNEL, rt._abi.FLAG_WAVEFRONT):
+        opts = rt.render_opts(seed=9, integrator=hs.integrator, flags=flag)
+        monkeypatch.delenv("RTB200_VARIANT", raising=False)
+        a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
+        monkeypatch.setenv("RTB200_VARIANT", "vall")
+        b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
+        monkeypatch.delenv("RTB200_VARIANT", raising=False)
+        assert np.array_equal(a, b, equal_nan=True)
+        assert sa.rays == sb.rays

@@ -11,7 +11,7 @@ for spec in "$@"; do
     out=$root/variants_build/$name
     mkdir -p $out
     cd raytracinginrust_b200/csrc
-    make -s OUT=$out EXTRA_NVCCFLAGS="$flags" > $out/build.log 2>&1 || echo "build failed: $name"
+    make -s -j4 OUT=$out EXTRA_NVCCFLAGS="$flags" > $out/build.log 2>&1 || echo "build failed: $name"
     grep -E "wf_extend|wf_shade|render_kernel" -A2 $out/ptxas.log | grep -oE "Used [0-9]+ registers|[0-9]+ bytes spill stores" | paste -sd' ' | sed "s|^|$name: |"
   ) &
 done
