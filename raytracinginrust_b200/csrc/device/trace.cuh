@@ -895,7 +895,7 @@ RT_DEV V3 random_cosine_direction(double r1, double r2) {  // pdf.rs:8-18
 struct PathState {
     Ray ray;
     V3 beta;      // product of the factors the recursion multiplies on the way back up
-    V3 radiance;  // what ray_color returns for the camera ray, accumulated front to back
+    V3 radiance;  // what ray_color returns for the camera ray: written by the segment that ends the path
     Rng rng;
     uint32_t depth_left;
     uint32_t segments;
@@ -909,6 +909,7 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
 // that scenes without volumes do not carry the boundary-query loop).
 template <bool MEDIA>
 RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint32_t flags) {
+    ps.radiance = mk(0.0, 0.0, 0.0);
     if (ps.depth_left == 0) return false;  // main.rs:42-45: contributes black
     HitRec rec;
     ps.segments += 1;
@@ -918,6 +919,10 @@ RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint
 
 // Everything ray_color does after world.hit returned (main.rs:62-119).
 RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags) {
+    // Every factor of the recursion L = emitted + f * L_next is zero-emission until the path ends
+    // (only DiffuseLight emits, and it never scatters), so the camera ray's radiance is written
+    // once, by the last segment: 0 + beta * emitted.  It is not carried from segment to segment.
+    ps.radiance = mk(0.0, 0.0, 0.0);
     if (!hit) {  // main.rs:118
         ps.radiance = ps.radiance + ps.beta * ld3(sc.background);
         return false;

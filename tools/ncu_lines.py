@@ -11,13 +11,16 @@ def run(cmd, cwd=None):
 
 def sass_lines(lib, kernel_sub, n_expected):
     """(file, line) of every SASS instruction of the kernel section whose size matches the capture."""
-    tmp = tempfile.mkdtemp()
-    run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp)
+    # `lib` may be a comma-separated list (.so or .o): objects compiled from the same source give
+    # cubins of the same name, so each file is extracted into a directory of its own
+    cubins = []
+    for one in lib.split(","):
+        tmp = tempfile.mkdtemp()
+        run(["cuobjdump", "-xelf", "all", os.path.abspath(one)], cwd=tmp)
+        cubins += [os.path.join(tmp, f) for f in sorted(os.listdir(tmp)) if f.endswith(".cubin")]
     best = None
-    for f in sorted(os.listdir(tmp)):
-        if not f.endswith(".cubin"):
-            continue
-        lines = run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)]).split("\n")
+    for f in cubins:
+        lines = run(["nvdisasm", "-gi", "-c", f]).split("\n")
         starts = [i for i, l in enumerate(lines) if l.strip().startswith(".section") and ".text." in l and kernel_sub in l]
         for start in starts:
             order, cur, open_ = [], None, False

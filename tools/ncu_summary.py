@@ -64,32 +64,12 @@ def main():
     for k, v in dyn.most_common(16):
         print("%-10s %5.1f%%   avg active threads %.1f" % (k, 100.0 * v / tot, thr[k] / max(v, 1)))
 
-    # per-function attribution through nvdisasm line info
-    tmp = tempfile.mkdtemp()
-    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    dis = ""
-    for f in os.listdir(tmp):
-        if f.endswith(".cubin"):
-            d = run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)])
-            if kernel in d:
-                dis = d
-    lines = dis.split("\n")
-    start = next((i for i, l in enumerate(lines) if l.strip().startswith(".section") and kernel in l and ".text." in l), None)
-    if start is None:
-        return
-    order, cur, open_ = [], None, False
-    for l in lines[start + 1:]:
-        if l.strip().startswith(".section"):
-            break
-        mm = re.search(r'//## File "([^"]+)", line (\d+)', l)
-        if mm:
-            if not open_:
-                cur, open_ = (mm.group(1), int(mm.group(2))), True
-        elif re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S+", l):
-            order.append(cur)
-            open_ = False
-    if len(order) != len(body):
-        print("\n(per-function attribution skipped: SASS listing and capture differ: %d vs %d)" % (len(order), len(body)))
+    # per-function attribution through nvdisasm line info (lib: .so or a comma-separated list of .o)
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from ncu_lines import sass_lines
+    order = sass_lines(lib, kernel, len(body))
+    if order is None or len(order) != len(body):
+        print("\n(per-function attribution skipped: SASS listing and capture differ: %s vs %d)" % (None if order is None else len(order), len(body)))
         return
     cache = {}
 
