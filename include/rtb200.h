@@ -84,14 +84,21 @@ typedef struct RtNode {
     double v[10];      /* parameters, meaning per kind (see RtNodeKind)           */
 } RtNode;
 
-/* src/mat.rs:199-422.  PBR (src/mat.rs:86-197) is not on the accelerated path. */
+/* src/mat.rs:86-422. */
 typedef enum RtMaterialKind {
     RT_MAT_LAMBERTIAN = 0,    /* texture = albedo                      */
     RT_MAT_METAL = 1,         /* albedo[3], fuzz                       */
     RT_MAT_DIELECTRIC = 2,    /* ir                                    */
     RT_MAT_DIFFUSE_LIGHT = 3, /* texture = emit                        */
-    RT_MAT_ISOTROPIC = 4      /* texture = albedo (legacy integrator)  */
+    RT_MAT_ISOTROPIC = 4,     /* texture = albedo (legacy integrator)  */
+    RT_MAT_PBR = 5            /* texture = base_color, pbr[10]: the Disney-style material of
+                                 src/mat.rs:86-197, sampled through PDF::BRDF (src/pdf.rs:20-60,97-130,151-160) */
 } RtMaterialKind;
+
+/* Index of each PBR::new argument (src/mat.rs:101-115) in RtMaterial.pbr */
+enum { RT_PBR_METALLIC = 0, RT_PBR_SUBSURFACE = 1, RT_PBR_SPECULAR = 2, RT_PBR_ROUGHNESS = 3,
+       RT_PBR_SPECULAR_TINT = 4, RT_PBR_ANISOTROPIC = 5, RT_PBR_SHEEN = 6, RT_PBR_SHEEN_TINT = 7,
+       RT_PBR_CLEARCOAT = 8, RT_PBR_CLEARCOAT_GLOSS = 9 };
 
 typedef struct RtMaterial {
     uint32_t kind;
@@ -99,6 +106,7 @@ typedef struct RtMaterial {
     double albedo[3];
     double fuzz;
     double ir;
+    double pbr[10];
 } RtMaterial;
 
 /* src/texture.rs */

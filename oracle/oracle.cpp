@@ -1059,13 +1059,140 @@ inline Vec3 random_cosine_direction(double r1, double r2) {
     return Vec3(x, y, z);
 }
 
-enum ScatterKind { SC_NONE, SC_SPECULAR, SC_SCATTER };
+enum ScatterKind { SC_NONE, SC_SPECULAR, SC_SCATTER, SC_MICROFACET };
 struct ScatterRecord {
     ScatterKind kind = SC_NONE;
     Ray specular_ray;
     Vec3 attenuation;
-    ONB cosine_uvw;  // PDF::Cosine { uvw } (pdf.rs:83-87)
+    ONB cosine_uvw;  // PDF::Cosine { uvw } (pdf.rs:83-87); PDF::BRDF { uvw, .. } (pdf.rs:70-79)
+    Vec3 brdf_r_in;  // PDF::BRDF { r_in }: the incoming direction, world space, not normalised
 };
+
+// ---- the Disney-style PBR material (mat.rs:10-52, :86-197) and PDF::BRDF (pdf.rs:20-60, :97-130, :151-160) ----
+inline double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }  // f64::clamp(0.0, 1.0): NaN stays NaN
+inline double schlick_fresnel(double u) {  // mat.rs:10-14
+    double m = clamp01(1.0 - u);
+    double m2 = powi2(m);
+    return m2 * m2 * m;
+}
+inline double GTR_1(double n_dot_h, double a) {  // mat.rs:16-24 (log2, as written)
+    if (a >= 1.0) return 1.0 / PI;
+    double a2 = a * a;
+    double t = 1.0 + (a2 - 1.0) * n_dot_h * n_dot_h;
+    return (a2 - 1.0) / (PI * std::log2(a2) * t);
+}
+inline double GTR_2_aniso(double n_dot_h, double h_dot_x, double h_dot_y, double ax, double ay) {  // mat.rs:32-34
+    return 1.0 / (PI * ax * ay * powi2(powi2(h_dot_x / ax) + powi2(h_dot_y / ay) + n_dot_h * n_dot_h));
+}
+inline double smithG_GGX(double n_dot_v, double alphaG) {  // mat.rs:36-40
+    double a = alphaG * alphaG;
+    double b = n_dot_v * n_dot_v;
+    return 1.0 / (n_dot_v + std::sqrt(a + b - a * b));
+}
+inline double smithG_GGX_aniso(double n_dot_v, double v_dot_x, double v_dot_y, double ax, double ay) {  // mat.rs:42-44
+    return 1.0 / (n_dot_v + std::sqrt(powi2(v_dot_x * ax) + powi2(v_dot_y * ay) + powi2(n_dot_v)));
+}
+inline Vec3 mon_to_lin(Vec3 x) { return Vec3(std::pow(x.x(), 2.2), std::pow(x.y(), 2.2), std::pow(x.z(), 2.2)); }  // mat.rs:46-48
+inline double mixd(double a, double b, double t) { return a * (1.0 - t) + b * t; }                                  // mat.rs:50-52
+inline Vec3 mixv(Vec3 a, Vec3 b, double t) {                                                                       // vec.rs:60-68
+    return Vec3(a[0] * (1.0 - t) + b[0] * t, a[1] * (1.0 - t) + b[1] * t, a[2] * (1.0 - t) + b[2] * t);
+}
+inline void pbr_alpha(const RtMaterial &m, double &ax, double &ay) {  // mat.rs:168-170 == pdf.rs:42-44 == :119-121
+    double aspect = std::sqrt(1.0 - m.pbr[RT_PBR_ANISOTROPIC] * 0.9);
+    ax = std::fmax(powi2(m.pbr[RT_PBR_ROUGHNESS]) / aspect, 0.001);
+    ay = std::fmax(powi2(m.pbr[RT_PBR_ROUGHNESS]) * aspect, 0.001);
+}
+
+// PBR::brdf (mat.rs:133-195)
+inline Vec3 pbr_brdf(const SceneData &sd, const RtMaterial &m, Vec3 r_in_dir, Vec3 r_out_dir, const HitRecord &rec) {
+    const double metallic = m.pbr[RT_PBR_METALLIC], subsurface = m.pbr[RT_PBR_SUBSURFACE], specular = m.pbr[RT_PBR_SPECULAR],
+                 roughness = m.pbr[RT_PBR_ROUGHNESS], specular_tint = m.pbr[RT_PBR_SPECULAR_TINT], sheen = m.pbr[RT_PBR_SHEEN],
+                 sheen_tint = m.pbr[RT_PBR_SHEEN_TINT], clearcoat = m.pbr[RT_PBR_CLEARCOAT], clearcoat_gloss = m.pbr[RT_PBR_CLEARCOAT_GLOSS];
+    Vec3 l = normalized(r_in_dir) * (-1.0);
+    Vec3 v = normalized(r_out_dir);
+    ONB onb = ONB::build_from_w(rec.normal);
+    Vec3 n = onb.w, x = onb.u, y = onb.v;
+    double n_dot_v = dot(n, v);
+    double n_dot_l = dot(n, l);
+    if (n_dot_l < 0.0 || n_dot_v < 0.0) return Vec3(0.0, 0.0, 0.0);
+    Vec3 h = normalized(l + v);
+    double n_dot_h = dot(n, h);
+    double l_dot_h = dot(l, h);
+    Vec3 cd_lin = mon_to_lin(sd.tex(m.texture, rec.u, rec.v, rec.position));
+    double cd_lum = 0.3 * cd_lin.x() + 0.6 * cd_lin.y() + 0.1 * cd_lin.z();
+    Vec3 c_tint = cd_lum > 0.0 ? cd_lin / cd_lum : Vec3(1.0, 1.0, 1.0);
+    Vec3 c_spec0 = mixv((mixv(Vec3(1.0, 1.0, 1.0), c_tint, specular_tint) * 0.08) * specular, cd_lin, metallic);
+    Vec3 c_sheen = mixv(Vec3(1.0, 1.0, 1.0), c_tint, sheen_tint);
+    double fresnel_l = schlick_fresnel(n_dot_l);
+    double fresnel_v = schlick_fresnel(n_dot_v);
+    double fresnel_diffuse_90 = 0.5 + 2.0 * l_dot_h * l_dot_h * roughness;
+    double fresnel_diffuse = mixd(1.0, fresnel_diffuse_90, fresnel_l) * mixd(1.0, fresnel_diffuse_90, fresnel_v);
+    double fss90 = l_dot_h * l_dot_h * roughness;
+    double fss = mixd(1.0, fss90, fresnel_l) * mixd(1.0, fss90, fresnel_v);
+    double subface_scatter = 1.25 * (fss * (1.0 / (n_dot_l + n_dot_v) - 0.5) + 0.5);
+    double ax, ay;
+    pbr_alpha(m, ax, ay);
+    double d_specular = GTR_2_aniso(n_dot_h, dot(h, x), dot(h, y), ax, ay);
+    double fresnel_h = schlick_fresnel(l_dot_h);
+    Vec3 f_specular = mixv(c_spec0, Vec3(1.0, 1.0, 1.0), fresnel_h);
+    double g_specular = smithG_GGX_aniso(n_dot_l, dot(l, x), dot(l, y), ax, ay) * smithG_GGX_aniso(n_dot_v, dot(v, x), dot(v, y), ax, ay);
+    Vec3 fresnel_sheen = (fresnel_h * sheen) * c_sheen;
+    double d_reflect = GTR_1(n_dot_h, mixd(0.1, 0.001, clearcoat_gloss));
+    double f_reflect = mixd(0.04, 1.0, fresnel_h);
+    double g_reflect = smithG_GGX(n_dot_l, 0.25) * smithG_GGX(n_dot_v, 0.25);
+    return ((((1.0 / PI) * mixd(fresnel_diffuse, subface_scatter, subsurface)) * cd_lin + fresnel_sheen) * (1.0 - metallic) +
+            (g_specular * f_specular) * d_specular) +
+           (((Vec3(0.25, 0.25, 0.25) * clearcoat) * g_reflect) * f_reflect) * d_reflect;
+}
+
+// PDF::BRDF value (pdf.rs:97-130)
+inline double brdf_pdf_value(const ONB &uvw, Vec3 r_in, const RtMaterial &m, Vec3 r_out) {
+    double cosine = dot(normalized(r_out), uvw.w);
+    if (cosine <= 0.0) return 0.0;
+    double diffuse_pdf = cosine / PI;
+    Vec3 l = normalized(r_in) * (-1.0);
+    Vec3 v = normalized(r_out);
+    Vec3 n = uvw.w, x = uvw.u, y = uvw.v;
+    double n_dot_l = dot(n, l);
+    Vec3 h = normalized(l + v);
+    double n_dot_h = dot(n, h);
+    if (n_dot_h <= 0.0) return 0.0;
+    double ax, ay;
+    pbr_alpha(m, ax, ay);
+    double specular_pdf = GTR_2_aniso(n_dot_h, dot(h, x), dot(h, y), ax, ay) * std::fabs(n_dot_h) * 0.25 / n_dot_l;
+    double clearcoat_pdf = GTR_1(n_dot_h, mixd(0.1, 0.001, m.pbr[RT_PBR_CLEARCOAT_GLOSS])) * std::fabs(n_dot_h) * 0.25 / n_dot_l;
+    return (diffuse_pdf + specular_pdf + clearcoat_pdf) / 3.0;
+}
+inline Vec3 spherical_direction(double sin_theta, double cos_theta, double sin_phi, double cos_phi) {  // pdf.rs:20-22
+    return Vec3(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta);
+}
+// pdf.rs:24-36.  r_in is the world-space incoming direction, wh a tangent-space half vector: the
+// reference reflects one about the other as written, then maps the result through uvw.local.
+inline Vec3 GTR_1_direction(Vec3 r_in, double clearcoat_gloss, double r1, double r2) {
+    double a = mixd(0.1, 0.001, clearcoat_gloss);
+    double a2 = a * a;
+    double cos_theta = std::sqrt(std::fmax(0.001, (1.0 - std::pow(a2, 1.0 - r1)) / (1.0 - a2)));
+    double sin_theta = std::sqrt(std::fmax(0.001, 1.0 - cos_theta * cos_theta));
+    double phi = PI * 2.0 * r2;
+    Vec3 wh = spherical_direction(sin_theta, cos_theta, std::sin(phi), std::cos(phi));
+    return reflect(r_in, wh);
+}
+inline Vec3 GTR_2_aniso_direction(Vec3 r_in, const RtMaterial &m, double r1, double r2) {  // pdf.rs:38-60
+    double ax, ay;
+    pbr_alpha(m, ax, ay);
+    double phi = std::atan(ay / ax * std::tan(2.0 * PI * r2 + 0.5 * PI));
+    if (r2 > 0.5) phi += PI;
+    double sin_phi = std::sin(phi);
+    double cos_phi = std::cos(phi);
+    double ax_2 = ax * ax;
+    double ay_2 = ay * ay;
+    double a2 = 1.0 / (cos_phi * cos_phi / ax_2 + sin_phi * sin_phi / ay_2);
+    double tan_theta_2 = a2 * r1 / (1.0 - r1);
+    double cos_theta = 1.0 / std::sqrt(1.0 + tan_theta_2);
+    double sin_theta = std::sqrt(std::fmax(0.001, 1.0 - cos_theta * cos_theta));
+    Vec3 wh = spherical_direction(sin_theta, cos_theta, std::sin(phi), std::cos(phi));
+    return reflect(r_in, wh);
+}
 
 // Material::emitted (mat.rs:70-72 default, :395-401 DiffuseLight)
 inline Vec3 emitted(const SceneData &sd, const HitRecord &rec) {
@@ -1116,6 +1243,11 @@ inline ScatterRecord scatter_mc(const SceneData &sd, const Ray &r_in, const HitR
             s.kind = SC_SPECULAR;
             s.attenuation = Vec3(1.0, 1.0, 1.0);
             s.specular_ray = Ray(rec.position, dielectric_direction(m, r_in, rec, rng), r_in.time);
+            break;
+        case RT_MAT_PBR:  // mat.rs:118-131
+            s.kind = SC_MICROFACET;
+            s.cosine_uvw = ONB::build_from_w(rec.normal);  // PDF::brdf_pdf (pdf.rs:70-79)
+            s.brdf_r_in = r_in.dir;
             break;
         default:  // DiffuseLight, Isotropic: trait default None (§Q6)
             break;
@@ -1179,6 +1311,25 @@ Vec3 ray_color(const Ray &ray, PathCtx &pc, uint32_t depth, uint32_t bounce) {
     if (srec.kind == SC_NONE) return em;                                          // main.rs:108-110
     if (srec.kind == SC_SPECULAR)                                                 // main.rs:89-91
         return srec.attenuation * ray_color(srec.specular_ray, pc, depth - 1, bounce + 1);
+    if (srec.kind == SC_MICROFACET) {  // main.rs:99-105: mixture of the light pdf and PDF::BRDF
+        const RtMaterial &m = sd.materials[rec.material];
+        Draw d = pc.rng.draw(SLOT_SCATTER, 0);
+        const HittableList &lights = *pc.sc->lights;
+        Vec3 dir;
+        if (d.bits_a & 1u) {  // pdf.rs:169
+            dir = lights.random(rec.position, d);
+        } else {  // pdf.rs:151-160: lobe by gen_range(0.0..1.0), then the lobe's own (r1, r2)
+            double lobe = pc.rng.draw(SLOT_SCATTER, 1).a;
+            if (lobe < 0.333) dir = srec.cosine_uvw.local(random_cosine_direction(d.a, d.b));
+            else if (lobe < 0.666) dir = srec.cosine_uvw.local(GTR_1_direction(srec.brdf_r_in, m.pbr[RT_PBR_CLEARCOAT_GLOSS], d.a, d.b));
+            else dir = srec.cosine_uvw.local(GTR_2_aniso_direction(srec.brdf_r_in, m, d.a, d.b));
+        }
+        Ray scattered(rec.position, dir, ray.time);
+        double pdf_value = 0.5 * lights.pdf_value(rec.position, scattered.dir) + 0.5 * brdf_pdf_value(srec.cosine_uvw, srec.brdf_r_in, m, scattered.dir);
+        Vec3 f = pbr_brdf(sd, m, ray.dir, scattered.dir, rec);
+        Vec3 li = ray_color(scattered, pc, depth - 1, bounce + 1);
+        return em + (f * li) / pdf_value;
+    }
     // main.rs:92-98: mixture of the light pdf and the cosine pdf
     Draw d = pc.rng.draw(SLOT_SCATTER, 0);
     const HittableList &lights = *pc.sc->lights;
@@ -1304,7 +1455,7 @@ int oracle_scene_create(const RtSceneDesc *d, OScene **out) {
     if (d->n_texel_bytes) sd.texels.assign(d->texels, d->texels + d->n_texel_bytes);
     sd.background = Vec3(d->background[0], d->background[1], d->background[2]);
     for (const RtMaterial &m : sd.materials)
-        if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC) &&
+        if ((m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC || m.kind == RT_MAT_PBR) &&
             m.texture >= sd.textures.size()) {
             g_err = "texture index out of range";
             return RT_ERR_BAD_ARGUMENT;
@@ -1485,6 +1636,17 @@ void oracle_refract(const double v[3], const double n[3], double eta, double out
     out[0] = r[0]; out[1] = r[1]; out[2] = r[2];
 }
 double oracle_reflectance(double cosine, double ir) { return reflectance(cosine, ir); }
+// the scalar helpers of the PBR material (mat.rs:10-44): which = 0 schlick_fresnel(a), 1 GTR_1(a, b),
+// 2 GTR_2_aniso(a, b, c, d, e), 3 smithG_GGX(a, b), 4 smithG_GGX_aniso(a, b, c, d, e)
+double oracle_pbr_scalar(int which, double a, double b, double c, double d, double e) {
+    switch (which) {
+        case 0: return schlick_fresnel(a);
+        case 1: return GTR_1(a, b);
+        case 2: return GTR_2_aniso(a, b, c, d, e);
+        case 3: return smithG_GGX(a, b);
+        default: return smithG_GGX_aniso(a, b, c, d, e);
+    }
+}
 void oracle_random_cosine_direction(double r1, double r2, double out[3]) {
     Vec3 d = random_cosine_direction(r1, r2);
     out[0] = d[0]; out[1] = d[1]; out[2] = d[2];

@@ -60,6 +60,8 @@ def _lib():
     lib.oracle_refract.restype = None
     lib.oracle_reflectance.argtypes = [C.c_double, C.c_double]
     lib.oracle_reflectance.restype = C.c_double
+    lib.oracle_pbr_scalar.argtypes = [C.c_int] + [C.c_double] * 5
+    lib.oracle_pbr_scalar.restype = C.c_double
     lib.oracle_random_cosine_direction.argtypes = [C.c_double, C.c_double, dp]
     lib.oracle_random_cosine_direction.restype = None
     lib.oracle_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_double, C.c_double, dp, dp]
@@ -198,6 +200,11 @@ def refract(v, n, eta):
 
 def reflectance(cosine, ir):
     return float(lib.oracle_reflectance(cosine, ir))
+
+
+def pbr_scalar(which, a, b=0.0, c=0.0, d=0.0, e=0.0):
+    """mat.rs:10-44: 0 schlick_fresnel, 1 GTR_1, 2 GTR_2_aniso, 3 smithG_GGX, 4 smithG_GGX_aniso."""
+    return float(lib.oracle_pbr_scalar(int(which), a, b, c, d, e))
 
 
 def random_cosine_direction(r1, r2):

@@ -216,6 +216,14 @@ class SceneBuilder:
     def isotropic(self, texture):
         return self._mat(_abi.MAT_ISOTROPIC, texture=texture)
 
+    def pbr(self, base_color, metallic=0.0, subsurface=0.0, specular=0.0, roughness=1.0, specular_tint=0.0,
+            anisotropic=0.0, sheen=0.0, sheen_tint=0.0, clearcoat=0.0, clearcoat_gloss=0.0):
+        """PBR::new(base_color texture, ...) in the argument order of src/mat.rs:101-115."""
+        k = self._mat(_abi.MAT_PBR, texture=base_color)
+        self.materials[k].pbr[:] = [float(x) for x in (metallic, subsurface, specular, roughness, specular_tint,
+                                                       anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss)]
+        return k
+
     # hittables
     def _node(self, kind, material=_abi.RT_NONE, child=_abi.RT_NONE, count=0, axis=0, v=()):
         n = RtNode()

@@ -19,7 +19,7 @@ STATUS_NAMES = ["RT_OK", "RT_ERR_BAD_ARGUMENT", "RT_ERR_EMPTY_SCENE", "RT_ERR_UN
  NODE_ROTATE, NODE_FLIP, NODE_MEDIUM) = range(11)
 PLANE_YZ, PLANE_XZ, PLANE_XY = 0, 1, 2
 AXIS_X, AXIS_Y, AXIS_Z = 0, 1, 2
-MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC = range(5)
+MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT, MAT_ISOTROPIC, MAT_PBR = range(6)
 TEX_CONSTANT, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = range(4)
 INTEGRATOR_HEAD, INTEGRATOR_LEGACY = 0, 1
 FLAG_TRACE_ZERO_THROUGHPUT = 1
@@ -34,7 +34,7 @@ class RtNode(C.Structure):
 
 class RtMaterial(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("texture", C.c_uint32), ("albedo", C.c_double * 3), ("fuzz", C.c_double),
-                ("ir", C.c_double)]
+                ("ir", C.c_double), ("pbr", C.c_double * 10)]
 
 
 class RtTexture(C.Structure):

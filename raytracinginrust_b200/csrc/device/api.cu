@@ -123,6 +123,12 @@ bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_dept
     return s.wavefront_default;
 }
 
+// A path whose throughput is exactly zero contributes nothing - unless something later in it is
+// NaN, because 0 * NaN is NaN and the reference has no guard (§Q10, §Q11).  With the reference's
+// PBR material that is common (0/0 at main.rs:104 for directions sampled below the surface), so
+// scenes that use it keep tracing zero-throughput paths, exactly like the reference.
+uint32_t pbr_flags(const RtScene &s) { return (s.features & F_PBR) ? RT_FLAG_TRACE_ZERO_THROUGHPUT : 0u; }
+
 RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
                      const RtRenderOpts *opts, bool wavefront, RenderParams &P) {
     if (width < 2 || height < 2) return fail(RT_ERR_BAD_ARGUMENT, "width and height must be at least 2 (main.rs:817-818 divides by W-1, H-1)");
@@ -143,7 +149,7 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.max_depth = max_depth;
     P.seed = o.seed;
     P.integrator = o.integrator;
-    P.flags = o.flags;
+    P.flags = o.flags | pbr_flags(s);
     P.sample_begin = begin;
     P.sample_end = begin + count;
     P.tiles_x = (width + 7) / 8;
@@ -185,6 +191,7 @@ uint32_t scene_features(const CompiledScene &cs) {
     for (const DMaterial &m : cs.materials) {
         if (m.kind == RT_MAT_METAL) f |= F_METAL;
         if (m.kind == RT_MAT_DIELECTRIC) f |= F_DIELECTRIC;
+        if (m.kind == RT_MAT_PBR) f |= F_PBR;
     }
     return f;
 }
@@ -483,7 +490,7 @@ static RtStatus hook_params(const RtScene &s, uint32_t width, uint32_t height, u
     P.max_depth = max_depth;
     P.seed = o.seed;
     P.integrator = o.integrator;
-    P.flags = o.flags;
+    P.flags = o.flags | pbr_flags(s);
     return RT_OK;
 }
 

@@ -826,11 +826,12 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         for (int a = 0; a < 3; ++a) dm.albedo[a] = m.albedo[a];
         dm.fuzz = m.fuzz;
         dm.ir = m.ir;
-        if (m.kind > RT_MAT_ISOTROPIC) {
+        for (int a = 0; a < 10; ++a) dm.pbr[a] = m.pbr[a];
+        if (m.kind > RT_MAT_PBR) {
             err = "unknown material kind";
             return RT_ERR_UNSUPPORTED;
         }
-        bool textured = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC;
+        bool textured = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC || m.kind == RT_MAT_PBR;
         if (textured && m.texture >= d.n_textures) {
             err = "texture index out of range";
             return RT_ERR_BAD_ARGUMENT;

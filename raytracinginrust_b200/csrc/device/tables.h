@@ -103,6 +103,7 @@ struct alignas(16) DMaterial {
     double albedo[3];
     double fuzz, ir;
     double pad2;
+    double pbr[10];  // RT_MAT_PBR: PBR::new's ten scalars (RT_PBR_* order)
 };
 
 struct alignas(16) DTexture {
@@ -131,6 +132,7 @@ enum Feat : uint32_t {
     F_SPHERE_LIGHT = 128,  // a sphere in the light list
     F_METAL = 256, F_DIELECTRIC = 512,
     F_LEGACY = 1024, F_HEAD = 2048,  // which ray_color (a render option, added at render time)
+    F_PBR = 4096,                    // the Disney-style material (mat.rs:86-197) and PDF::BRDF
     F_ALL = 0xFFFFFFFFu
 };
 

@@ -892,6 +892,134 @@ RT_DEV V3 random_cosine_direction(double r1, double r2) {  // pdf.rs:8-18
     return mk(x, y, z);
 }
 
+// ---------------------------------------------------------------------------
+// The Disney-style PBR material (mat.rs:10-52, :86-197) and PDF::BRDF (pdf.rs:20-60, :97-130, :151-160)
+// ---------------------------------------------------------------------------
+RT_DEV double clamp01(double x) { return x < 0.0 ? 0.0 : (x > 1.0 ? 1.0 : x); }  // f64::clamp: NaN stays NaN
+RT_DEV double schlick_fresnel(double u) {  // mat.rs:10-14
+    double m = clamp01(1.0 - u);
+    double m2 = powi2(m);
+    return m2 * m2 * m;
+}
+RT_DEV double GTR_1(double n_dot_h, double a) {  // mat.rs:16-24 (log2, as written)
+    if (a >= 1.0) return 1.0 / kPi;
+    double a2 = a * a;
+    double t = 1.0 + (a2 - 1.0) * n_dot_h * n_dot_h;
+    return (a2 - 1.0) / (kPi * log2(a2) * t);
+}
+RT_DEV double GTR_2_aniso(double n_dot_h, double h_dot_x, double h_dot_y, double ax, double ay) {  // mat.rs:32-34
+    return 1.0 / (kPi * ax * ay * powi2(powi2(h_dot_x / ax) + powi2(h_dot_y / ay) + n_dot_h * n_dot_h));
+}
+RT_DEV double smithG_GGX(double n_dot_v, double alphaG) {  // mat.rs:36-40
+    double a = alphaG * alphaG;
+    double b = n_dot_v * n_dot_v;
+    return 1.0 / (n_dot_v + sqrt(a + b - a * b));
+}
+RT_DEV double smithG_GGX_aniso(double n_dot_v, double v_dot_x, double v_dot_y, double ax, double ay) {  // mat.rs:42-44
+    return 1.0 / (n_dot_v + sqrt(powi2(v_dot_x * ax) + powi2(v_dot_y * ay) + powi2(n_dot_v)));
+}
+RT_DEV double mixd(double a, double b, double t) { return a * (1.0 - t) + b * t; }  // mat.rs:50-52
+RT_DEV V3 mixv(V3 a, V3 b, double t) {                                              // vec.rs:60-68
+    return mk(a.x * (1.0 - t) + b.x * t, a.y * (1.0 - t) + b.y * t, a.z * (1.0 - t) + b.z * t);
+}
+RT_DEV void pbr_alpha(const DMaterial &m, double &ax, double &ay) {  // mat.rs:168-170 == pdf.rs:42-44 == :119-121
+    double aspect = sqrt(1.0 - m.pbr[RT_PBR_ANISOTROPIC] * 0.9);
+    ax = fmax(powi2(m.pbr[RT_PBR_ROUGHNESS]) / aspect, 0.001);
+    ay = fmax(powi2(m.pbr[RT_PBR_ROUGHNESS]) * aspect, 0.001);
+}
+// PBR::brdf (mat.rs:133-195); cd = base_color.mapping(u, v, p)
+RT_DEV_COLD V3 pbr_brdf(const DMaterial *mp, V3 cd, V3 r_in_dir, V3 r_out_dir, V3 normal) {
+    const DMaterial &m = *mp;
+    const double metallic = m.pbr[RT_PBR_METALLIC], subsurface = m.pbr[RT_PBR_SUBSURFACE], specular = m.pbr[RT_PBR_SPECULAR],
+                 roughness = m.pbr[RT_PBR_ROUGHNESS], specular_tint = m.pbr[RT_PBR_SPECULAR_TINT], sheen = m.pbr[RT_PBR_SHEEN],
+                 sheen_tint = m.pbr[RT_PBR_SHEEN_TINT], clearcoat = m.pbr[RT_PBR_CLEARCOAT], clearcoat_gloss = m.pbr[RT_PBR_CLEARCOAT_GLOSS];
+    V3 l = normalized(r_in_dir) * (-1.0);
+    V3 v = normalized(r_out_dir);
+    ONB onb = onb_from_w(normal);
+    V3 n = onb.w, x = onb.u, y = onb.v;
+    double n_dot_v = dot(n, v);
+    double n_dot_l = dot(n, l);
+    if (n_dot_l < 0.0 || n_dot_v < 0.0) return mk(0.0, 0.0, 0.0);
+    V3 h = normalized(l + v);
+    double n_dot_h = dot(n, h);
+    double l_dot_h = dot(l, h);
+    V3 cd_lin = mk(pow(cd.x, 2.2), pow(cd.y, 2.2), pow(cd.z, 2.2));  // mon_to_lin, mat.rs:46-48
+    double cd_lum = 0.3 * cd_lin.x + 0.6 * cd_lin.y + 0.1 * cd_lin.z;
+    V3 c_tint = cd_lum > 0.0 ? cd_lin / cd_lum : mk(1.0, 1.0, 1.0);
+    V3 c_spec0 = mixv((mixv(mk(1.0, 1.0, 1.0), c_tint, specular_tint) * 0.08) * specular, cd_lin, metallic);
+    V3 c_sheen = mixv(mk(1.0, 1.0, 1.0), c_tint, sheen_tint);
+    double fresnel_l = schlick_fresnel(n_dot_l);
+    double fresnel_v = schlick_fresnel(n_dot_v);
+    double fresnel_diffuse_90 = 0.5 + 2.0 * l_dot_h * l_dot_h * roughness;
+    double fresnel_diffuse = mixd(1.0, fresnel_diffuse_90, fresnel_l) * mixd(1.0, fresnel_diffuse_90, fresnel_v);
+    double fss90 = l_dot_h * l_dot_h * roughness;
+    double fss = mixd(1.0, fss90, fresnel_l) * mixd(1.0, fss90, fresnel_v);
+    double subface_scatter = 1.25 * (fss * (1.0 / (n_dot_l + n_dot_v) - 0.5) + 0.5);
+    double ax, ay;
+    pbr_alpha(m, ax, ay);
+    double d_specular = GTR_2_aniso(n_dot_h, dot(h, x), dot(h, y), ax, ay);
+    double fresnel_h = schlick_fresnel(l_dot_h);
+    V3 f_specular = mixv(c_spec0, mk(1.0, 1.0, 1.0), fresnel_h);
+    double g_specular = smithG_GGX_aniso(n_dot_l, dot(l, x), dot(l, y), ax, ay) * smithG_GGX_aniso(n_dot_v, dot(v, x), dot(v, y), ax, ay);
+    V3 fresnel_sheen = (fresnel_h * sheen) * c_sheen;
+    double d_reflect = GTR_1(n_dot_h, mixd(0.1, 0.001, clearcoat_gloss));
+    double f_reflect = mixd(0.04, 1.0, fresnel_h);
+    double g_reflect = smithG_GGX(n_dot_l, 0.25) * smithG_GGX(n_dot_v, 0.25);
+    return ((((1.0 / kPi) * mixd(fresnel_diffuse, subface_scatter, subsurface)) * cd_lin + fresnel_sheen) * (1.0 - metallic) +
+            (g_specular * f_specular) * d_specular) +
+           (((mk(0.25, 0.25, 0.25) * clearcoat) * g_reflect) * f_reflect) * d_reflect;
+}
+// PDF::BRDF value (pdf.rs:97-130)
+RT_DEV_COLD double brdf_pdf_value(const DMaterial *mp, V3 uu, V3 uv, V3 uw, V3 r_in, V3 r_out) {
+    const DMaterial &m = *mp;
+    double cosine = dot(normalized(r_out), uw);
+    if (cosine <= 0.0) return 0.0;
+    double diffuse_pdf = cosine / kPi;
+    V3 l = normalized(r_in) * (-1.0);
+    V3 v = normalized(r_out);
+    double n_dot_l = dot(uw, l);
+    V3 h = normalized(l + v);
+    double n_dot_h = dot(uw, h);
+    if (n_dot_h <= 0.0) return 0.0;
+    double ax, ay;
+    pbr_alpha(m, ax, ay);
+    double specular_pdf = GTR_2_aniso(n_dot_h, dot(h, uu), dot(h, uv), ax, ay) * fabs(n_dot_h) * 0.25 / n_dot_l;
+    double clearcoat_pdf = GTR_1(n_dot_h, mixd(0.1, 0.001, m.pbr[RT_PBR_CLEARCOAT_GLOSS])) * fabs(n_dot_h) * 0.25 / n_dot_l;
+    return (diffuse_pdf + specular_pdf + clearcoat_pdf) / 3.0;
+}
+RT_DEV V3 spherical_direction(double sin_theta, double cos_theta, double sin_phi, double cos_phi) {  // pdf.rs:20-22
+    return mk(sin_theta * cos_phi, sin_theta * sin_phi, cos_theta);
+}
+// pdf.rs:24-36 and :38-60.  r_in is the world-space incoming direction, wh a tangent-space half
+// vector: the reference reflects one about the other as written, then maps the result through uvw.local.
+RT_DEV_COLD V3 brdf_lobe_direction(const DMaterial *mp, bool aniso, V3 r_in, double r1, double r2) {
+    const DMaterial &m = *mp;
+    V3 wh;
+    if (!aniso) {  // GTR_1_direction
+        double a = mixd(0.1, 0.001, m.pbr[RT_PBR_CLEARCOAT_GLOSS]);
+        double a2 = a * a;
+        double cos_theta = sqrt(fmax(0.001, (1.0 - pow(a2, 1.0 - r1)) / (1.0 - a2)));
+        double sin_theta = sqrt(fmax(0.001, 1.0 - cos_theta * cos_theta));
+        double phi = kPi * 2.0 * r2;
+        wh = spherical_direction(sin_theta, cos_theta, sin(phi), cos(phi));
+    } else {  // GTR_2_aniso_direction
+        double ax, ay;
+        pbr_alpha(m, ax, ay);
+        double phi = atan(ay / ax * tan(2.0 * kPi * r2 + 0.5 * kPi));
+        if (r2 > 0.5) phi += kPi;
+        double sin_phi = sin(phi);
+        double cos_phi = cos(phi);
+        double ax_2 = ax * ax;
+        double ay_2 = ay * ay;
+        double a2 = 1.0 / (cos_phi * cos_phi / ax_2 + sin_phi * sin_phi / ay_2);
+        double tan_theta_2 = a2 * r1 / (1.0 - r1);
+        double cos_theta = 1.0 / sqrt(1.0 + tan_theta_2);
+        double sin_theta = sqrt(fmax(0.001, 1.0 - cos_theta * cos_theta));
+        wh = spherical_direction(sin_theta, cos_theta, sin(phi), cos(phi));
+    }
+    return reflect(r_in, wh);
+}
+
 struct PathState {
     Ray ray;
     V3 beta;      // product of the factors the recursion multiplies on the way back up
@@ -904,6 +1032,13 @@ struct PathState {
 // One call of ray_color (one segment).  Returns false when the path ended.
 //   recursion:  L = emitted + f * L_next      iteration:  radiance += beta*emitted ; beta *= f
 RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags);
+
+// The path ends with nothing emitted: the recursion returns f * 0 / pdf all the way up, which is
+// 0 - or NaN when some factor on the way was not finite (0/0 or x/0 at main.rs:97,104; §Q10).
+RT_DEV bool path_end_black(PathState &ps) {
+    ps.radiance = ps.beta * 0.0;
+    return false;
+}
 
 // MEDIA: the scene has ConstantMedium objects (a compile-time property of the kernel variant, so
 // that scenes without volumes do not carry the boundary-query loop).
@@ -933,6 +1068,7 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
     if (mkind == RT_MAT_DIFFUSE_LIGHT) {
         // DiffuseLight never scatters (mat.rs:391-393 / default scatter_mc_method): return emitted
         if (rec.front_face) ps.radiance = ps.radiance + ps.beta * texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+        else return path_end_black(ps);
         return false;
     }
     V3 new_dir = mk(0.0, 0.0, 0.0);
@@ -942,7 +1078,7 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
         // random_in_unit_sphere is drawn even for fuzz == 0 (§Q12); with slot addressing the
         // draw can be skipped when its product with fuzz is exactly zero.
         new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * random_in_unit_sphere(ps.rng) : reflected;
-        if (!(dot(new_dir, rec.normal) > 0.0)) return false;  // None -> emitted (black)
+        if (!(dot(new_dir, rec.normal) > 0.0)) return path_end_black(ps);  // None -> emitted (black)
         factor = ld3(m.albedo);
     } else if (feat(F_DIELECTRIC) && mkind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
         new_dir = dielectric_direction(m, ps.ray.d, rec, ps.rng);
@@ -951,12 +1087,27 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
         if (mkind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
             new_dir = rec.normal + normalized(random_in_unit_sphere(ps.rng));
             if (near_zero(new_dir)) new_dir = rec.normal;
-        } else {  // Isotropic, mat.rs:418-421
+        } else if (mkind == RT_MAT_ISOTROPIC) {  // mat.rs:418-421
             new_dir = random_in_unit_sphere(ps.rng);
+        } else {
+            return path_end_black(ps);  // PBR has no legacy scatter (trait default None, mat.rs:56-58)
         }
         factor = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+    } else if (feat(F_HEAD) && feat(F_PBR) && mkind == RT_MAT_PBR) {  // main.rs:99-105 with mat.rs:118-131
+        ONB uvw = onb_from_w(rec.normal);  // PDF::brdf_pdf (pdf.rs:70-79)
+        Draw d = draw(ps.rng, SLOT_SCATTER, 0);
+        if (d.bits_a & 1u) {  // pdf.rs:169
+            new_dir = lights_random(sc, rec.p, d);
+        } else {  // pdf.rs:151-160: the lobe by gen_range(0.0..1.0), then the lobe's own (r1, r2)
+            double lobe = draw(ps.rng, SLOT_SCATTER, 1).a;
+            V3 local = lobe < 0.333 ? random_cosine_direction(d.a, d.b) : brdf_lobe_direction(&m, !(lobe < 0.666), ps.ray.d, d.a, d.b);
+            new_dir = onb_local(uvw, local);
+        }
+        double pdf_value = 0.5 * lights_pdf_value(sc, rec.p, new_dir) + 0.5 * brdf_pdf_value(&m, uvw.u, uvw.v, uvw.w, ps.ray.d, new_dir);
+        V3 f = pbr_brdf(&m, texture_value(sc, m.texture, rec.u, rec.v, rec.p), ps.ray.d, new_dir, rec.normal);
+        factor = f / pdf_value;  // main.rs:104
     } else if (feat(F_HEAD)) {
-        if (mkind != RT_MAT_LAMBERTIAN) return false;  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
+        if (mkind != RT_MAT_LAMBERTIAN) return path_end_black(ps);  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
         // main.rs:92-98
         V3 attenuation = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
         ONB uvw = onb_from_w(rec.normal);  // PDF::cosine_pdf (pdf.rs:83-87)
@@ -980,7 +1131,8 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
     ps.rng.bounce += 1;
     if (!(flags & RT_FLAG_TRACE_ZERO_THROUGHPUT) && ps.beta.x == 0.0 && ps.beta.y == 0.0 && ps.beta.z == 0.0)
         return false;  // §Q11: the reference keeps tracing; the contribution is zero either way
-    return ps.depth_left != 0;
+    if (ps.depth_left == 0) return path_end_black(ps);  // the next call is ray_color(depth = 0): black (main.rs:42-45)
+    return true;
 }
 
 // The sample closure of main.rs:811-829: pixel jitter + Camera::get_ray (camera.rs:51-59)

@@ -14,7 +14,7 @@ namespace rtb200dev {
 #define RT_MASK_vflat (F_RECT | F_BOX | F_METAL | F_HEAD)                                        /* Cornell box, Cornell smoke */
 #define RT_MASK_vmesh (F_RECT | F_TRI | F_BVH | F_METAL | F_DIELECTRIC | F_HEAD)                  /* triangle-mesh scenes        */
 #define RT_MASK_vspheres (F_SPHERE | F_MSPHERE | F_BVH | F_TEX | F_METAL | F_DIELECTRIC | F_LEGACY) /* RTiOW random spheres       */
-#define RT_MASK_vnextweek (F_ALL & ~(F_TRI | F_LEGACY | F_SPHERE_LIGHT))                          /* Next Week final scene       */
+#define RT_MASK_vnextweek (F_ALL & ~(F_TRI | F_LEGACY | F_SPHERE_LIGHT | F_PBR))                          /* Next Week final scene       */
 #define RT_MASK_vall F_ALL
 #define RT_VARIANT_LIST(X) X(vflat) X(vmesh) X(vspheres) X(vnextweek) X(vall)
 

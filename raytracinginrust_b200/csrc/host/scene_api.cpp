@@ -156,6 +156,13 @@ uint32_t Metal::flatten(SceneBuilder &b) const {
 uint32_t Dielectric::flatten(SceneBuilder &b) const {
     return memoised(b, this, [&] { return push_material(b, RT_MAT_DIELECTRIC, RT_NONE, Color(), 0, ir); });
 }
+uint32_t PBR::flatten(SceneBuilder &b) const {
+    return memoised(b, this, [&] {
+        uint32_t k = push_material(b, RT_MAT_PBR, base_color->flatten(b), Color(), 0, 0);
+        for (int i = 0; i < 10; ++i) b.materials[k].pbr[i] = p[i];
+        return k;
+    });
+}
 uint32_t DiffuseLight::flatten(SceneBuilder &b) const {
     return memoised(b, this, [&] { return push_material(b, RT_MAT_DIFFUSE_LIGHT, emit->flatten(b), Color(), 0, 0); });
 }

@@ -167,6 +167,20 @@ struct DiffuseLight : Material {  // mat.rs:377-402
     static MaterialPtr make(TexturePtr e) { return std::make_shared<DiffuseLight>(e); }
     uint32_t flatten(SceneBuilder &b) const override;
 };
+struct PBR : Material {  // mat.rs:86-197 (PBR::new, :101-115)
+    TexturePtr base_color;
+    double p[10];  // metallic, subsurface, specular, roughness, specular_tint, anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss
+    PBR(TexturePtr c, double metallic, double subsurface, double specular, double roughness, double specular_tint,
+        double anisotropic, double sheen, double sheen_tint, double clearcoat, double clearcoat_gloss)
+        : base_color(c), p{metallic, subsurface, specular, roughness, specular_tint, anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss} {}
+    static MaterialPtr make(TexturePtr c, double metallic, double subsurface, double specular, double roughness,
+                            double specular_tint, double anisotropic, double sheen, double sheen_tint, double clearcoat,
+                            double clearcoat_gloss) {
+        return std::make_shared<PBR>(c, metallic, subsurface, specular, roughness, specular_tint, anisotropic, sheen, sheen_tint,
+                                     clearcoat, clearcoat_gloss);
+    }
+    uint32_t flatten(SceneBuilder &b) const override;
+};
 struct Isotropic : Material {  // mat.rs:404-422
     TexturePtr albedo;
     explicit Isotropic(TexturePtr a) : albedo(a) {}

@@ -285,6 +285,77 @@ static SceneSpec two_spheres() {
     return SceneSpec{world, lights, Color(0.7, 0.8, 1.0), cam, RT_INTEGRATOR_LEGACY, 500, 500, 800, 100};
 }
 
+// two_perlin_sphere (main.rs:229-244) + camera main.rs:652-663.  Empty light list: HEAD's integrator
+// panics at the first Lambertian hit (§Q7), so the scene renders with the legacy integrator.
+static SceneSpec two_perlin_spheres(uint32_t seed) {
+    SceneRng rng(seed, 7);
+    auto world = std::make_shared<HittableList>();
+    auto lights = std::make_shared<HittableList>();
+    auto top_mat = Lambertian::make(NoiseTexture::make(2.0, rng));
+    auto bottom_mat = Lambertian::make(NoiseTexture::make(2.0, rng));
+    // "hash goes wrong in negative field, move object to First Quadrant for now" (main.rs:235, §Q15)
+    world->push(Sphere::make(Point3(1000.0, 2.0, 1000.0), 2.0, top_mat));
+    world->push(Sphere::make(Point3(1000.0, -1000.0, 1000.0), 1000.0, bottom_mat));
+    Camera cam(Point3(1013.0, 2.0, 1003.0), Point3(1000.0, 0.0, 1000.0), Vec3(0.0, 1.0, 0.0), 20.0, 1.0, 0.0, 10.0, 0.0, 1.0);
+    return SceneSpec{world, lights, Color(0.7, 0.8, 1.0), cam, RT_INTEGRATOR_LEGACY, 500, 500, 800, 100};
+}
+// earth (main.rs:246-254) + camera main.rs:665-676; the world is the sphere itself, no list
+static SceneSpec earth(const std::string &assets_dir) {
+    auto world = std::make_shared<HittableList>();
+    auto lights = std::make_shared<HittableList>();
+    world->push(Sphere::make(Point3(0.0, 0.0, 0.0), 2.0, Lambertian::make(earth_texture(assets_dir))));
+    Camera cam(Point3(13.0, 2.0, 3.0), Point3(0.0, 0.0, 0.0), Vec3(0.0, 1.0, 0.0), 20.0, 1.0, 0.1, 10.0, 0.0, 1.0);
+    return SceneSpec{world, lights, Color(0.7, 0.8, 1.0), cam, RT_INTEGRATOR_LEGACY, 500, 500, 800, 100};
+}
+// progress_showcase (main.rs:515-562) + camera main.rs:752-763.  At HEAD the whole body is commented
+// out (an empty world: every ray returns the black background); this is that body, restored: checker
+// ground, diffuse / metal / glossy spheres, a hollow glass sphere (negative radius), a rotated and
+// translated rect, one triangle, and a SPHERE light (Sphere::pdf_value / random, sphere.rs:104-119).
+static SceneSpec progress_showcase() {
+    auto world = std::make_shared<HittableList>();
+    auto lights = std::make_shared<HittableList>();
+    auto ground_mat = Lambertian::make(CheckTexture::make(solid(1.0, 1.0, 1.0), solid(0.04, 0.01, 0.02)));
+    auto green = Lambertian::make(solid(0.12, 0.45, 0.15));
+    auto tomato = Lambertian::make(solid(1.0, 0.39, 0.28));
+    auto violet = Lambertian::make(solid(0.93, 0.51, 0.93));
+    auto red = Lambertian::make(solid(0.65, 0.05, 0.05));
+    auto dielectric = Dielectric::make(1.5);
+    auto metal = Metal::make(Color(0.8, 0.85, 0.88), 0.0);
+    auto glossy = Metal::make(Color(1.0, 0.4, 0.0), 0.3);
+    auto light = DiffuseLight::make(ConstantTexture::make(Color(1.0, 1.0, 0.88) * 25.0));
+    auto sphere_5 = Sphere::make(Point3(-3.3, 2.4, -2.9), 0.3, light);
+    world->push(Sphere::make(Point3(0.0, 1.0, 0.0), 1.0, green));
+    world->push(Sphere::make(Point3(-1.7, 1.0, 1.7), 1.0, metal));
+    world->push(Sphere::make(Point3(1.7, 1.0, -1.7), 1.0, violet));
+    world->push(Sphere::make(Point3(0.0, -1000.0, 0.0), 1000.0, ground_mat));
+    world->push(Translate::make(Rotate::make(Axis::Y, AARect::make(Plane::YZ, 0.0, 0.7, 0.1, 0.3, 0.0, tomato), 104.0), Vec3(0.5, 1.9, 1.7)));
+    world->push(Triangle::make(Point3(-2.4, 3.3, 4.6), Point3(-3.2, 1.3, 2.1), Point3(-0.8, 1.5, 3.4), red));
+    world->push(Sphere::make(Point3(3.7, 0.0, 5.4), 3.4, dielectric));
+    world->push(Sphere::make(Point3(3.7, 0.0, 5.4), -3.3, dielectric));
+    world->push(sphere_5);
+    world->push(Sphere::make(Point3(-1.2, 0.4, -1.8), 0.5, glossy));
+    lights->push(sphere_5);
+    Camera cam(Point3(-3.3, 6.8, -9.8), Point3(0.0, 1.0, 0.0), Vec3(0.0, 1.0, 0.0), 40.0, 1.0, 0.2, 12.0, 0.0, 1.0);
+    return SceneSpec{world, lights, Color(0.0, 0.0, 0.0), cam, RT_INTEGRATOR_HEAD, 500, 500, 800, 100};
+}
+// Not a reference scene: the Cornell box with the reference's PBR material (mat.rs:86-197) on its
+// objects, so that the one material no reference scene attaches to anything is exercised.  The
+// short box carries the parameters of the only PBR::new call in the reference (main.rs:398-408).
+static SceneSpec cornell_pbr() {
+    auto world = std::make_shared<HittableList>();
+    auto lights = std::make_shared<HittableList>();
+    cornell_shell(*world, *lights);
+    auto pbr_ref = PBR::make(solid(1.0, 1.0, 1.0), 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+    auto pbr_coat = PBR::make(solid(0.8, 0.25, 0.1), 0.1, 0.3, 0.5, 0.4, 0.5, 0.6, 0.4, 0.5, 1.0, 0.8);
+    auto pbr_gold = PBR::make(solid(1.0, 0.78, 0.34), 0.9, 0.0, 0.5, 0.25, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0);
+    world->push(Translate::make(Rotate::make(Axis::Y, Cube::make(Point3(0.0, 0.0, 0.0), Point3(165.0, 165.0, 165.0), pbr_ref), -18.0),
+                                Vec3(130.0, 0.0, 65.0)));
+    world->push(Translate::make(Rotate::make(Axis::Y, Cube::make(Point3(0.0, 0.0, 0.0), Point3(165.0, 330.0, 165.0), pbr_coat), 15.0),
+                                Vec3(265.0, 0.0, 295.0)));
+    world->push(Sphere::make(Point3(190.0, 225.0, 145.0), 60.0, pbr_gold));
+    return SceneSpec{world, lights, Color(0.0, 0.0, 0.0), cornell_camera(), RT_INTEGRATOR_HEAD, 600, 600, 1000, 100};
+}
+
 SceneSpec make_scene(const std::string &name, uint32_t construction_seed, const std::string &assets_dir, uint32_t mesh_detail) {
     if (name == "random") return random_scene(construction_seed);
     if (name == "cornell") return cornell_box();
@@ -293,6 +364,10 @@ SceneSpec make_scene(const std::string &name, uint32_t construction_seed, const 
     if (name == "mesh") return mesh_scene(assets_dir, mesh_detail);
     if (name == "light_room") return light_room();
     if (name == "two_spheres") return two_spheres();
+    if (name == "two_perlin_spheres") return two_perlin_spheres(construction_seed);
+    if (name == "earth") return earth(assets_dir);
+    if (name == "progress_showcase") return progress_showcase();
+    if (name == "cornell_pbr") return cornell_pbr();
     throw std::runtime_error("unknown scene: " + name);
 }
 

@@ -27,7 +27,7 @@ def test_header_functions_are_exported(rt):
 def test_struct_sizes_match_header(rt):
     """Compile-free layout check: sizes implied by the header's field lists."""
     A = rt._abi
-    assert C.sizeof(A.RtNode) == 24 + 80 and C.sizeof(A.RtMaterial) == 8 + 40 and C.sizeof(A.RtTexture) == 16 + 32
+    assert C.sizeof(A.RtNode) == 24 + 80 and C.sizeof(A.RtMaterial) == 8 + 40 + 80 and C.sizeof(A.RtTexture) == 16 + 32
     assert C.sizeof(A.RtPerlin) == 768 * 8 + 3 * 1024 and C.sizeof(A.RtImage) == 16
     assert C.sizeof(A.RtCamera) == 21 * 8 and C.sizeof(A.RtRenderOpts) == 24 and C.sizeof(A.RtStats) == 64
     assert C.sizeof(A.RtRay) == 56 and C.sizeof(A.RtHit) == 16 + 9 * 8

@@ -252,3 +252,42 @@ def test_feature_variants_identical(rt, orc, name, monkeypatch):
         monkeypatch.delenv("RTB200_VARIANT", raising=False)
         assert np.array_equal(a, b, equal_nan=True)
         assert sa.rays == sb.rays
+
+
+EXTRA_SCENES = ["light_room", "two_spheres", "two_perlin_spheres", "earth", "progress_showcase", "cornell_pbr"]
+
+
+@pytest.mark.parametrize("name", EXTRA_SCENES)
+def test_extra_scenes_match_oracle(rt, orc, name):
+    """the reference's remaining scene constructors (main.rs:212-276, :515-562; sphere
+    lights, Perlin and image textures outside the final scene) and the PBR material + PDF::BRDF
+    (mat.rs:86-197, pdf.rs:20-60,97-130,151-160) - the same three checks as the five configs."""
+    hs, dev, osc = scenes(rt, orc, name)
+    W, H, depth = 96, 96, 100
+    opts = rt.render_opts(seed=4, integrator=hs.integrator)
+    # 1. first hits
+    px, py, s = random_path_ids(40000, W, H, 64, seed=12)
+    rays = orc.camera_rays(hs.camera, W, H, opts, px, py, s)
+    r = compare_hits(dev.trace_first_hit(rays), osc.trace_first_hit(rays))
+    assert r["id_mismatch"] == 0 and r["t_max_rel"] <= 1e-5 and r["normal_max_abs"] <= 1e-5 and r["uv_max_abs"] <= 1e-5
+    # 2. per-path radiance (a path the reference turns into NaN must be NaN here too, §Q10)
+    px, py, s = random_path_ids(20000, W, H, 256, seed=13)
+    rd, sd = dev.path_radiance(hs.camera, W, H, depth, opts, px, py, s)
+    ro, so = osc.path_radiance(hs.camera, W, H, depth, opts, px, py, s)
+    nan_d, nan_o = np.isnan(rd).any(axis=1), np.isnan(ro).any(axis=1)
+    err = rel_err(np.nan_to_num(rd), np.nan_to_num(ro), floor=1e-9).max(axis=1)
+    ok = ((err <= 1e-4) & ~nan_d & ~nan_o) | (nan_d & nan_o)
+    print(name, "paths ok %.6f  nan gpu %.4f oracle %.4f  median err %.2e" % (ok.mean(), nan_d.mean(), nan_o.mean(), np.median(err)))
+    assert ok.mean() >= 0.999
+    # 3. the image, both pipelines
+    for flag in (rt._abi.FLAG_MEGAKERNEL, rt._abi.FLAG_WAVEFRONT):
+        o = rt.render_opts(seed=4, integrator=hs.integrator, flags=flag)
+        img, stats = dev.render(hs.camera, 48, 48, 16, depth, o)
+        ref, _ = osc.render(hs.camera, 48, 48, 16, depth, o)
+        nd, no = np.isnan(img).any(axis=2), np.isnan(ref).any(axis=2)
+        e = rel_err(np.nan_to_num(img), np.nan_to_num(ref), floor=1e-6).max(axis=2)
+        good = ((e <= 1e-4) & ~nd & ~no) | (nd & no)
+        assert good.mean() >= 0.99, (name, flag, good.mean())
+        a = rt.format_image(img, 16).astype(np.float64)
+        b = orc.format_image(ref, 16).astype(np.float64)
+        assert float(np.sqrt(np.mean((a - b) ** 2)) / 255.0) <= 0.01

@@ -366,3 +366,65 @@ def test_oracle_render_is_sum_of_paths(rt, orc):
     half = osc.render(hs.camera, W, H, spp, 20, rt.render_opts(seed=2, sample_begin=0, sample_count=3))[0] + \
         osc.render(hs.camera, W, H, spp, 20, rt.render_opts(seed=2, sample_begin=3, sample_count=3))[0]
     assert np.allclose(img, half, rtol=1e-13)
+
+
+# ---- the PBR material's scalar helpers (mat.rs:10-44) -------------------------------------------
+def test_pbr_schlick_and_smith(orc):
+    assert orc.pbr_scalar(0, 0.0) == 1.0 and orc.pbr_scalar(0, 1.0) == 0.0
+    assert orc.pbr_scalar(0, 0.5) == pytest.approx(1.0 / 32.0, rel=1e-15)
+    assert orc.pbr_scalar(0, -3.0) == 1.0 and orc.pbr_scalar(0, 7.0) == 0.0  # clamp(0, 1), mat.rs:11
+    # smithG_GGX(1, a) = 1 / (1 + sqrt(a^2 + 1 - a^2)) = 1/2 for every a (mat.rs:36-40)
+    for a in (0.0, 0.25, 0.9):
+        assert orc.pbr_scalar(3, 1.0, a) == pytest.approx(0.5, rel=1e-15)
+    # the anisotropic form with ax = ay = a, v in the x-z plane, equals 1 / (n.v + sqrt(sin^2 a^2 + cos^2))
+    c, sn, a = 0.6, 0.8, 0.3
+    assert orc.pbr_scalar(4, c, sn, 0.0, a, a) == pytest.approx(1.0 / (c + np.sqrt((sn * a) ** 2 + c * c)), rel=1e-15)
+
+
+def _hemisphere_integral(fn, n_theta=2000, n_phi=720):
+    """Integral over the hemisphere of fn * cos(theta) d_omega (midpoint rule).  fn(cos_theta) for a
+    lobe that does not depend on phi, else fn(cos_theta, hx, hy)."""
+    th = (np.arange(n_theta) + 0.5) * (np.pi / 2) / n_theta
+    ph = (np.arange(n_phi) + 0.5) * (2 * np.pi) / n_phi
+    d_theta = (np.pi / 2) / n_theta
+    tot = 0.0
+    for t in th:
+        ct, st = np.cos(t), np.sin(t)
+        if fn.__code__.co_argcount == 1:
+            ring = fn(ct) * 2 * np.pi
+        else:
+            ring = sum(fn(ct, st * np.cos(p), st * np.sin(p)) for p in ph) * (2 * np.pi) / n_phi
+        tot += ring * ct * st * d_theta
+    return tot
+
+
+def test_pbr_gtr2_aniso_is_a_normalised_distribution(orc):
+    """GTR_2_aniso (mat.rs:32-34) integrates to 1 against cos(theta) over the hemisphere."""
+    iso = _hemisphere_integral(lambda ct, hx, hy: orc.pbr_scalar(2, ct, hx, hy, 0.3, 0.3), n_theta=1500, n_phi=8)
+    assert iso == pytest.approx(1.0, abs=2e-3)
+    aniso = _hemisphere_integral(lambda ct, hx, hy: orc.pbr_scalar(2, ct, hx, hy, 0.25, 0.6), n_theta=600, n_phi=240)
+    assert aniso == pytest.approx(1.0, abs=5e-3)
+
+
+def test_pbr_gtr1_keeps_the_reference_log2(orc):
+    """GTR_1 divides by log2(a^2) where Burley's normalisation has ln(a^2) (mat.rs:22): the
+    reference's lobe therefore integrates to ln 2, not 1.  a >= 1 is the uniform 1/pi."""
+    a = 0.1
+    got = _hemisphere_integral(lambda ct: orc.pbr_scalar(1, ct, a), n_theta=20000)
+    assert got == pytest.approx(np.log(2.0), rel=2e-3)
+    assert orc.pbr_scalar(1, 0.3, 1.0) == pytest.approx(1.0 / np.pi, rel=1e-15)
+    assert orc.pbr_scalar(1, 0.3, 2.5) == pytest.approx(1.0 / np.pi, rel=1e-15)
+
+
+def test_pbr_paths_reproduce_the_reference_nan(rt, orc):
+    """PDF::BRDF reflects the WORLD-space incoming direction about a TANGENT-space half vector
+    (pdf.rs:35,59), so many sampled directions leave below the surface: brdf = 0 and pdf = 0, and
+    main.rs:104 divides 0 by 0.  The restatement keeps that (no NaN guard, §Q10)."""
+    hs = rt.HostScene("cornell_pbr")
+    osc = orc.OracleScene(hs.scene_desc)
+    rng = np.random.default_rng(3)
+    px, py, s = (rng.integers(0, 64, 4000, dtype=np.uint32) for _ in range(3))
+    rgb, seg = osc.path_radiance(hs.camera, 64, 64, 100, rt.render_opts(seed=2), px, py, s)
+    nan = np.isnan(rgb).any(axis=1)
+    assert 0.02 < nan.mean() < 0.5
+    assert np.isfinite(rgb[~nan]).all() and (rgb[~nan] >= 0.0).all()
