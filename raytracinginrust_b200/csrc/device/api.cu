@@ -245,7 +245,7 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
         RtStatus a__ = wf_alloc(s, w.field, (count)); \
         if (a__ != RT_OK) return a__;                 \
     } while (0)
-        WA(slots, cap); WA(sum, cap); WA(ctl, 1);
+        WA(slots, cap); WA(sum, cap); WA(state, cap); WA(ctl, 1);
 #undef WA
         w.capacity = cap;
         s.wf = w;

@@ -38,7 +38,7 @@ struct alignas(128) WfSlot {
     double oz, dx;        // u1  ray direction (never normalised, ray.rs)
     double dy, dz;        // u2
     double time;          // u3  ray time
-    uint32_t state;       //     WfState
+    uint32_t state_unused;  //   (the state lives in WfPool::state)
     uint32_t depth_left;  //     bounce = max_depth - depth_left
     double bx, by;        // u4  throughput (beta)
     double bz;            // u5
@@ -57,6 +57,7 @@ static_assert(sizeof(WfSlot) == 128, "one slot per 128-byte line");
 struct WfPool {
     WfSlot *slots;
     double4 *sum;       // per slot: the item's radiance sum (x,y,z), samples added in sample order
+    uint32_t *state;    // per slot: WfState, apart from the record so that sparse rounds stay cheap
     WfCtl *ctl;
     uint32_t capacity;  // slots allocated
     uint32_t n_slots;   // slots used by the current render (<= capacity)

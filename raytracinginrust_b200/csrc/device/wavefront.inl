@@ -76,6 +76,7 @@ __global__ void wf_init_kernel(const __grid_constant__ WfPool pool) {
     for (; k < pool.n_slots; k += stride) {
         double2 *u = slot_d2w(pool, k);
         st_u4(u + 3, pack_time_state(0.0, WF_REGEN, 0u));
+        pool.state[k] = WF_REGEN;
         st_u4(u + 5, pack_bz_keys(0.0, 0u, 0u));
         st_u4(u + 7, make_uint4(0u, 0u, kWfNoItem, 0u));  // no item: sample + 1 >= s_end
         pool.sum[k] = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -94,9 +95,11 @@ wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Rende
     const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
     bool alive = false, bad = false;
     if (slot < pool.n_slots) {
-        const double2 *u = slot_d2(pool, slot);
-        const uint4 u3 = ld_u4(u + 3);
-        if (u3.z == WF_LIVE) {
+        // the state array is read first: 4 bytes per slot, so a round over a pool that is nearly
+        // empty (the tail of a render) moves 16 MB, not the 512 MB of the slot records
+        if (pool.state[slot] == WF_LIVE) {
+            const double2 *u = slot_d2(pool, slot);
+            const uint4 u3 = ld_u4(u + 3);
             const double2 u0 = u[0], u1 = u[1], u2 = u[2], u4 = u[4];
             const uint4 u5 = ld_u4(u + 5), u6 = ld_u4(u + 6);
             PathState ps;
@@ -127,7 +130,7 @@ wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Rende
                 w[4] = make_double2(ps.beta.x, ps.beta.y);
                 st_u4(w + 5, pack_bz_keys(ps.beta.z, u5.z, u5.w));
             } else {
-                st_u4(w + 3, make_uint4(u3.x, u3.y, WF_REGEN, 0u));
+                pool.state[slot] = WF_REGEN;
                 // vec.rs:253-260 Sum, in sample order (the slot runs its samples one after the other)
                 const V3 L = ps.radiance;
                 bad = !(isfinite(L.x) && isfinite(L.y) && isfinite(L.z));  // §Q10: counted, not guarded
@@ -165,10 +168,9 @@ wf_generate_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__
     bool regen = false, have = false, need_item = false;
     if (threadIdx.x == 0) s_need = 0u;
     if (slot < pool.n_slots) {
-        const double2 *u = slot_d2(pool, slot);
-        const uint4 u3 = ld_u4(u + 3);
-        regen = u3.z == WF_REGEN;
+        regen = pool.state[slot] == WF_REGEN;
         if (regen) {
+            const double2 *u = slot_d2(pool, slot);
             const uint4 u5 = ld_u4(u + 5), u7 = ld_u4(u + 7);
             rng_pixel = u5.z;
             sample = u5.w + 1u;
@@ -242,11 +244,12 @@ wf_generate_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__
             w[1] = make_double2(r.o.z, r.d.x);
             w[2] = make_double2(r.d.y, r.d.z);
             st_u4(w + 3, pack_time_state(r.time, WF_LIVE, P.max_depth));
+            pool.state[slot] = WF_LIVE;
             w[4] = make_double2(1.0, 1.0);
             st_u4(w + 5, pack_bz_keys(1.0, rng_pixel, sample));
             st_u4(w + 7, make_uint4(out_pixel, s_end, chunk, 0u));
         } else {
-            st_u4(w + 3, pack_time_state(0.0, WF_EMPTY, 0u));
+            pool.state[slot] = WF_EMPTY;
             st_u4(w + 7, make_uint4(0u, 0u, kWfNoItem, 0u));
         }
     }
@@ -317,10 +320,10 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
             const unsigned rank = __popc(want & lt);
             if (!has_ray && rank < avail) {
                 const uint32_t cand = wbase + rank;
-                const double2 *u = slot_d2(pool, cand);
-                const uint4 u3 = ld_u4(u + 3);
-                if (u3.z == WF_LIVE) {  // not LIVE only in the tail of a render, when items have run out
+                if (pool.state[cand] == WF_LIVE) {  // not LIVE only in the tail of a render, when items have run out
                     slot = cand;
+                    const double2 *u = slot_d2(pool, cand);
+                    const uint4 u3 = ld_u4(u + 3);
                     const double2 r0 = u[0], r1 = u[1], r2 = u[2];
                     ray.o = mk(r0.x, r0.y, r1.x);
                     ray.d = mk(r1.y, r2.x, r2.y);
