@@ -245,7 +245,7 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
         RtStatus a__ = wf_alloc(s, w.field, (count)); \
         if (a__ != RT_OK) return a__;                 \
     } while (0)
-        WA(slots, cap); WA(sum, cap); WA(state, cap); WA(ctl, 1);
+        WA(slots, cap); WA(sum, cap); WA(state, cap); WA(defer_q, cap); WA(ctl, 1);
 #undef WA
         w.capacity = cap;
         s.wf = w;
@@ -266,7 +266,7 @@ RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &ca
     s.pending_launches += 1;
     for (;;) {
         for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, st));
-        s.pending_launches += (uint64_t)kRoundsPerCheck * kWfLaunchesPerRound;
+        s.pending_launches += (uint64_t)kRoundsPerCheck * (kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0));
         CU(cudaMemcpyAsync(s.wf_status_host, &s.wf.ctl->status_live, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*s.wf_status_host == 0u) break;

@@ -737,6 +737,13 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
     return true;
 }
 
+bool texture_is_costly(const RtSceneDesc &d, uint32_t id, int depth) {
+    if (id >= d.n_textures || depth > 16) return false;
+    const RtTexture &t = d.textures[id];
+    if (t.kind == RT_TEX_NOISE || t.kind == RT_TEX_IMAGE) return true;
+    if (t.kind == RT_TEX_CHECKER) return texture_is_costly(d, t.a, depth + 1) || texture_is_costly(d, t.b, depth + 1);
+    return false;
+}
 bool texture_needs_uv(const RtSceneDesc &d, uint32_t id, int depth) {
     if (id >= d.n_textures || depth > 16) return false;
     const RtTexture &t = d.textures[id];
@@ -837,6 +844,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
             return RT_ERR_BAD_ARGUMENT;
         }
         dm.needs_uv = textured && texture_needs_uv(d, m.texture, 0) ? 1u : 0u;
+        dm.costly = textured && texture_is_costly(d, m.texture, 0) ? 1u : 0u;
         out.materials.push_back(dm);
     }
     for (int a = 0; a < 3; ++a) out.background[a] = d.background[a];

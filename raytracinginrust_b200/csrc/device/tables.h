@@ -99,7 +99,7 @@ struct alignas(16) DMaterial {
     uint32_t kind;     // RtMaterialKind
     uint32_t texture;
     uint32_t needs_uv;  // the texture tree reads (u,v): only image textures do
-    uint32_t pad;
+    uint32_t costly;    // the texture tree has Perlin noise or an image: shaded in the compacted second pass (wavefront)
     double albedo[3];
     double fuzz, ir;
     double pad2;

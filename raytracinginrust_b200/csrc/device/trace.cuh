@@ -36,7 +36,7 @@ namespace rtb200dev {
 inline namespace RT_VARIANT_NS {
 
 #define RT_DEV __device__ __forceinline__
-__device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
+__host__ __device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
 #define RT_DEV_COLD static __device__ __noinline__
 
 constexpr double kPi = 3.14159265358979323846264338327950288;

@@ -23,7 +23,8 @@ struct WfCtl {
     unsigned ext_cursor;   // dynamic-fetch cursor of the extend stage (slots handed out so far)
     unsigned status_live;  // live count of the last finished round (the host loop reads it back)
     unsigned rounds_done;
-    unsigned pad0, pad1;
+    unsigned defer_n;      // entries of the deferred-shade queue of this round
+    unsigned pad1;
 };
 
 // One 128-byte record per slot = one L2 line, eight 128-bit units; a lane moves a unit with one
@@ -58,12 +59,13 @@ struct WfPool {
     WfSlot *slots;
     double4 *sum;       // per slot: the item's radiance sum (x,y,z), samples added in sample order
     uint32_t *state;    // per slot: WfState, apart from the record so that sparse rounds stay cheap
+    uint32_t *defer_q;  // shade pass 2: slots whose hit material is costly (Perlin noise, image textures)
     WfCtl *ctl;
     uint32_t capacity;  // slots allocated
     uint32_t n_slots;   // slots used by the current render (<= capacity)
 };
 
 // (launchers: per pipeline variant, see variants.h)
-constexpr int kWfLaunchesPerRound = 4;
+constexpr int kWfLaunchesPerRound = 4;  // + 1 (shade pass 2) in the variants with textures
 
 }  // namespace rtb200dev

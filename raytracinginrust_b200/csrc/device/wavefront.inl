@@ -88,67 +88,118 @@ __global__ void wf_init_kernel(const __grid_constant__ WfPool pool) {
 // ---------------------------------------------------------------------------
 // One slot per thread: the stage's cost is the latency of the slot record, which only
 // parallelism hides.
-__global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
-wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams P,
-                const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
-    const unsigned cur = pool.ctl->round & 1u;
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    bool alive = false, bad = false;
-    if (slot < pool.n_slots) {
-        // the state array is read first: 4 bytes per slot, so a round over a pool that is nearly
-        // empty (the tail of a render) moves 16 MB, not the 512 MB of the slot records
-        if (pool.state[slot] == WF_LIVE) {
-            const double2 *u = slot_d2(pool, slot);
-            const uint4 u3 = ld_u4(u + 3);
-            const double2 u0 = u[0], u1 = u[1], u2 = u[2], u4 = u[4];
-            const uint4 u5 = ld_u4(u + 5), u6 = ld_u4(u + 6);
-            PathState ps;
-            ps.ray.o = mk(u0.x, u0.y, u1.x);
-            ps.ray.d = mk(u1.y, u2.x, u2.y);
-            ps.ray.time = unpack_lo_double(u3);
-            ps.beta = mk(u4.x, u4.y, unpack_lo_double(u5));
-            ps.radiance = mk(0.0, 0.0, 0.0);  // non-zero only at the segment that ends the path
-            ps.rng = Rng{P.seed, u5.z, u5.w, P.max_depth - u3.w};
-            ps.depth_left = u3.w;
-            ps.segments = 0;
-            const uint32_t prim = u6.x;
-            const double t = __hiloint2double((int)u6.w, (int)u6.z);
-            HitRec rec;
-            const bool hit = prim != kNoPrim;
-            if (hit) {
-                Best win{t, prim, 0u, (int)u6.y};
-                if (prim & kMediumFlag) resolve_medium(sc, ps.ray, win, t, rec);
-                else resolve_hit<false>(sc, ps.ray, win, t, rec);
-            }
-            alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
-            double2 *w = slot_d2w(pool, slot);
-            if (alive) {
-                w[0] = make_double2(ps.ray.o.x, ps.ray.o.y);
-                w[1] = make_double2(ps.ray.o.z, ps.ray.d.x);
-                w[2] = make_double2(ps.ray.d.y, ps.ray.d.z);
-                st_u4(w + 3, make_uint4(u3.x, u3.y, WF_LIVE, ps.depth_left));  // time is inherited (main.rs:95, mat.rs:219,270,368)
-                w[4] = make_double2(ps.beta.x, ps.beta.y);
-                st_u4(w + 5, pack_bz_keys(ps.beta.z, u5.z, u5.w));
-            } else {
-                pool.state[slot] = WF_REGEN;
-                // vec.rs:253-260 Sum, in sample order (the slot runs its samples one after the other)
-                const V3 L = ps.radiance;
-                bad = !(isfinite(L.x) && isfinite(L.y) && isfinite(L.z));  // §Q10: counted, not guarded
-                if (L.x != 0.0 || L.y != 0.0 || L.z != 0.0) {              // x + 0 == x
-                    double4 s = pool.sum[slot];
-                    s.x += L.x;
-                    s.y += L.y;
-                    s.z += L.z;
-                    pool.sum[slot] = s;
-                }
-            }
+//
+// Two passes.  A few materials cost an order of magnitude more than the rest (the marble sphere:
+// 7 octaves of f64 Perlin noise; image textures: atan2 + acos for the uv), and in slot order they
+// sit one or two to a warp, so the other thirty lanes wait for them (measured on the Next Week
+// final scene: 31 % of the stage's instructions at 2.3 active lanes).  Pass 1 shades everything
+// else and COMPACTS the slots that hit such a material into a queue (__ballot_sync/__popc, one
+// atomic per warp that has any); pass 2 walks that queue, so those paths fill whole warps.
+__device__ __forceinline__ void shade_slot(const DScene &sc, const RenderParams &P, const WfPool &pool, uint32_t slot,
+                                           const uint4 u3, const uint4 u6, bool &alive, bool &bad) {
+    const double2 *u = slot_d2(pool, slot);
+    const double2 u0 = u[0], u1 = u[1], u2 = u[2], u4 = u[4];
+    const uint4 u5 = ld_u4(u + 5);
+    PathState ps;
+    ps.ray.o = mk(u0.x, u0.y, u1.x);
+    ps.ray.d = mk(u1.y, u2.x, u2.y);
+    ps.ray.time = unpack_lo_double(u3);
+    ps.beta = mk(u4.x, u4.y, unpack_lo_double(u5));
+    ps.radiance = mk(0.0, 0.0, 0.0);  // non-zero only at the segment that ends the path
+    ps.rng = Rng{P.seed, u5.z, u5.w, P.max_depth - u3.w};
+    ps.depth_left = u3.w;
+    ps.segments = 0;
+    const uint32_t prim = u6.x;
+    const double t = __hiloint2double((int)u6.w, (int)u6.z);
+    HitRec rec;
+    const bool hit = prim != kNoPrim;
+    if (hit) {
+        Best win{t, prim, 0u, (int)u6.y};
+        if (prim & kMediumFlag) resolve_medium(sc, ps.ray, win, t, rec);
+        else resolve_hit<false>(sc, ps.ray, win, t, rec);
+    }
+    alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
+    double2 *w = slot_d2w(pool, slot);
+    if (alive) {
+        w[0] = make_double2(ps.ray.o.x, ps.ray.o.y);
+        w[1] = make_double2(ps.ray.o.z, ps.ray.d.x);
+        w[2] = make_double2(ps.ray.d.y, ps.ray.d.z);
+        st_u4(w + 3, make_uint4(u3.x, u3.y, WF_LIVE, ps.depth_left));  // time is inherited (main.rs:95, mat.rs:219,270,368)
+        w[4] = make_double2(ps.beta.x, ps.beta.y);
+        st_u4(w + 5, pack_bz_keys(ps.beta.z, u5.z, u5.w));
+    } else {
+        pool.state[slot] = WF_REGEN;
+        // vec.rs:253-260 Sum, in sample order (the slot runs its samples one after the other)
+        const V3 L = ps.radiance;
+        bad = !(isfinite(L.x) && isfinite(L.y) && isfinite(L.z));  // §Q10: counted, not guarded
+        if (L.x != 0.0 || L.y != 0.0 || L.z != 0.0) {              // x + 0 == x
+            double4 s = pool.sum[slot];
+            s.x += L.x;
+            s.y += L.y;
+            s.z += L.z;
+            pool.sum[slot] = s;
         }
     }
+}
+
+__device__ __forceinline__ void shade_epilogue(const WfPool &pool, unsigned cur, bool alive, bool bad,
+                                               unsigned long long *counters) {
     block_count_add(&pool.ctl->live[cur], alive ? 1u : 0u);
     if (__syncthreads_or(bad)) {
         const unsigned nb = __popc(__ballot_sync(kFull, bad));
         if ((threadIdx.x & 31u) == 0u && nb) atomicAdd(&counters[kCounterNonFinite], (unsigned long long)nb);
     }
+}
+
+__global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
+wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams P,
+                const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
+    const unsigned cur = pool.ctl->round & 1u;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool alive = false, bad = false, defer = false;
+    // the state array is read first: 4 bytes per slot, so a round over a pool that is nearly
+    // empty (the tail of a render) moves 16 MB, not the 512 MB of the slot records
+    if (slot < pool.n_slots && pool.state[slot] == WF_LIVE) {
+        const double2 *u = slot_d2(pool, slot);
+        const uint4 u3 = ld_u4(u + 3), u6 = ld_u4(u + 6);
+        if (feat(F_TEX)) {
+            const uint32_t prim = u6.x;
+            defer = prim != kNoPrim && !(prim & kMediumFlag) && sc.materials[sc.prims[prim].material].costly != 0u;
+        }
+        if (!defer) shade_slot(sc, P, pool, slot, u3, u6, alive, bad);
+    }
+    if (feat(F_TEX)) {  // compact the deferred slots
+        const unsigned m = __ballot_sync(kFull, defer);
+        if (m != 0u) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(&pool.ctl->defer_n, (unsigned)__popc(m));
+            base = __shfl_sync(kFull, base, 0);
+            if (defer) pool.defer_q[base + __popc(m & ((1u << lane) - 1u))] = slot;
+        }
+    }
+    shade_epilogue(pool, cur, alive, bad, counters);
+}
+
+// pass 2: the compacted queue of slots that hit a costly material
+__global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
+wf_shade_deferred_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams P,
+                         const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
+    const unsigned cur = pool.ctl->round & 1u;
+    const unsigned n = pool.ctl->defer_n;
+    const unsigned stride = gridDim.x * blockDim.x;
+    bool bad_any = false;
+    unsigned alive_n = 0;
+    for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const uint32_t slot = pool.defer_q[k];
+        const double2 *u = slot_d2(pool, slot);
+        bool alive = false, bad = false;
+        shade_slot(sc, P, pool, slot, ld_u4(u + 3), ld_u4(u + 6), alive, bad);
+        alive_n += alive ? 1u : 0u;
+        bad_any |= bad;
+        if (bad) atomicAdd(&counters[kCounterNonFinite], 1ull);
+    }
+    block_count_add(&pool.ctl->live[cur], alive_n);
 }
 
 // ---------------------------------------------------------------------------
@@ -496,6 +547,7 @@ __global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned 
     c->status_live = live;
     c->live[cur ^ 1u] = 0u;
     c->ext_cursor = 0u;
+    c->defer_n = 0u;
     c->round += 1u;
     c->rounds_done += 1u;
 }
@@ -531,6 +583,10 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
     const unsigned ext_want = (per_reserve + (kWfBlock / 32) - 1) / (kWfBlock / 32);
     if (ext_grid > ext_want) ext_grid = ext_want ? ext_want : 1u;
     wf_shade_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);
+    if (feat(F_TEX)) {  // pass 2 of shade; a grid-stride loop over a queue whose length only the device knows
+        unsigned g = per_slot / 16u;
+        wf_shade_deferred_kernel<<<g ? g : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);
+    }
     wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
     if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
     else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
