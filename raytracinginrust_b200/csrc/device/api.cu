@@ -262,10 +262,18 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
 // rounds (an empty round is four kernels that find nothing to do).
 RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
     const int kRoundsPerCheck = 8;
+    // When a warp of the extend stage goes back for new rays (wavefront.inl, phase C): with long,
+    // uneven traversals (triangle BVHs) as soon as half of its rays wait; otherwise never - every
+    // ray of a media / sphere scene walks the same sequence of queries, and a warp that stays in
+    // lockstep runs those steps with all lanes (measured: profiles/r1_f_pipeline_ab.md).
+    uint32_t leave = (s.features & F_TRI) ? 16u : 1u;
+    if (const char *v = std::getenv("RTB200_WF_LEAVE")) leave = (uint32_t)std::atoi(v);
+    if (leave < 1u) leave = 1u;
+    if (leave > 32u) leave = 32u;
     CU(pv.wf_launch_init(s.wf, st));
     s.pending_launches += 1;
     for (;;) {
-        for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, st));
+        for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, leave, st));
         s.pending_launches += (uint64_t)kRoundsPerCheck * (kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0));
         CU(cudaMemcpyAsync(s.wf_status_host, &s.wf.ctl->status_live, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));

@@ -28,7 +28,8 @@ struct PipelineVariant {
     // wavefront
     cudaError_t (*wf_launch_init)(const WfPool &pool, cudaStream_t stream);
     cudaError_t (*wf_launch_round)(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
-                                   double *planes, unsigned long long *counters, bool media, int sms, cudaStream_t stream);
+                                   double *planes, unsigned long long *counters, bool media, int sms, uint32_t leave_threshold,
+                                   cudaStream_t stream);
 };
 
 #define RT_DECLARE_VARIANT(ns) const PipelineVariant *rtb200_variant_##ns();

@@ -328,7 +328,8 @@ constexpr unsigned kWfReserve = RT_WF_RESERVE;  // slots a warp reserves per glo
 
 template <bool MEDIA>
 __global__ void __launch_bounds__(kWfBlock, RT_WF_EXTEND_MIN_BLOCKS)
-wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth) {
+wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth,
+                 uint32_t leave_threshold) {
     const int kDone = (int)0x80000000;
     const unsigned n = pool.n_slots;
     unsigned *cursor = &pool.ctl->ext_cursor;
@@ -406,8 +407,9 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
             if (exhausted) break;
             continue;
         }
-        // leave the traversal loop once a quarter of the rays in flight wait for a transition
-        const unsigned leave_below = (n_has * (unsigned)RT_WF_REFILL_THRESHOLD) >> 5;
+        // leave the traversal loop once fewer than leave_threshold/32 of the rays in flight still traverse
+        // (a launch parameter: 1 = never, the warp stays in lockstep; see wf_launch_round)
+        const unsigned leave_below = (n_has * leave_threshold) >> 5;
         const unsigned inner_below = (n_has * (unsigned)RT_WF_INNER_THRESHOLD) >> 5;
 
         // ---- B: transition ------------------------------------------------------------------
@@ -564,7 +566,8 @@ static cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
 }
 
 static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
-                            double *planes, unsigned long long *counters, bool media, int sms, cudaStream_t stream) {
+                            double *planes, unsigned long long *counters, bool media, int sms, uint32_t leave_threshold,
+                            cudaStream_t stream) {
     static int ext_per_sm[2] = {0, 0};
     if (ext_per_sm[0] == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_per_sm[0], wf_extend_kernel<false>, kWfBlock, 0);
@@ -588,8 +591,8 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
         wf_shade_deferred_kernel<<<g ? g : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);
     }
     wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
-    if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
-    else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+    if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
+    else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
     wf_control_kernel<<<1, 1, 0, stream>>>(pool, counters);
     return cudaGetLastError();
 }
