@@ -130,7 +130,7 @@ bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_dept
 uint32_t pbr_flags(const RtScene &s) { return (s.features & F_PBR) ? RT_FLAG_TRACE_ZERO_THROUGHPUT : 0u; }
 
 RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-                     const RtRenderOpts *opts, bool wavefront, RenderParams &P) {
+                     const RtRenderOpts *opts, RenderParams &P) {
     if (width < 2 || height < 2) return fail(RT_ERR_BAD_ARGUMENT, "width and height must be at least 2 (main.rs:817-818 divides by W-1, H-1)");
     if ((uint64_t)width * height > (1ull << 31)) return fail(RT_ERR_BAD_ARGUMENT, "image too large");
     RtRenderOpts o{};
@@ -424,7 +424,7 @@ RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t
     CU(cudaSetDevice(s.device));
     RenderParams P;
     const bool wavefront = use_wavefront(s, opts, max_depth);
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, wavefront, P);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
     if (st != RT_OK) return st;
     st = ensure_scratch(s, P, false);
     if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
@@ -453,7 +453,7 @@ RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width,
     CU(cudaSetDevice(s.device));
     RenderParams P;
     const bool wavefront = use_wavefront(s, opts, max_depth);
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, wavefront, P);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
     if (st != RT_OK) return st;
     st = ensure_scratch(s, P, true);
     if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);

@@ -6,6 +6,11 @@
 #include "compile.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include <future>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -163,8 +168,9 @@ struct TNode {
 struct Builder {
     const std::vector<Box> &boxes;
     std::vector<uint32_t> &order;
-    std::vector<TNode> nodes;
-    uint32_t max_depth = 0;
+    std::vector<TNode> nodes;  // pre-sized to 2 * count; ids are handed out by `next`
+    std::atomic<int> next{0};
+    std::atomic<uint32_t> max_depth{0};
     std::vector<double> cx[3];
 
     Builder(const std::vector<Box> &b, std::vector<uint32_t> &o) : boxes(b), order(o) {
@@ -174,9 +180,10 @@ struct Builder {
         }
     }
 
+    // The two halves of a node own disjoint ranges of order[] and disjoint node ids, so large
+    // subtrees are built in parallel (the tree does not depend on the schedule).
     int build(uint32_t first, uint32_t count, uint32_t depth) {
-        int id = (int)nodes.size();
-        nodes.emplace_back();
+        int id = next.fetch_add(1);
         Box box, cbox;
         box.reset();
         cbox.reset();
@@ -186,7 +193,8 @@ struct Builder {
             cbox.grow(c);
         }
         nodes[id].box = box;
-        max_depth = std::max(max_depth, depth);
+        for (uint32_t seen = max_depth.load(); seen < depth && !max_depth.compare_exchange_weak(seen, depth);) {
+        }
         if (count <= LEAF_MAX) {
             nodes[id].first = first;
             nodes[id].count = count;
@@ -259,8 +267,15 @@ struct Builder {
             std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
                              [&](uint32_t a, uint32_t b) { return cx[axis][a] < cx[axis][b]; });
         }
-        int l = build(first, mid - first, depth + 1);
-        int r = build(mid, first + count - mid, depth + 1);
+        int l, r;
+        if (count >= 32768 && depth <= 6) {
+            auto left = std::async(std::launch::async, [&] { return build(first, mid - first, depth + 1); });
+            r = build(mid, first + count - mid, depth + 1);
+            l = left.get();
+        } else {
+            l = build(first, mid - first, depth + 1);
+            r = build(mid, first + count - mid, depth + 1);
+        }
         nodes[id].left = l;
         nodes[id].right = r;
         return id;
@@ -290,9 +305,10 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     std::vector<uint32_t> order(count);
     for (uint32_t i = 0; i < count; ++i) order[i] = i;
     Builder b(boxes, order);
-    b.nodes.reserve(2 * count);
+    b.nodes.resize(2 * (size_t)count);
     int root = b.build(0, count, 1);
-    out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth);
+    b.nodes.resize((size_t)b.next.load());
+    out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth.load());
     // permute the primitives into leaf order
     std::vector<DPrim> tmp(count);
     for (uint32_t i = 0; i < count; ++i) tmp[i] = out.prims[first + order[i]];
@@ -443,7 +459,59 @@ bool ref_bbox(const RtSceneDesc &d, uint32_t id, double t0, double t1, RefBox &o
 }
 
 // Leaf order of BVH::new(hit, t0, t1): left subtree first, then right (bvh.rs:64-70,79-84).
-bool ref_bvh_order(const RtSceneDesc &d, std::vector<uint32_t> hit, double t0, double t1, std::vector<uint32_t> &out,
+// The reference recomputes every bounding box at every level and sorts a fresh Vec per node; the
+// order it arrives at only depends on the boxes, so they are computed once, the recursion sorts
+// index ranges in place, and the two halves of a large node are ordered in parallel.
+struct RefOrder {
+    const std::vector<uint32_t> &hit;
+    const std::vector<RefBox> &boxes;
+    std::vector<uint32_t> idx;   // permutation of [0, n), sorted range by range
+    std::vector<uint32_t> &out;  // out[k] = hit[idx[k]] once the recursion is done
+    std::atomic<int> bad{0};     // 1: NaN extent, 2: NaN centroid
+
+    void rec(size_t first, size_t n, int depth) {
+        if (n <= 1 || bad.load(std::memory_order_relaxed)) return;
+        int axis = 0;
+        double range[3];
+        for (int a = 0; a < 3; ++a) {  // bvh.rs:33-48
+            double bmin = DBL_MAX, bmax = -DBL_MAX;
+            for (size_t i = first; i < first + n; ++i) {
+                bmin = std::fmin(bmin, boxes[idx[i]].lo[a]);
+                bmax = std::fmax(bmax, boxes[idx[i]].hi[a]);
+            }
+            range[a] = bmax - bmin;
+            if (range[a] != range[a]) {  // partial_cmp().unwrap(), bvh.rs:47
+                bad.store(1);
+                return;
+            }
+        }
+        if (range[1] > range[axis]) axis = 1;
+        if (range[2] > range[axis]) axis = 2;
+        for (size_t i = first; i < first + n; ++i) {
+            const RefBox &b = boxes[idx[i]];
+            if (b.lo[axis] + b.hi[axis] != b.lo[axis] + b.hi[axis]) {  // partial_cmp().unwrap(), bvh.rs:26
+                bad.store(2);
+                return;
+            }
+        }
+        // bvh.rs:51 sort_unstable_by: the order of equal keys is unspecified in the reference;
+        // a stable sort fixes it (same choice as the oracle)
+        std::stable_sort(idx.begin() + first, idx.begin() + first + n, [&](uint32_t x, uint32_t y) {
+            return boxes[x].lo[axis] + boxes[x].hi[axis] < boxes[y].lo[axis] + boxes[y].hi[axis];
+        });
+        const size_t half = n / 2;
+        if (n >= 16384 && depth < 5) {
+            auto left = std::async(std::launch::async, [&] { rec(first, half, depth + 1); });
+            rec(first + half, n - half, depth + 1);
+            left.get();
+        } else {
+            rec(first, half, depth + 1);
+            rec(first + half, n - half, depth + 1);
+        }
+    }
+};
+
+bool ref_bvh_order(const RtSceneDesc &d, const std::vector<uint32_t> &hit, double t0, double t1, std::vector<uint32_t> &out,
                    std::string &err) {
     if (hit.empty()) {
         err = "no object in the scene";  // bvh.rs:55
@@ -455,42 +523,15 @@ bool ref_bvh_order(const RtSceneDesc &d, std::vector<uint32_t> hit, double t0, d
             err = "no bounding box in bvh node";  // bvh.rs:28,61
             return false;
         }
-    if (hit.size() == 1) {
-        out.push_back(hit[0]);
-        return true;
+    RefOrder ro{hit, boxes, std::vector<uint32_t>(hit.size()), out};
+    for (size_t i = 0; i < hit.size(); ++i) ro.idx[i] = (uint32_t)i;
+    ro.rec(0, hit.size(), 0);
+    if (ro.bad.load()) {
+        err = ro.bad.load() == 1 ? "NaN extent in BVH build" : "NaN centroid in BVH build";
+        return false;
     }
-    int axis = 0;
-    double range[3];
-    for (int a = 0; a < 3; ++a) {  // bvh.rs:33-48
-        double bmin = DBL_MAX, bmax = -DBL_MAX;
-        for (const RefBox &b : boxes) {
-            bmin = std::fmin(bmin, b.lo[a]);
-            bmax = std::fmax(bmax, b.hi[a]);
-        }
-        range[a] = bmax - bmin;
-        if (range[a] != range[a]) {
-            err = "NaN extent in BVH build";  // partial_cmp().unwrap(), bvh.rs:47
-            return false;
-        }
-    }
-    if (range[1] > range[axis]) axis = 1;
-    if (range[2] > range[axis]) axis = 2;
-    std::vector<uint32_t> idx(hit.size());
-    for (size_t i = 0; i < idx.size(); ++i) idx[i] = (uint32_t)i;
-    for (const RefBox &b : boxes)
-        if (b.lo[axis] + b.hi[axis] != b.lo[axis] + b.hi[axis]) {
-            err = "NaN centroid in BVH build";  // partial_cmp().unwrap(), bvh.rs:26
-            return false;
-        }
-    // bvh.rs:51 sort_unstable_by: the order of equal keys is unspecified in the reference;
-    // a stable sort fixes it (same choice as the oracle)
-    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
-        return boxes[a].lo[axis] + boxes[a].hi[axis] < boxes[b].lo[axis] + boxes[b].hi[axis];
-    });
-    size_t half = hit.size() / 2;
-    std::vector<uint32_t> left, right;
-    for (size_t i = 0; i < idx.size(); ++i) (i < half ? left : right).push_back(hit[idx[i]]);
-    return ref_bvh_order(d, std::move(left), t0, t1, out, err) && ref_bvh_order(d, std::move(right), t0, t1, out, err);
+    for (size_t i = 0; i < hit.size(); ++i) out.push_back(hit[ro.idx[i]]);
+    return true;
 }
 
 struct Walker {
@@ -850,13 +891,17 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     for (int a = 0; a < 3; ++a) out.background[a] = d.background[a];
 
     // ---- world ----
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[compile] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     Walker w{d, out, err};
     std::vector<GroupBuild> world_groups;
     std::vector<PendingMedium> pending;
     w.groups = &world_groups;
     w.media = &pending;
     if (!w.walk(d.world, 0)) return w.status;
+    lap("walk");
     if (!finalize_groups(out, world_groups, err)) return RT_ERR_BAD_ARGUMENT;
+    lap("finalize (BVH build)");
     out.n_world_groups = (uint32_t)out.groups.size();
     if (out.n_world_groups == 0 && pending.empty()) {
         err = "no object in the scene";

@@ -19,9 +19,6 @@
 // to the megakernel's and to itself run after run.
 // (included by pipelines.cu inside the variant namespace)
 
-#ifndef RT_WF_REFILL_THRESHOLD
-#define RT_WF_REFILL_THRESHOLD 24
-#endif
 #ifndef RT_WF_INNER_THRESHOLD
 #define RT_WF_INNER_THRESHOLD 12
 #endif

@@ -291,3 +291,20 @@ def test_extra_scenes_match_oracle(rt, orc, name):
         a = rt.format_image(img, 16).astype(np.float64)
         b = orc.format_image(ref, 16).astype(np.float64)
         assert float(np.sqrt(np.mean((a - b) ** 2)) / 255.0) <= 0.01
+
+
+def test_render_info_reports_pipeline_and_variant(rt, orc):
+    """rt_render_info: which pipeline build a render ran (the choice is per scene)."""
+    abi = rt._abi
+    expect = {"cornell": ("megakernel", "vflat"), "final": ("wavefront", "vnextweek"), "mesh": ("megakernel", "vmesh"),
+              "random": ("megakernel", "vspheres"), "cornell_pbr": ("megakernel", "vall")}
+    for name, (pipeline, variant) in expect.items():
+        hs, dev, _ = scenes(rt, orc, name)
+        dev.render(hs.camera, 32, 32, 2, 10, rt.render_opts(seed=1, integrator=hs.integrator))
+        info = dev.render_info
+        assert (info["pipeline"], info["variant"]) == (pipeline, variant), (name, info)
+    hs, dev, _ = scenes(rt, orc, "cornell")
+    dev.render(hs.camera, 32, 32, 2, 10, rt.render_opts(seed=1, flags=abi.FLAG_WAVEFRONT))
+    assert dev.render_info["pipeline"] == "wavefront" and int(dev.render_info["pool_slots"]) == 32 * 32 * 2
+    with pytest.raises(rt.RtError):
+        dev.render(hs.camera, 32, 32, 2, 10, rt.render_opts(seed=1, flags=abi.FLAG_WAVEFRONT | abi.FLAG_MEGAKERNEL))
