@@ -67,6 +67,11 @@ struct RtScene {
     bool has_media = false;
     bool wavefront_default = false;
     std::string render_info;
+    cudaGraphExec_t wf_exec = nullptr;  // the wavefront round loop as a CUDA graph (kept alive until the next render)
+    cudaGraph_t wf_graph = nullptr;
+    cudaStream_t wf_capture_stream = nullptr;
+    WfCtl *wf_ctl_host = nullptr;  // pinned copy of the control block (rounds_done for the stats)
+    int wf_rounds_per_launches = 0;  // graph mode: kernels per round, to complete the launch count after the fact
     // last async render
     bool pending = false;
     cudaStream_t pending_stream = nullptr;
@@ -80,6 +85,10 @@ struct RtScene {
         if (out_dev) cudaFree(out_dev);
         if (counters) cudaFree(counters);
         if (counters_host) cudaFreeHost(counters_host);
+        if (wf_exec) cudaGraphExecDestroy(wf_exec);
+        if (wf_graph) cudaGraphDestroy(wf_graph);
+        if (wf_capture_stream) cudaStreamDestroy(wf_capture_stream);
+        if (wf_ctl_host) cudaFreeHost(wf_ctl_host);
         for (void *p : wf_allocations) cudaFree(p);
         if (wf_status_host) cudaFreeHost(wf_status_host);
         if (ev0) cudaEventDestroy(ev0);
@@ -250,6 +259,7 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
         w.capacity = cap;
         s.wf = w;
         if (!s.wf_status_host) CU(cudaMallocHost((void **)&s.wf_status_host, sizeof(unsigned)));
+        if (!s.wf_ctl_host) CU(cudaMallocHost((void **)&s.wf_ctl_host, sizeof(WfCtl)));
     }
     // never more slots than there are work items
     uint64_t items = (uint64_t)P.width * P.height * P.n_chunks;
@@ -258,23 +268,73 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
 }
 
 // The wavefront pipeline: rounds of shade / generate / extend / control until no path is alive.
-// The number of rounds depends on the paths, so the host reads the live count back every few
-// rounds (an empty round is four kernels that find nothing to do).
-RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
-    const int kRoundsPerCheck = 8;
+// The number of rounds depends on the paths.  Default: the round is the body of a CUDA-graph WHILE
+// node whose condition the control kernel sets on the device (cudaGraphSetConditional), so the whole
+// loop is ONE graph launch - no host round trip, and rt_render_device stays asynchronous.
+// Fallback (RTB200_WF_GRAPH=0, or a driver without conditional nodes): the host enqueues 8 rounds at
+// a time and reads the live count back (an empty round is a few kernels that find nothing to do).
+uint32_t wf_leave_threshold(const RtScene &s) {
     // When a warp of the extend stage goes back for new rays (wavefront.inl, phase C): with long,
     // uneven traversals (triangle BVHs) as soon as half of its rays wait; otherwise never - every
     // ray of a media / sphere scene walks the same sequence of queries, and a warp that stays in
     // lockstep runs those steps with all lanes (measured: profiles/r1_f_pipeline_ab.md).
     uint32_t leave = (s.features & F_TRI) ? 16u : 1u;
     if (const char *v = std::getenv("RTB200_WF_LEAVE")) leave = (uint32_t)std::atoi(v);
-    if (leave < 1u) leave = 1u;
-    if (leave > 32u) leave = 32u;
+    return leave < 1u ? 1u : (leave > 32u ? 32u : leave);
+}
+
+cudaError_t build_wavefront_graph(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P) {
+    if (s.wf_exec) cudaGraphExecDestroy(s.wf_exec);
+    if (s.wf_graph) cudaGraphDestroy(s.wf_graph);
+    s.wf_exec = nullptr;
+    s.wf_graph = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (!s.wf_capture_stream) e = cudaStreamCreateWithFlags(&s.wf_capture_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaGraphCreate(&s.wf_graph, 0)) != cudaSuccess) return e;
+    cudaGraphConditionalHandle handle;
+    if ((e = cudaGraphConditionalHandleCreate(&handle, s.wf_graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return e;
+    cudaGraphNodeParams np{};
+    np.type = cudaGraphNodeTypeConditional;
+    np.conditional.handle = handle;
+    np.conditional.type = cudaGraphCondTypeWhile;
+    np.conditional.size = 1;
+    cudaGraphNode_t node;
+    if ((e = cudaGraphAddNode(&node, s.wf_graph, nullptr, 0, &np)) != cudaSuccess) return e;
+    cudaGraph_t body = np.conditional.phGraph_out[0];
+    if ((e = cudaStreamBeginCaptureToGraph(s.wf_capture_stream, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed)) != cudaSuccess) return e;
+    cudaError_t le = pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, wf_leave_threshold(s),
+                                        (unsigned long long)handle, s.wf_capture_stream);
+    e = cudaStreamEndCapture(s.wf_capture_stream, nullptr);
+    if (le != cudaSuccess) return le;
+    if (e != cudaSuccess) return e;
+    return cudaGraphInstantiate(&s.wf_exec, s.wf_graph, 0);
+}
+
+RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
+    const int per_round = kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0);
     CU(pv.wf_launch_init(s.wf, st));
     s.pending_launches += 1;
+    const char *g = std::getenv("RTB200_WF_GRAPH");
+    if (!g || std::atoi(g) != 0) {
+        cudaError_t e = build_wavefront_graph(s, pv, cam, P);
+        if (e == cudaSuccess) e = cudaGraphLaunch(s.wf_exec, st);
+        if (e == cudaSuccess) {
+            // rounds_done comes back with the counters; the launch count is completed in finish_render
+            CU(cudaMemcpyAsync(s.wf_ctl_host, s.wf.ctl, sizeof(WfCtl), cudaMemcpyDeviceToHost, st));
+            s.wf_rounds_per_launches = per_round;
+            s.render_info += " loop=graph";
+            return RT_OK;
+        }
+        cudaGetLastError();  // conditional graph nodes unavailable: the host drives the loop
+    }
+    const int kRoundsPerCheck = 8;
+    const uint32_t leave = wf_leave_threshold(s);
+    s.wf_rounds_per_launches = 0;
+    s.render_info += " loop=host";
     for (;;) {
-        for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, leave, st));
-        s.pending_launches += (uint64_t)kRoundsPerCheck * (kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0));
+        for (int k = 0; k < kRoundsPerCheck; ++k) CU(pv.wf_launch_round(s.ds, cam, P, s.wf, s.planes, s.counters, s.has_media, s.sms, leave, 0ull, st));
+        s.pending_launches += (uint64_t)kRoundsPerCheck * per_round;
         CU(cudaMemcpyAsync(s.wf_status_host, &s.wf.ctl->status_live, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         if (*s.wf_status_host == 0u) break;
@@ -286,6 +346,7 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
     CU(cudaMemsetAsync(s.counters, 0, sizeof(unsigned long long) * kNumCounters, st));
     CU(cudaEventRecord(s.ev0, st));
     s.pending_launches = 0;
+    s.wf_rounds_per_launches = 0;
     const PipelineVariant &pv = *pick_variant(s, P.integrator);
     if (wavefront) {
         s.render_info = std::string("pipeline=wavefront variant=") + pv.name + " pool_slots=" + std::to_string(s.wf.n_slots);
@@ -316,6 +377,10 @@ RtStatus finish_render(RtScene &s, cudaStream_t st, RtStats *stats, uint64_t d2h
         stats->nonfinite_samples = s.counters_host[kCounterNonFinite];
         stats->render_ms = ms;
         stats->total_ms = now_ms() - s.t_call0;
+        if (s.wf_rounds_per_launches) {  // the graph ran rounds_done rounds on its own
+            s.pending_launches += (uint64_t)s.wf_ctl_host->rounds_done * s.wf_rounds_per_launches;
+            s.wf_rounds_per_launches = 0;
+        }
         stats->kernel_launches = s.pending_launches;
         stats->h2d_bytes = sizeof(DScene) + sizeof(RtCamera) + sizeof(RenderParams);  // kernel arguments only
         stats->d2h_bytes = d2h_bytes + sizeof(unsigned long long) * kNumCounters;

@@ -29,7 +29,7 @@ struct PipelineVariant {
     cudaError_t (*wf_launch_init)(const WfPool &pool, cudaStream_t stream);
     cudaError_t (*wf_launch_round)(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
                                    double *planes, unsigned long long *counters, bool media, int sms, uint32_t leave_threshold,
-                                   cudaStream_t stream);
+                                   unsigned long long cond_handle, cudaStream_t stream);
 };
 
 #define RT_DECLARE_VARIANT(ns) const PipelineVariant *rtb200_variant_##ns();

@@ -538,7 +538,9 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
 // ---------------------------------------------------------------------------
 // control: end of a round
 // ---------------------------------------------------------------------------
-__global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
+// cond: the handle of the CUDA-graph while-node whose body this round is (0: the host drives the loop)
+__global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters,
+                                  cudaGraphConditionalHandle cond) {
     WfCtl *c = pool.ctl;
     const unsigned cur = c->round & 1u;
     const unsigned live = c->live[cur];
@@ -549,6 +551,7 @@ __global__ void wf_control_kernel(const __grid_constant__ WfPool pool, unsigned 
     c->defer_n = 0u;
     c->round += 1u;
     c->rounds_done += 1u;
+    if (cond) cudaGraphSetConditional(cond, live != 0u ? 1u : 0u);  // another round while any path is alive
 }
 
 // ---------------------------------------------------------------------------
@@ -564,7 +567,7 @@ static cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
 
 static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
                             double *planes, unsigned long long *counters, bool media, int sms, uint32_t leave_threshold,
-                            cudaStream_t stream) {
+                            unsigned long long cond_handle, cudaStream_t stream) {
     static int ext_per_sm[2] = {0, 0};
     if (ext_per_sm[0] == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_per_sm[0], wf_extend_kernel<false>, kWfBlock, 0);
@@ -590,7 +593,7 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
     wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
     if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
     else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
-    wf_control_kernel<<<1, 1, 0, stream>>>(pool, counters);
+    wf_control_kernel<<<1, 1, 0, stream>>>(pool, counters, (cudaGraphConditionalHandle)cond_handle);
     return cudaGetLastError();
 }
 
