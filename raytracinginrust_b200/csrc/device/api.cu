@@ -278,9 +278,9 @@ uint32_t wf_leave_threshold(const RtScene &s) {
     // uneven traversals (triangle BVHs) as soon as half of its rays wait; otherwise never - every
     // ray of a media / sphere scene walks the same sequence of queries, and a warp that stays in
     // lockstep runs those steps with all lanes (measured: profiles/r1_f_pipeline_ab.md).
-    uint32_t leave = (s.features & F_TRI) ? 16u : 1u;
+    uint32_t leave = (s.features & F_TRI) ? 16u : 33u;
     if (const char *v = std::getenv("RTB200_WF_LEAVE")) leave = (uint32_t)std::atoi(v);
-    return leave < 1u ? 1u : (leave > 32u ? 32u : leave);
+    return leave > 33u ? 33u : leave;  // 0: batch mode (refill only when the whole warp is idle); 33: the simple extend kernel
 }
 
 cudaError_t build_wavefront_graph(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P) {

@@ -639,22 +639,16 @@ RT_DEV void resolve_medium(const DScene &sc, const Ray &world, const Best &best,
 // query 0 is the world's surfaces; then, per ConstantMedium, the two boundary queries of
 // medium.rs:29-30.  Media are visited after the surfaces: with slot-addressed draws the outcome
 // does not depend on list order.  `closest` is closest_so_far (hit.rs:61-66) in reference arithmetic.
-template <bool WITH_MEDIA, bool WANT_UV>
-RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &rec) {
+// The SEARCH half of world_hit: which primitive (or medium) wins, and closest_so_far in reference
+// arithmetic.  Returns false on a miss.
+template <bool WITH_MEDIA>
+RT_DEV bool world_search(const DScene &sc, const Ray &r, const Rng &rng, Best &win, double &closest) {
     V3 inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
-    Best win{RT_INF, kNoPrim, 0, 0};
-    double closest = RT_INF;
+    win = Best{RT_INF, kNoPrim, 0, 0};
+    closest = RT_INF;
     double t1 = 0.0;
     bool have_t1 = false;
     const uint32_t nq = 1u + (WITH_MEDIA ? 2u * sc.n_media : 0u);
-    if (!WITH_MEDIA) {  // one query; t and the record come from one object-space ray
-        trace_groups(sc, 0, sc.n_world_groups, r, inv, kTMin, win);
-        if (win.prim == kNoPrim) return false;
-        V3 o, d;
-        object_ray(sc, sc.prims[win.prim].chain, r, o, d);
-        resolve_hit_obj<WANT_UV>(sc, r, win, exact_t_obj(sc, win, o, d, r.time, kTMin), o, d, rec);
-        return true;
-    }
 #pragma unroll 1
     for (uint32_t q = 0; q < nq; ++q) {
         uint32_t fg = 0, ng = sc.n_world_groups, mi = 0;
@@ -704,7 +698,23 @@ RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &re
             }
         }
     }
-    if (win.prim == kNoPrim) return false;
+    return win.prim != kNoPrim;
+}
+
+template <bool WITH_MEDIA, bool WANT_UV>
+RT_DEV bool world_hit(const DScene &sc, const Ray &r, const Rng &rng, HitRec &rec) {
+    Best win{RT_INF, kNoPrim, 0, 0};
+    if (!WITH_MEDIA) {  // one query; t and the record come from one object-space ray
+        V3 inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
+        trace_groups(sc, 0, sc.n_world_groups, r, inv, kTMin, win);
+        if (win.prim == kNoPrim) return false;
+        V3 o, d;
+        object_ray(sc, sc.prims[win.prim].chain, r, o, d);
+        resolve_hit_obj<WANT_UV>(sc, r, win, exact_t_obj(sc, win, o, d, r.time, kTMin), o, d, rec);
+        return true;
+    }
+    double closest;
+    if (!world_search<WITH_MEDIA>(sc, r, rng, win, closest)) return false;
     if (win.prim & kMediumFlag) resolve_medium(sc, r, win, closest, rec);
     else resolve_hit<WANT_UV>(sc, r, win, closest, rec);
     return true;

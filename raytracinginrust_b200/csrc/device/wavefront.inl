@@ -26,7 +26,7 @@
 #define RT_WF_EXTEND_MIN_BLOCKS 4
 #endif
 #ifndef RT_WF_SHADE_MIN_BLOCKS
-#define RT_WF_SHADE_MIN_BLOCKS 4
+#define RT_WF_SHADE_MIN_BLOCKS 6
 #endif
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
@@ -356,7 +356,9 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
     for (;;) {
         // ---- A: refill ----------------------------------------------------------------------
         const unsigned want = __ballot_sync(kFull, !has_ray);
-        if (want != 0u && !exhausted) {
+        // leave_threshold == 0: batch mode - new rays only when the whole warp is idle, so that all
+        // its rays walk the query / group sequence of world_hit in step
+        if (want != 0u && !exhausted && (leave_threshold != 0u || want == kFull)) {
             if (wbase == wend) {
                 unsigned got = 0;
                 if (lane == 0) got = atomicAdd(cursor, kWfReserve);
@@ -535,6 +537,37 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
     }
 }
 
+// extend, simple form: one slot per thread, world_hit's search as straight-line code.  Used where
+// every ray walks the same sequence of queries and groups (no triangle BVH): the warp stays in
+// step through the bookkeeping, and the state machine above has nothing to replace.
+#ifndef RT_WF_SIMPLE_MIN_BLOCKS
+#define RT_WF_SIMPLE_MIN_BLOCKS 8
+#endif
+template <bool MEDIA>
+__global__ void __launch_bounds__(kWfBlock, RT_WF_SIMPLE_MIN_BLOCKS)
+wf_extend_simple_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= pool.n_slots || pool.state[slot] != WF_LIVE) return;
+    const double2 *u = slot_d2(pool, slot);
+    const double2 r0 = u[0], r1 = u[1], r2 = u[2];
+    const uint4 u3 = ld_u4(u + 3);
+    Ray ray;
+    ray.o = mk(r0.x, r0.y, r1.x);
+    ray.d = mk(r1.y, r2.x, r2.y);
+    ray.time = unpack_lo_double(u3);
+    Rng rng{seed, 0u, 0u, 0u};
+    if (MEDIA) {
+        const uint4 u5 = ld_u4(u + 5);
+        rng.pixel = u5.z;
+        rng.sample = u5.w;
+        rng.bounce = max_depth - u3.w;
+    }
+    Best win;
+    double closest;
+    world_search<MEDIA>(sc, ray, rng, win, closest);
+    st_u4(slot_d2w(pool, slot) + 6, make_uint4(win.prim, (uint32_t)win.face, (uint32_t)__double2loint(closest), (uint32_t)__double2hiint(closest)));
+}
+
 // ---------------------------------------------------------------------------
 // control: end of a round
 // ---------------------------------------------------------------------------
@@ -591,8 +624,14 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
         wf_shade_deferred_kernel<<<g ? g : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);
     }
     wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
-    if (media) wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
-    else wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
+    if (leave_threshold == 33u) {  // the simple form: one slot per thread
+        if (media) wf_extend_simple_kernel<true><<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+        else wf_extend_simple_kernel<false><<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+    } else if (media) {
+        wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
+    } else {
+        wf_extend_kernel<false><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
+    }
     wf_control_kernel<<<1, 1, 0, stream>>>(pool, counters, (cudaGraphConditionalHandle)cond_handle);
     return cudaGetLastError();
 }
