@@ -257,7 +257,8 @@ uint64_t rt_scene_device_bytes(const RtScene *scene);
  * over the rendered sample range into caller-owned host memory, rows top-down
  * (first row is j = H-1, src/main.rs:772), columns left to right, RGB
  * interleaved.  The host divides by spp, applies format_color
- * (src/vec.rs:125-131) and writes the PPM. */
+ * (src/vec.rs:125-131) and writes the PPM.  out_rgb_sum may be NULL: the image then
+ * only stays resident on the device, for rt_encode_rgb8 / rt_encode_ppm. */
 RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height,
                    uint32_t spp, uint32_t max_depth, const RtRenderOpts *opts,
                    float *out_rgb_sum, RtStats *stats);
@@ -292,6 +293,58 @@ RtStatus rt_path_radiance(const RtScene *scene, const RtCamera *camera, uint32_t
 RtStatus rt_camera_rays(const RtScene *scene, const RtCamera *camera, uint32_t width,
                         uint32_t height, const RtRenderOpts *opts, const uint32_t *px,
                         const uint32_t *py, const uint32_t *sample, uint64_t n, RtRay *rays);
+
+/* ------------------------------------------------------------------------ */
+/* One host thread, N GPUs (SURVEY §8(b) "Threading", §8(e))                  */
+/* ------------------------------------------------------------------------ */
+
+/* A scene replicated on several GPUs of one box.  The Rust host is one process
+ * (src/main.rs has one main thread above rayon); this is the handle it holds
+ * when render() should use every GPU.  The scene graph is compiled ONCE on the
+ * host and the tables are uploaded to each device. */
+typedef struct RtSceneGroup RtSceneGroup;
+
+/* devices = NULL means devices 0..n_devices-1; n_devices = 0 means all visible devices. */
+RtStatus rt_scene_group_create(const RtSceneDesc *desc, const int *devices, uint32_t n_devices,
+                               RtSceneGroup **out_group);
+void rt_scene_group_destroy(RtSceneGroup *group);
+uint32_t rt_scene_group_size(const RtSceneGroup *group);
+/* The per-device scene (i = 0 is the root that holds the combined image). */
+const RtScene *rt_scene_group_scene(const RtSceneGroup *group, uint32_t i);
+
+/* rt_render over all GPUs of the group.  The sample range of `opts` is cut into
+ * contiguous blocks, one per GPU, every GPU renders its block for ALL pixels with
+ * the same Philox keys (the union of samples is identical for any GPU count), and
+ * the fp32 sum images are added on the root GPU in device order by ONE kernel that
+ * reads the peers' images through NVLink peer mappings (staged with
+ * cudaMemcpyPeerAsync where two devices cannot map each other).  The result is
+ * bit-identical to rendering the same blocks one after the other and adding them
+ * in fp32.  out_rgb_sum (host, W*H*3) may be NULL: the combined image then stays on
+ * the root GPU for rt_encode_rgb8 / rt_encode_ppm. */
+RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint32_t width, uint32_t height,
+                         uint32_t spp, uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum,
+                         RtStats *stats);
+
+/* ------------------------------------------------------------------------ */
+/* Output on the device: Vec3::format_color + the P3 body                    */
+/* ------------------------------------------------------------------------ */
+
+/* Vec3::format_color (src/vec.rs:125-131) for every pixel, on the GPU:
+ * channel = (256 * clamp(sqrt(sum / samples_per_pixel), 0, 0.999)) as u64, with Rust's
+ * saturating cast (NaN -> 0).  rgb_sum_device = NULL takes the image the last
+ * rt_render / rt_render_multi on `scene` produced (it stays resident on the device);
+ * otherwise it is a W*H*3 fp32 device buffer on the scene's device (e.g. the
+ * ncclReduce result).  out_rgb8 is HOST memory, W*H*3 bytes. */
+RtStatus rt_encode_rgb8(const RtScene *scene, const float *rgb_sum_device, uint32_t width, uint32_t height,
+                        uint64_t samples_per_pixel, uint8_t *out_rgb8);
+
+/* The whole P3 file the reference prints (src/main.rs:767-769,832): "P3\nW H\n255\n"
+ * and one "r g b\n" line per pixel, formatted on the GPU (format_color, decimal
+ * digits, a prefix sum over the line lengths) and copied out as text.  `out` is HOST
+ * memory of `capacity` bytes; 32 + 12*W*H always suffices.  *length receives the file
+ * size (no terminating NUL).  Byte-identical to the host writer. */
+RtStatus rt_encode_ppm(const RtScene *scene, const float *rgb_sum_device, uint32_t width, uint32_t height,
+                       uint64_t samples_per_pixel, char *out, uint64_t capacity, uint64_t *length);
 
 /* Diagnostic: which pipeline build the last rt_render / rt_render_device on this scene ran, e.g.
  * "pipeline=megakernel variant=vflat blocks_per_sm=6".  The string lives until the next render

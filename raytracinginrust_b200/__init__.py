@@ -69,6 +69,18 @@ _dev.rt_camera_rays.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c
 _dev.rt_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
 _dev.rt_last_error.restype = C.c_char_p
 _dev.rt_version.restype = C.c_char_p
+_dev.rt_scene_group_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]
+_dev.rt_scene_group_destroy.argtypes = [C.c_void_p]
+_dev.rt_scene_group_destroy.restype = None
+_dev.rt_scene_group_size.argtypes = [C.c_void_p]
+_dev.rt_scene_group_size.restype = C.c_uint32
+_dev.rt_scene_group_scene.argtypes = [C.c_void_p, C.c_uint32]
+_dev.rt_scene_group_scene.restype = C.c_void_p
+_dev.rt_render_multi.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(RtStats)]
+_dev.rt_encode_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
+_dev.rt_encode_ppm.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
+                               C.POINTER(C.c_uint64)]
 
 _host.rth_last_error.restype = C.c_char_p
 _host.rth_scene_build.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]
@@ -88,6 +100,8 @@ _host.rth_format_image.restype = None
 _host.rth_write_ppm.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64]
 _host.rth_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
                              C.c_int, C.c_void_p, C.POINTER(RtStats)]
+_host.rth_render_ppm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
+                                 C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(RtStats)]
 _host.rth_obj_triangle_count.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
 
 
@@ -329,18 +343,35 @@ class HostScene:
         return out, stats
 
 
+    def render_ppm(self, width, height, spp, max_depth, opts=None, n_gpus=1):
+        """render() over n_gpus GPUs (0 = all) with format_color and the P3 text done on the GPU -> bytes:
+        what `rtb200_render --scene ... > image.ppm` writes."""
+        opts = opts or render_opts(integrator=self.integrator)
+        cap = 32 + 12 * width * height
+        buf = np.empty(cap, dtype=np.uint8)
+        n, stats = C.c_uint64(), RtStats()
+        _check_host(_host.rth_render_ppm(self._h, width, height, spp, max_depth, C.byref(opts), n_gpus,
+                                         buf.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(stats)))
+        return buf[:int(n.value)].tobytes(), stats
+
+
 class DeviceScene:
     """A scene compiled and resident on one GPU (rt_scene_create)."""
 
-    def __init__(self, scene_desc, device=0):
+    def __init__(self, scene_desc, device=0, _borrowed=None):
         self._h = C.c_void_p()
         self._desc = scene_desc
-        _check(_dev.rt_scene_create(scene_desc.ptr, device, C.byref(self._h)))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            _check(_dev.rt_scene_create(scene_desc.ptr, device, C.byref(self._h)))
+        else:  # a member of a SceneGroup: the group owns the handle
+            self._h = C.c_void_p(_borrowed)
         self.device = device
 
     def close(self):
         if getattr(self, "_h", None):
-            _dev.rt_scene_destroy(self._h)
+            if self._owned:
+                _dev.rt_scene_destroy(self._h)
             self._h = None
 
     __del__ = close
@@ -355,13 +386,31 @@ class DeviceScene:
         text = (_dev.rt_render_info(self._h) or b"").decode()
         return dict(kv.split("=", 1) for kv in text.split() if "=" in kv)
 
-    def render(self, camera, width, height, spp, max_depth, opts=None):
+    def render(self, camera, width, height, spp, max_depth, opts=None, want_sums=True):
+        """rt_render.  want_sums=False leaves the image on the device (for encode_rgb8 / encode_ppm)."""
         opts = opts or render_opts()
-        out = np.empty((height, width, 3), dtype=np.float32)
+        out = np.empty((height, width, 3), dtype=np.float32) if want_sums else None
         stats = RtStats()
         _check(_dev.rt_render(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
-                              out.ctypes.data_as(C.c_void_p), C.byref(stats)))
+                              out.ctypes.data_as(C.c_void_p) if want_sums else None, C.byref(stats)))
         return out, stats
+
+    def encode_rgb8(self, width, height, samples_per_pixel, sums_ptr=0):
+        """Vec3::format_color (src/vec.rs:125-131) on the GPU -> (H, W, 3) uint8.  sums_ptr: a W*H*3 fp32
+        device buffer on this scene's GPU, or 0 for the image the last render left resident."""
+        out = np.empty((height, width, 3), dtype=np.uint8)
+        _check(_dev.rt_encode_rgb8(self._h, C.c_void_p(sums_ptr) if sums_ptr else None, width, height, samples_per_pixel,
+                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def encode_ppm(self, width, height, samples_per_pixel, sums_ptr=0, capacity=None):
+        """The whole P3 file (src/main.rs:767-769,832), formatted on the GPU -> bytes."""
+        cap = int(capacity if capacity is not None else 32 + 12 * width * height)
+        buf = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_uint64()
+        _check(_dev.rt_encode_ppm(self._h, C.c_void_p(sums_ptr) if sums_ptr else None, width, height, samples_per_pixel,
+                                  buf.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return buf[:int(n.value)].tobytes()
 
     def render_device(self, camera, width, height, spp, max_depth, opts, out_ptr, stream_ptr=0):
         """Enqueue a render into device memory `out_ptr` (W*H*3 fp32) on CUDA stream `stream_ptr`."""
@@ -399,6 +448,44 @@ class DeviceScene:
                                    px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
                                    sample.ctypes.data_as(C.c_void_p), n, rays.ctypes.data_as(C.c_void_p)))
         return rays
+
+
+class SceneGroup:
+    """A scene replicated on several GPUs of one box, driven by ONE host thread (rt_scene_group_create /
+    rt_render_multi): contiguous sample blocks per GPU, one combine kernel over NVLink peer memory."""
+
+    def __init__(self, scene_desc, devices=None):
+        self._h = C.c_void_p()
+        self._desc = scene_desc
+        if devices is None:
+            arr, n = None, 0
+        else:
+            devices = [int(d) for d in devices]
+            arr, n = (C.c_int * len(devices))(*devices), len(devices)
+        _check(_dev.rt_scene_group_create(scene_desc.ptr, arr, n, C.byref(self._h)))
+        self.size = int(_dev.rt_scene_group_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _dev.rt_scene_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def scene(self, i=0):
+        """The i-th per-device scene (0 = the root, which holds the combined image)."""
+        h = _dev.rt_scene_group_scene(self._h, i)
+        if not h:
+            raise IndexError(i)
+        return DeviceScene(self._desc, _borrowed=h)
+
+    def render(self, camera, width, height, spp, max_depth, opts=None, want_sums=True):
+        opts = opts or render_opts()
+        out = np.empty((height, width, 3), dtype=np.float32) if want_sums else None
+        stats = RtStats()
+        _check(_dev.rt_render_multi(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
+                                    out.ctypes.data_as(C.c_void_p) if want_sums else None, C.byref(stats)))
+        return out, stats
 
 
 # ---------------------------------------------------------------------------------------

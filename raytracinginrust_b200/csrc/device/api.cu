@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/rtb200.h"
@@ -57,6 +58,7 @@ struct RtScene {
     size_t planes_bytes = 0;
     float *out_dev = nullptr;
     size_t out_bytes = 0;
+    uint32_t out_width = 0, out_height = 0;  // the image out_dev holds (rt_render / rt_render_multi), for rt_encode_*
     unsigned long long *counters = nullptr;
     unsigned long long *counters_host = nullptr;  // pinned
     // wavefront pipeline: path pool + queues, allocated on first use
@@ -388,39 +390,31 @@ RtStatus finish_render(RtScene &s, cudaStream_t st, RtStats *stats, uint64_t d2h
     return RT_OK;
 }
 
-}  // namespace
-
-extern "C" {
-
-const char *rt_last_error(void) { return g_err.c_str(); }
-const char *rt_version(void) { return "rtb200 abi 1 sm_100a f64"; }
-
-int rt_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-    }
-    return n;
-}
-
-RtStatus rt_measure_fp64_peak(int device, double *tflops_out) {
-    if (!tflops_out) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
-    int n = rt_device_count();
-    if (n == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
-    if (device < 0 || device >= n) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
-    CU(cudaSetDevice(device));
-    CU(measure_fp64_peak(device, tflops_out));
+// rt_render's first half: parameters, scratch, kernels enqueued on the scene's own stream into its own
+// resident image (s.out_dev).  rt_render_multi runs this once per GPU.
+RtStatus start_render_own(RtScene &s, const RtCamera &camera, uint32_t width, uint32_t height, uint32_t spp,
+                          uint32_t max_depth, const RtRenderOpts *opts) {
+    s.t_call0 = now_ms();
+    CU(cudaSetDevice(s.device));
+    RenderParams P;
+    const bool wavefront = use_wavefront(s, opts, max_depth);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    if (st != RT_OK) return st;
+    st = ensure_scratch(s, P, true);
+    if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
+    if (st != RT_OK) return st;
+    s.out_width = s.out_height = 0;
+    st = enqueue_render(s, camera, P, wavefront, s.out_dev, s.stream);
+    if (st != RT_OK) return st;
+    s.out_width = width;
+    s.out_height = height;
     return RT_OK;
 }
 
-RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
-    if (!desc || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+// Upload a compiled scene to one device (the second half of rt_scene_create; a scene group compiles
+// once and calls this per GPU).
+RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_scene) {
     *out_scene = nullptr;
-    CompiledScene cs;
-    std::string err;
-    RtStatus st = compile_scene(*desc, cs, err);
-    if (st != RT_OK) return fail(st, err);
     int n = rt_device_count();
     if (n == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
     if (device < 0 || device >= n) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
@@ -475,6 +469,42 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
     return RT_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+const char *rt_last_error(void) { return g_err.c_str(); }
+const char *rt_version(void) { return "rtb200 abi 1 sm_100a f64"; }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+RtStatus rt_measure_fp64_peak(int device, double *tflops_out) {
+    if (!tflops_out) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    int n = rt_device_count();
+    if (n == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    CU(measure_fp64_peak(device, tflops_out));
+    return RT_OK;
+}
+
+RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
+    if (!desc || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *out_scene = nullptr;
+    CompiledScene cs;
+    std::string err;
+    RtStatus st = compile_scene(*desc, cs, err);
+    if (st != RT_OK) return fail(st, err);
+    return create_on_device(cs, device, out_scene);
+}
+
 void rt_scene_destroy(RtScene *scene) { delete scene; }
 
 uint64_t rt_scene_device_bytes(const RtScene *scene) { return scene ? scene->device_bytes : 0; }
@@ -512,22 +542,293 @@ RtStatus rt_render_wait(const RtScene *scene, RtStats *stats) {
 
 RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height, uint32_t spp,
                    uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum, RtStats *stats) {
-    if (!scene || !camera || !out_rgb_sum) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    if (!scene || !camera) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     RtScene &s = *const_cast<RtScene *>(scene);
-    s.t_call0 = now_ms();
-    CU(cudaSetDevice(s.device));
-    RenderParams P;
-    const bool wavefront = use_wavefront(s, opts, max_depth);
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
+    RtStatus st = start_render_own(s, *camera, width, height, spp, max_depth, opts);
     if (st != RT_OK) return st;
-    st = ensure_scratch(s, P, true);
-    if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
-    if (st != RT_OK) return st;
-    st = enqueue_render(s, *camera, P, wavefront, s.out_dev, s.stream);
-    if (st != RT_OK) return st;
-    size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
-    CU(cudaMemcpyAsync(out_rgb_sum, s.out_dev, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+    size_t out_bytes = out_rgb_sum ? (size_t)width * height * 3 * sizeof(float) : 0;
+    if (out_rgb_sum) CU(cudaMemcpyAsync(out_rgb_sum, s.out_dev, out_bytes, cudaMemcpyDeviceToHost, s.stream));
     return finish_render(s, s.stream, stats, out_bytes);
+}
+
+// ---------------------------------------------------------------------------
+// One host thread, N GPUs
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct RtSceneGroup {
+    std::vector<RtScene *> scenes;   // scenes[0] is the root
+    std::vector<cudaEvent_t> done;   // per scene: its image is complete (recorded on its stream)
+    std::vector<char> mapped;        // per scene: the root can read its memory directly (same device or peer access)
+    std::vector<float *> staging;    // per scene, on the root device: copy target when not mapped
+    size_t staging_bytes = 0;
+    cudaEvent_t g0 = nullptr, g1 = nullptr;  // on the root stream: begin of the call / image combined
+
+    ~RtSceneGroup() {
+        if (!scenes.empty() && scenes[0]) {
+            cudaSetDevice(scenes[0]->device);
+            for (float *p : staging)
+                if (p) cudaFree(p);
+            if (g0) cudaEventDestroy(g0);
+            if (g1) cudaEventDestroy(g1);
+        }
+        for (size_t i = 0; i < scenes.size(); ++i) {
+            if (i < done.size() && done[i] && scenes[i]) {
+                cudaSetDevice(scenes[i]->device);
+                cudaEventDestroy(done[i]);
+            }
+            delete scenes[i];
+        }
+    }
+};
+
+namespace {
+// Contiguous, balanced split of `count` samples over n devices (the first count % n get one more):
+// the same partition as raytracinginrust_b200/multi_gpu.py: sample_partition.
+void sample_block(uint32_t count, uint32_t i, uint32_t n, uint32_t *begin, uint32_t *len) {
+    const uint32_t base = count / n, extra = count % n;
+    *len = base + (i < extra ? 1u : 0u);
+    *begin = i * base + (i < extra ? i : extra);
+}
+}  // namespace
+
+extern "C" {
+
+RtStatus rt_scene_group_create(const RtSceneDesc *desc, const int *devices, uint32_t n_devices, RtSceneGroup **out_group) {
+    if (!desc || !out_group) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *out_group = nullptr;
+    CompiledScene cs;
+    std::string err;
+    RtStatus st = compile_scene(*desc, cs, err);  // once, whatever the number of GPUs
+    if (st != RT_OK) return fail(st, err);
+    const int visible = rt_device_count();
+    if (visible == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    if (n_devices == 0) {
+        if (devices) return fail(RT_ERR_BAD_ARGUMENT, "a device list with n_devices = 0");
+        n_devices = (uint32_t)visible;
+    }
+    if (n_devices > kMaxGroupDevices) return fail(RT_ERR_BAD_ARGUMENT, "at most 16 devices per group");
+    std::vector<int> dev(n_devices);
+    for (uint32_t i = 0; i < n_devices; ++i) {
+        dev[i] = devices ? devices[i] : (int)i;
+        if (dev[i] < 0 || dev[i] >= visible) return fail(RT_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    }
+    std::unique_ptr<RtSceneGroup> g(new RtSceneGroup());
+    g->scenes.assign(n_devices, nullptr);
+    g->done.assign(n_devices, nullptr);
+    g->mapped.assign(n_devices, 0);
+    g->staging.assign(n_devices, nullptr);
+    // context creation and the uploads run per device in parallel (a context alone is ~0.2 s)
+    std::vector<RtStatus> status(n_devices, RT_OK);
+    std::vector<std::string> message(n_devices);
+    {
+        std::vector<std::thread> workers;
+        for (uint32_t i = 0; i < n_devices; ++i)
+            workers.emplace_back([&, i]() {
+                status[i] = create_on_device(cs, dev[i], &g->scenes[i]);
+                if (status[i] == RT_OK && cudaEventCreateWithFlags(&g->done[i], cudaEventDisableTiming) != cudaSuccess) {
+                    status[i] = RT_ERR_CUDA;
+                    g_err = "cudaEventCreate";
+                }
+                if (status[i] != RT_OK) message[i] = g_err;
+            });
+        for (std::thread &w : workers) w.join();
+    }
+    for (uint32_t i = 0; i < n_devices; ++i)
+        if (status[i] != RT_OK) return fail(status[i], "device " + std::to_string(dev[i]) + ": " + message[i]);
+    // the root maps its peers (NVLink / NVSwitch on a B200 box)
+    CU(cudaSetDevice(dev[0]));
+    CU(cudaEventCreate(&g->g0));
+    CU(cudaEventCreate(&g->g1));
+    g->mapped[0] = 1;
+    for (uint32_t i = 1; i < n_devices; ++i) {
+        if (dev[i] == dev[0]) {
+            g->mapped[i] = 1;
+            continue;
+        }
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, dev[0], dev[i]) != cudaSuccess) can = 0;
+        if (can && !std::getenv("RTB200_NO_PEER")) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev[i], 0);
+            if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) g->mapped[i] = 1;
+        }
+        cudaGetLastError();
+    }
+    *out_group = g.release();
+    return RT_OK;
+}
+
+void rt_scene_group_destroy(RtSceneGroup *group) { delete group; }
+uint32_t rt_scene_group_size(const RtSceneGroup *group) { return group ? (uint32_t)group->scenes.size() : 0u; }
+const RtScene *rt_scene_group_scene(const RtSceneGroup *group, uint32_t i) {
+    return (group && i < group->scenes.size()) ? group->scenes[i] : nullptr;
+}
+
+RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint32_t width, uint32_t height, uint32_t spp,
+                         uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum, RtStats *stats) {
+    if (!group || !camera) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    RtSceneGroup &g = *const_cast<RtSceneGroup *>(group);
+    const double t0 = now_ms();
+    RtRenderOpts o{};
+    if (opts) o = *opts;
+    const uint32_t begin = o.sample_begin;
+    const uint32_t count = o.sample_count ? o.sample_count : (spp > begin ? spp - begin : 0);
+    if (count == 0) return fail(RT_ERR_BAD_ARGUMENT, "empty sample range");
+    const uint32_t n = (uint32_t)g.scenes.size();
+    RtScene &root = *g.scenes[0];
+    const size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
+    CU(cudaSetDevice(root.device));
+    CU(cudaEventRecord(g.g0, root.stream));
+    // every GPU gets its block; the calls only enqueue, so the GPUs run side by side
+    std::vector<uint32_t> active;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t b, len;
+        sample_block(count, i, n, &b, &len);
+        if (len == 0) continue;
+        RtRenderOpts oi = o;
+        oi.sample_begin = begin + b;
+        oi.sample_count = len;
+        RtScene &s = *g.scenes[i];
+        RtStatus st = start_render_own(s, *camera, width, height, spp, max_depth, &oi);
+        if (st == RT_OK && cudaEventRecord(g.done[i], s.stream) != cudaSuccess) st = fail(RT_ERR_CUDA, "cudaEventRecord");
+        if (st != RT_OK) {
+            for (uint32_t k : active) cudaStreamSynchronize(g.scenes[k]->stream);
+            return st;
+        }
+        active.push_back(i);
+    }
+    // combine on the root: one kernel, the peers' images read in place over NVLink
+    CU(cudaSetDevice(root.device));
+    PeerImages peers{};
+    for (uint32_t i : active) {
+        if (i == 0) continue;
+        RtScene &s = *g.scenes[i];
+        CU(cudaStreamWaitEvent(root.stream, g.done[i], 0));
+        const float *src = s.out_dev;
+        if (!g.mapped[i]) {  // no peer mapping between the two devices: stage the image on the root
+            if (g.staging_bytes < out_bytes) {
+                for (float *&p : g.staging) {
+                    if (p) cudaFree(p);
+                    p = nullptr;
+                }
+                g.staging_bytes = out_bytes;
+            }
+            if (!g.staging[i]) CU(cudaMalloc((void **)&g.staging[i], g.staging_bytes));
+            CU(cudaMemcpyPeerAsync(g.staging[i], root.device, s.out_dev, s.device, out_bytes, root.stream));
+            src = g.staging[i];
+        }
+        peers.image[peers.n++] = src;
+    }
+    CU(launch_sum_peers(root.out_dev, peers, (uint64_t)width * height * 3, root.sms, root.stream));
+    CU(cudaEventRecord(g.g1, root.stream));
+    if (out_rgb_sum) CU(cudaMemcpyAsync(out_rgb_sum, root.out_dev, out_bytes, cudaMemcpyDeviceToHost, root.stream));
+    RtStats total{};
+    for (size_t k = active.size(); k-- > 0;) {  // the root last: its stream ends with the combined image
+        RtScene &s = *g.scenes[active[k]];
+        CU(cudaSetDevice(s.device));
+        RtStats one{};
+        RtStatus st = finish_render(s, s.stream, &one, 0);
+        if (st != RT_OK) return st;
+        total.paths += one.paths;
+        total.rays += one.rays;
+        total.nonfinite_samples += one.nonfinite_samples;
+        total.kernel_launches += one.kernel_launches;
+        total.h2d_bytes += one.h2d_bytes;
+        total.d2h_bytes += one.d2h_bytes;
+    }
+    if (stats) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, g.g0, g.g1));
+        total.render_ms = ms;  // on the root's stream: first enqueue -> combined image
+        total.total_ms = now_ms() - t0;
+        total.kernel_launches += peers.n ? 1 : 0;
+        total.d2h_bytes += out_rgb_sum ? out_bytes : 0;
+        *stats = total;
+    }
+    root.render_info += " gpus=" + std::to_string(active.size());
+    return RT_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Output on the device
+// ---------------------------------------------------------------------------
+static RtStatus encode_source(RtScene &s, const float *rgb_sum_device, uint32_t width, uint32_t height,
+                              uint64_t samples_per_pixel, const float **src) {
+    if (width == 0 || height == 0 || samples_per_pixel == 0) return fail(RT_ERR_BAD_ARGUMENT, "zero size");
+    if ((uint64_t)width * height > (1ull << 31)) return fail(RT_ERR_BAD_ARGUMENT, "image too large");
+    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
+    if (rgb_sum_device) {
+        if ((uintptr_t)rgb_sum_device & 15u) return fail(RT_ERR_BAD_ARGUMENT, "rgb_sum_device must be 16-byte aligned");
+        *src = rgb_sum_device;
+    } else {
+        if (!s.out_dev || s.out_width != width || s.out_height != height)
+            return fail(RT_ERR_BAD_ARGUMENT, "no resident image of this size (call rt_render / rt_render_multi first)");
+        *src = s.out_dev;
+    }
+    return RT_OK;
+}
+
+RtStatus rt_encode_rgb8(const RtScene *scene, const float *rgb_sum_device, uint32_t width, uint32_t height,
+                        uint64_t samples_per_pixel, uint8_t *out_rgb8) {
+    if (!scene || !out_rgb8) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    RtScene &s = *const_cast<RtScene *>(scene);
+    const float *src = nullptr;
+    RtStatus st = encode_source(s, rgb_sum_device, width, height, samples_per_pixel, &src);
+    if (st != RT_OK) return st;
+    CU(cudaSetDevice(s.device));
+    const uint64_t n_values = (uint64_t)width * height * 3;
+    uint8_t *d = nullptr;
+    CU(cudaMalloc((void **)&d, n_values + 16));
+    cudaError_t e = launch_format_rgb8(src, d, n_values, (double)samples_per_pixel, s.sms, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb8, d, n_values, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_encode_rgb8");
+    return RT_OK;
+}
+
+RtStatus rt_encode_ppm(const RtScene *scene, const float *rgb_sum_device, uint32_t width, uint32_t height,
+                       uint64_t samples_per_pixel, char *out, uint64_t capacity, uint64_t *length) {
+    if (!scene || !out || !length) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *length = 0;
+    RtScene &s = *const_cast<RtScene *>(scene);
+    const float *src = nullptr;
+    RtStatus st = encode_source(s, rgb_sum_device, width, height, samples_per_pixel, &src);
+    if (st != RT_OK) return st;
+    char header[48];
+    const int hl = std::snprintf(header, sizeof(header), "P3\n%u %u\n255\n", width, height);  // main.rs:767-769
+    CU(cudaSetDevice(s.device));
+    const uint64_t n_pixels = (uint64_t)width * height;
+    const uint32_t nb = ppm_block_count(n_pixels);
+    // one allocation: body (12 B/pixel at most) | packed | block_off | total | block_len
+    const size_t body_bytes = (size_t)((n_pixels * 12 + 255) & ~255ull);
+    const size_t packed_bytes = (size_t)((n_pixels * 4 + 255) & ~255ull);
+    const size_t off_bytes = (size_t)(((uint64_t)nb * 8 + 255) & ~255ull);
+    const size_t len_bytes = (size_t)(((uint64_t)nb * 4 + 255) & ~255ull);
+    char *d = nullptr;
+    CU(cudaMalloc((void **)&d, body_bytes + packed_bytes + off_bytes + 256 + len_bytes));
+    char *body = d;
+    uint32_t *packed = (uint32_t *)(d + body_bytes);
+    uint64_t *block_off = (uint64_t *)(d + body_bytes + packed_bytes);
+    uint64_t *total_dev = (uint64_t *)(d + body_bytes + packed_bytes + off_bytes);
+    uint32_t *block_len = (uint32_t *)(d + body_bytes + packed_bytes + off_bytes + 256);
+    uint64_t total = 0;
+    cudaError_t e = launch_ppm_measure(src, packed, block_len, block_off, total_dev, n_pixels, (double)samples_per_pixel, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    if (e == cudaSuccess && (uint64_t)hl + total > capacity) {
+        cudaFree(d);
+        *length = (uint64_t)hl + total;  // what it would have taken
+        return fail(RT_ERR_BAD_ARGUMENT, "output buffer too small for the PPM (32 + 12*W*H always suffices)");
+    }
+    if (e == cudaSuccess) e = launch_ppm_write(packed, block_off, body, n_pixels, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out + hl, body, total, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "rt_encode_ppm");
+    std::memcpy(out, header, (size_t)hl);
+    *length = (uint64_t)hl + total;
+    return RT_OK;
 }
 
 RtStatus rt_trace_first_hit(const RtScene *scene, const RtRay *rays, uint64_t n, RtHit *hits) {

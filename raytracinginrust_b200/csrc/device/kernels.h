@@ -39,4 +39,19 @@ cudaError_t launch_path_radiance(const DScene &sc, const RtCamera &cam, const Re
 cudaError_t launch_camera_rays(const RtCamera &cam, const RenderParams &P, const uint32_t *px, const uint32_t *py,
                                const uint32_t *sample, uint64_t n, RtRay *rays, cudaStream_t stream);
 
+
+// ---- image.cu: multi-GPU combine, format_color, P3 text ----
+constexpr uint32_t kMaxGroupDevices = 16;
+struct PeerImages {
+    const float *image[kMaxGroupDevices - 1];  // W*H*3 fp32 sums on the peers (mapped into the root's address space)
+    uint32_t n;
+};
+cudaError_t launch_sum_peers(float *out, const PeerImages &peers, uint64_t n_values, int sms, cudaStream_t stream);
+cudaError_t launch_format_rgb8(const float *sum, uint8_t *out, uint64_t n_values, double spp, int sms, cudaStream_t stream);
+uint32_t ppm_block_count(uint64_t n_pixels);
+// packed: n_pixels u32; block_len / block_off: ppm_block_count(n_pixels) entries; total: the body's size in bytes
+cudaError_t launch_ppm_measure(const float *sum, uint32_t *packed, uint32_t *block_len, uint64_t *block_off, uint64_t *total,
+                               uint64_t n_pixels, double spp, cudaStream_t stream);
+cudaError_t launch_ppm_write(const uint32_t *packed, const uint64_t *block_off, char *body, uint64_t n_pixels, cudaStream_t stream);
+
 }  // namespace rtb200dev

@@ -96,6 +96,28 @@ int rth_render(const RthScene *s, uint32_t width, uint32_t height, uint32_t spp,
     }
 }
 
+// render() over n_gpus GPUs (0 = all) with the P3 file produced on the GPU: what the CLI writes to stdout.
+// out_ppm: host buffer of `capacity` bytes (32 + 12*W*H suffices); *length = file size.
+int rth_render_ppm(const RthScene *s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                   const RtRenderOpts *opts, uint32_t n_gpus, char *out_ppm, uint64_t capacity, uint64_t *length,
+                   RtStats *stats) {
+    try {
+        RenderResult r = render_ppm(s->spec.world, s->spec.lights, s->spec.background, s->spec.camera, width, height, spp,
+                                    max_depth, *opts, n_gpus);
+        if (r.ppm.size() > capacity) {
+            g_host_err = "output buffer too small";
+            return RT_ERR_BAD_ARGUMENT;
+        }
+        std::memcpy(out_ppm, r.ppm.data(), r.ppm.size());
+        *length = r.ppm.size();
+        if (stats) *stats = r.stats;
+        return RT_OK;
+    } catch (const std::exception &e) {
+        g_host_err = e.what();
+        return RT_ERR_INTERNAL;
+    }
+}
+
 // OBJ reader check (mesh.rs:40-52): number of triangles of the first model
 int rth_obj_triangle_count(const char *path, uint64_t *n_vertices, uint64_t *n_triangles) {
     try {

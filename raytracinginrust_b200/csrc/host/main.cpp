@@ -14,6 +14,8 @@ int main(int argc, char **argv) {
     std::string scene = "cornell", assets = "assets";
     uint32_t width = 0, height = 0, spp = 0, depth = 0, seed = 1, cseed = 1, detail = 0;
     int device = 0;
+    int gpus = -1;  // -1: one GPU (--device); 0: all GPUs of the box; N: the first N
+    bool host_ppm = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char * {
@@ -33,11 +35,13 @@ int main(int argc, char **argv) {
         else if (a == "--construction-seed") cseed = (uint32_t)std::atoi(next());
         else if (a == "--mesh-detail") detail = (uint32_t)std::atoi(next());
         else if (a == "--device") device = std::atoi(next());
+        else if (a == "--gpus") gpus = std::atoi(next());
+        else if (a == "--host-ppm") host_ppm = true;
         else {
             std::fprintf(stderr,
                          "usage: %s [--scene random|cornell|cornell_smoke|final|mesh|light_room|two_spheres] [--width W] "
                          "[--height H] [--spp N] [--depth D] [--seed S] [--construction-seed S] [--assets DIR] "
-                         "[--mesh-detail K] [--device I] > image.ppm\n",
+                         "[--mesh-detail K] [--device I | --gpus N (0 = all)] [--host-ppm] > image.ppm\n",
                          argv[0]);
             return 2;
         }
@@ -51,8 +55,20 @@ int main(int argc, char **argv) {
         RtRenderOpts opts{};
         opts.seed = seed;
         opts.integrator = spec.integrator;
-        RenderResult r = render(spec.world, spec.lights, spec.background, spec.camera, width, height, spp, depth, opts, device);
-        write_ppm(stdout, r.rgb_sum.data(), width, height, spp);
+        RenderResult r;
+        if (host_ppm) {  // the reference's way: fp32 sums to the host, format_color + one line per pixel there
+            r = gpus < 0 ? render(spec.world, spec.lights, spec.background, spec.camera, width, height, spp, depth, opts, device)
+                         : render_gpus(spec.world, spec.lights, spec.background, spec.camera, width, height, spp, depth, opts, (uint32_t)gpus);
+            write_ppm(stdout, r.rgb_sum.data(), width, height, spp);
+        } else {  // default: the P3 text is produced on the GPU
+            if (gpus < 0 && device != 0) {
+                std::fprintf(stderr, "--device needs --host-ppm (the multi-GPU entry takes the first N devices)\n");
+                return 2;
+            }
+            r = render_ppm(spec.world, spec.lights, spec.background, spec.camera, width, height, spp, depth, opts,
+                           gpus < 0 ? 1u : (uint32_t)gpus);
+            std::fwrite(r.ppm.data(), 1, r.ppm.size(), stdout);
+        }
         std::fprintf(stderr, "Done. %llu paths, %llu rays, %.1f ms on device (%.1f Mpaths/s, %.1f Mrays/s), %llu non-finite samples\n",
                      (unsigned long long)r.stats.paths, (unsigned long long)r.stats.rays, r.stats.render_ms,
                      r.stats.paths / r.stats.render_ms / 1e3, r.stats.rays / r.stats.render_ms / 1e3,

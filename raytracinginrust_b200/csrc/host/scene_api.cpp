@@ -442,4 +442,44 @@ RenderResult render(const HittablePtr &world, const std::shared_ptr<const Hittab
     return out;
 }
 
+namespace {
+RenderResult render_group(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights, Color background,
+                          const Camera &camera, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                          const RtRenderOpts &opts, uint32_t n_gpus, bool want_sums, bool want_ppm) {
+    FlatScene flat(world, lights, background);
+    RtSceneGroup *group = nullptr;
+    if (rt_scene_group_create(&flat.desc, nullptr, n_gpus, &group) != RT_OK)
+        throw std::runtime_error(std::string("rt_scene_group_create: ") + rt_last_error());
+    RenderResult out;
+    if (want_sums) out.rgb_sum.resize((size_t)width * height * 3);
+    RtStatus st = rt_render_multi(group, &camera.pod, width, height, spp, max_depth, &opts,
+                                  want_sums ? out.rgb_sum.data() : nullptr, &out.stats);
+    std::string err = st == RT_OK ? "" : std::string("rt_render_multi: ") + rt_last_error();
+    if (st == RT_OK && want_ppm) {
+        // the sample range the image holds (RtRenderOpts: 0 = all of spp)
+        const uint64_t n_samples = opts.sample_count ? opts.sample_count : (spp > opts.sample_begin ? spp - opts.sample_begin : 0);
+        out.ppm.resize(32 + 12 * (size_t)width * height);
+        uint64_t len = 0;
+        st = rt_encode_ppm(rt_scene_group_scene(group, 0), nullptr, width, height, n_samples, &out.ppm[0], out.ppm.size(), &len);
+        if (st != RT_OK) err = std::string("rt_encode_ppm: ") + rt_last_error();
+        out.ppm.resize(st == RT_OK ? (size_t)len : 0);
+    }
+    rt_scene_group_destroy(group);
+    if (st != RT_OK) throw std::runtime_error(err);
+    return out;
+}
+}  // namespace
+
+RenderResult render_gpus(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights, Color background,
+                         const Camera &camera, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                         const RtRenderOpts &opts, uint32_t n_gpus) {
+    return render_group(world, lights, background, camera, width, height, spp, max_depth, opts, n_gpus, true, false);
+}
+
+RenderResult render_ppm(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights, Color background,
+                        const Camera &camera, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                        const RtRenderOpts &opts, uint32_t n_gpus) {
+    return render_group(world, lights, background, camera, width, height, spp, max_depth, opts, n_gpus, false, true);
+}
+
 }  // namespace rtb200

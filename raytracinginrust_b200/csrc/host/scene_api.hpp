@@ -322,7 +322,8 @@ struct FlatScene {
 
 // ---- render(): the function BASELINE's north star introduces ------------------------
 struct RenderResult {
-    std::vector<float> rgb_sum;  // W*H*3, rows top-down
+    std::vector<float> rgb_sum;  // W*H*3, rows top-down (empty when only the PPM was asked for)
+    std::string ppm;             // the P3 file, formatted on the GPU (render_ppm only)
     RtStats stats;
 };
 // Replaces the loop at src/main.rs:772-834.  `lights` and `background` are inputs of
@@ -331,6 +332,16 @@ struct RenderResult {
 RenderResult render(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights,
                     Color background, const Camera &camera, uint32_t width, uint32_t height,
                     uint32_t spp, uint32_t max_depth, const RtRenderOpts &opts, int device = 0);
+// The same over `n_gpus` GPUs of the box (0 = all): one host thread, contiguous sample blocks per GPU,
+// one combine kernel over NVLink peer memory (rt_scene_group_create / rt_render_multi).
+RenderResult render_gpus(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights,
+                         Color background, const Camera &camera, uint32_t width, uint32_t height,
+                         uint32_t spp, uint32_t max_depth, const RtRenderOpts &opts, uint32_t n_gpus);
+// render_gpus + format_color + the P3 text of src/main.rs:767-769,832 on the GPU: what `cargo run
+// --release > image.ppm` prints, ready for one fwrite.  The fp32 sums do not come back to the host.
+RenderResult render_ppm(const HittablePtr &world, const std::shared_ptr<const HittableList> &lights,
+                        Color background, const Camera &camera, uint32_t width, uint32_t height,
+                        uint32_t spp, uint32_t max_depth, const RtRenderOpts &opts, uint32_t n_gpus);
 
 // Vec3::format_color (src/vec.rs:125-131) on a sum of `samples_per_pixel` samples.
 void format_color(const float sum[3], uint64_t samples_per_pixel, uint64_t out[3]);

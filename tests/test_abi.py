@@ -125,3 +125,26 @@ def test_product_does_not_reference_the_oracle():
                 assert "oracle_" not in text, path
             elif f == "Makefile":
                 assert "oracle" not in open(path).read(), path
+
+
+def test_group_and_encode_argument_checks(rt):
+    """The multi-GPU and output entry points validate without a GPU and never compute on the CPU."""
+    b, s, light = _simple(rt)
+    sd = b.finish(b.list([s, light]), b.list([light]))
+    h = C.c_void_p()
+    assert rt._dev.rt_scene_group_create(None, None, 0, C.byref(h)) == rt._abi.RT_ERR_BAD_ARGUMENT
+    st = rt._dev.rt_scene_group_create(sd.ptr, None, 2, C.byref(h))
+    if rt.device_count() == 0:
+        assert st == rt._abi.RT_ERR_CUDA and "no CPU path" in rt._dev.rt_last_error().decode()
+        assert not h.value
+    elif st == 0:
+        rt._dev.rt_scene_group_destroy(h)
+    assert rt._dev.rt_scene_group_size(None) == 0 and not rt._dev.rt_scene_group_scene(None, 0)
+    assert rt._dev.rt_render_multi(None, None, 4, 4, 1, 1, None, None, None) == rt._abi.RT_ERR_BAD_ARGUMENT
+    n = C.c_uint64()
+    assert rt._dev.rt_encode_rgb8(None, None, 4, 4, 1, None) == rt._abi.RT_ERR_BAD_ARGUMENT
+    assert rt._dev.rt_encode_ppm(None, None, 4, 4, 1, None, 0, C.byref(n)) == rt._abi.RT_ERR_BAD_ARGUMENT
+    # a malformed graph is reported by the group entry exactly like rt_scene_create
+    b2 = rt.SceneBuilder()
+    sd2 = b2.finish(0, 0)
+    assert rt._dev.rt_scene_group_create(sd2.ptr, None, 1, C.byref(h)) == _status(rt, sd2)[0]
