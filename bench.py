@@ -290,6 +290,22 @@ def main():
             e2e_ms.append(float(tt.item()))
     e2e_value = (W * H * spp) / (sum(e2e_ms) / len(e2e_ms) * 1e-3) / 1e6
 
+    # ---- the whole `cargo run --release > image.ppm` job at N=1: scene graph -> flatten -> compile/upload ->
+    # render -> format_color + P3 text on the GPU -> the file's bytes in host memory (rtb200_render's path) ----
+    e2e_ppm = None
+    if world == 1:
+        ppm_ms, ppm_len = [], 0
+        for it in range(2):
+            t0 = time.perf_counter()
+            ppm, _ = hs.render_ppm(W, H, spp, depth, opts, n_gpus=1)
+            if it > 0:
+                ppm_ms.append((time.perf_counter() - t0) * 1e3)
+            ppm_len = len(ppm)
+        e2e_ppm = {"value": (W * H * spp) / (ppm_ms[0] * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_step": ppm_ms[0],
+                   "d2h_bytes_per_step": ppm_len,
+                   "what": "host scene graph -> flatten -> rt_scene_group_create -> rt_render_multi -> rt_encode_ppm "
+                           "(format_color + P3 text on the GPU) -> the PPM file in host memory"}
+
     if rank != 0:
         if dist is not None:
             dist.barrier()
@@ -359,6 +375,7 @@ def main():
                 "ms_per_step": sum(e2e_ms) / len(e2e_ms),
                 "what": "RtSceneDesc in host memory -> rt_scene_create (compile, BVH build, upload) -> render -> "
                         "fp32 sums copied to pinned host memory"},
+        "e2e_ppm": e2e_ppm,
         "gpu_launches": int(launches),  # this rank's render + reduce kernels inside the timed steps (RtStats.kernel_launches)
         "roofline": roofline, "roofline_fp64": roofline64, "cpu_baseline": cpu,
         "algorithmic_tests_per_segment": per_seg, "checksum": checksum,
