@@ -34,16 +34,19 @@ struct Box {
             hi[a] = -DBL_MAX;
         }
     }
+    // plain comparisons (minsd / maxsd), not fmin / fmax: at -O2 those are libm calls, and the builder
+    // makes ~10^8 of them.  A NaN operand is ignored like fmin would (the comparison is false), and
+    // finalize_groups rejects non-finite bounds before any tree is built.
     void grow(const Box &b) {
         for (int a = 0; a < 3; ++a) {
-            lo[a] = std::fmin(lo[a], b.lo[a]);
-            hi[a] = std::fmax(hi[a], b.hi[a]);
+            lo[a] = b.lo[a] < lo[a] ? b.lo[a] : lo[a];
+            hi[a] = b.hi[a] > hi[a] ? b.hi[a] : hi[a];
         }
     }
     void grow(const double p[3]) {
         for (int a = 0; a < 3; ++a) {
-            lo[a] = std::fmin(lo[a], p[a]);
-            hi[a] = std::fmax(hi[a], p[a]);
+            lo[a] = p[a] < lo[a] ? p[a] : lo[a];
+            hi[a] = p[a] > hi[a] ? p[a] : hi[a];
         }
     }
     double area() const {
@@ -207,40 +210,48 @@ struct Builder {
         uint32_t mid = first + count / 2;
         bool done = false;
         if ((int)depth < FORCE_MEDIAN_DEPTH && ext[axis] > 0.0) {
-            // binned SAH over all three axes
+            // binned SAH over all three axes; one pass over the primitives fills the bins of every axis
             double best_cost = DBL_MAX;
             int best_axis = -1, best_bin = -1;
+            Box bb[3][N_BINS];
+            uint32_t bn[3][N_BINS];
+            double scale3[3];
+            for (int ax = 0; ax < 3; ++ax) {
+                scale3[ax] = ext[ax] > 0.0 ? (double)N_BINS / ext[ax] : 0.0;
+                for (int k = 0; k < N_BINS; ++k) {
+                    bb[ax][k].reset();
+                    bn[ax][k] = 0;
+                }
+            }
+            for (uint32_t i = first; i < first + count; ++i) {
+                const uint32_t p = order[i];
+                const Box &pb = boxes[p];
+                for (int ax = 0; ax < 3; ++ax) {
+                    if (!(ext[ax] > 0.0)) continue;
+                    int k = (int)((cx[ax][p] - cbox.lo[ax]) * scale3[ax]);
+                    k = std::min(std::max(k, 0), N_BINS - 1);
+                    bb[ax][k].grow(pb);
+                    bn[ax][k]++;
+                }
+            }
             for (int ax = 0; ax < 3; ++ax) {
                 if (!(ext[ax] > 0.0)) continue;
-                Box bb[N_BINS];
-                uint32_t bn[N_BINS];
-                for (int k = 0; k < N_BINS; ++k) {
-                    bb[k].reset();
-                    bn[k] = 0;
-                }
-                double scale = (double)N_BINS / ext[ax];
-                for (uint32_t i = first; i < first + count; ++i) {
-                    int k = (int)((cx[ax][order[i]] - cbox.lo[ax]) * scale);
-                    k = std::min(std::max(k, 0), N_BINS - 1);
-                    bb[k].grow(boxes[order[i]]);
-                    bn[k]++;
-                }
                 double right_area[N_BINS];
                 uint32_t right_n[N_BINS];
                 Box acc;
                 acc.reset();
                 uint32_t n = 0;
                 for (int k = N_BINS - 1; k > 0; --k) {
-                    if (bn[k]) acc.grow(bb[k]);
-                    n += bn[k];
+                    if (bn[ax][k]) acc.grow(bb[ax][k]);
+                    n += bn[ax][k];
                     right_area[k] = n ? acc.area() : 0.0;
                     right_n[k] = n;
                 }
                 acc.reset();
                 n = 0;
                 for (int k = 0; k < N_BINS - 1; ++k) {
-                    if (bn[k]) acc.grow(bb[k]);
-                    n += bn[k];
+                    if (bn[ax][k]) acc.grow(bb[ax][k]);
+                    n += bn[ax][k];
                     if (n == 0 || right_n[k + 1] == 0) continue;
                     double cost = acc.area() * (double)n + right_area[k + 1] * (double)right_n[k + 1];
                     if (cost < best_cost) {
@@ -297,6 +308,8 @@ float f32_up(double x) {
 // Builds the BVH of prims[first, first+count) (reordering them) and appends the
 // nodes, breadth-first, to out.nodes.  Returns the root node index.
 int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING") && count > 10000) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[bvh %u] %s %.3f s\n", count, what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     std::vector<Box> boxes(count);
     for (uint32_t i = 0; i < count; ++i) {
         boxes[i] = prim_box(out.prims[first + i]);
@@ -304,15 +317,19 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     }
     std::vector<uint32_t> order(count);
     for (uint32_t i = 0; i < count; ++i) order[i] = i;
+    lap("boxes");
     Builder b(boxes, order);
     b.nodes.resize(2 * (size_t)count);
+    lap("builder init");
     int root = b.build(0, count, 1);
+    lap("build");
     b.nodes.resize((size_t)b.next.load());
     out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth.load());
     // permute the primitives into leaf order
     std::vector<DPrim> tmp(count);
     for (uint32_t i = 0; i < count; ++i) tmp[i] = out.prims[first + order[i]];
     std::copy(tmp.begin(), tmp.end(), out.prims.begin() + first);
+    lap("permute");
     // breadth-first emission of the inner nodes
     uint32_t base = (uint32_t)out.nodes.size();
     std::vector<int> bfs;  // temp-node ids of inner nodes in BFS order
@@ -349,6 +366,7 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
         dn.child1 = encode(n.right);
         dn.pad0 = dn.pad1 = 0;
     }
+    lap("emit");
     return (int32_t)base;
 }
 

@@ -44,13 +44,6 @@ constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
 constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
 constexpr uint32_t kMediumFlag = 0x80000000u;
 constexpr int kStackSize = 64;
-// The short stack of the BVH traversal: its first RT_SMEM_STACK entries live in shared memory (one
-// column per thread, so a warp's accesses never conflict), deeper ones in local memory.  0: all local.
-#ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 0
-#endif
-constexpr int kSmemStack = RT_SMEM_STACK;
-constexpr int kStackThreads = 128;  // every kernel that traverses runs 128-thread blocks
 #define RT_INF (__longlong_as_double(0x7FF0000000000000ll))
 
 // ---------------------------------------------------------------------------
@@ -381,27 +374,7 @@ RT_DEV bool slab2f(const FRay &f, float lx, float ly, float lz, float hx, float 
 // leaves are tested together, which keeps the warp together in both phases.
 RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double t_min, Best &best) {
     const int kDone = (int)0x80000000;
-#if RT_SMEM_STACK > 0
-    __shared__ int s_stack[kSmemStack * kStackThreads];
-    int *ss = s_stack + threadIdx.x;
-    int deep[kStackSize - kSmemStack];
-    auto push = [&](int &sp, int v) {
-        if (sp < kSmemStack) ss[sp * kStackThreads] = v;
-        else if (sp < kStackSize) deep[sp - kSmemStack] = v;
-        else return;
-        ++sp;
-    };
-    auto pop = [&](int &sp) -> int {
-        --sp;
-        return sp < kSmemStack ? ss[sp * kStackThreads] : deep[sp - kSmemStack];
-    };
-#else
     int stack[kStackSize];
-    auto push = [&](int &sp, int v) {
-        if (sp < kStackSize) stack[sp++] = v;
-    };
-    auto pop = [&](int &sp) -> int { return stack[--sp]; };
-#endif
     int sp = 0;
     int node = g.bvh_root;
     FRay f;
@@ -423,14 +396,14 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double
             if (h0 && h1) {
                 bool swap = e1 < e0;
                 int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
-                push(sp, far_c);
+                if (sp < kStackSize) stack[sp++] = far_c;
                 node = near_c;
             } else if (h0) {
                 node = ch.x;
             } else if (h1) {
                 node = ch.y;
             } else {
-                node = sp ? pop(sp) : kDone;
+                node = sp ? stack[--sp] : kDone;
             }
         }
         if (node != kDone) {
@@ -439,7 +412,7 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double
             double before = best.t;
             for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, best);
             if (best.t != before) t_max_f = __double2float_ru(best.t);
-            node = sp ? pop(sp) : kDone;
+            node = sp ? stack[--sp] : kDone;
         }
     }
 }
