@@ -481,23 +481,30 @@ bool ref_bbox(const RtSceneDesc &d, uint32_t id, double t0, double t1, RefBox &o
 // order it arrives at only depends on the boxes, so they are computed once, the recursion sorts
 // index ranges in place, and the two halves of a large node are ordered in parallel.
 struct RefOrder {
-    const std::vector<uint32_t> &hit;
+    struct Item {
+        double key;    // lo + hi on the split axis of the node being sorted (bvh.rs:23-25)
+        uint32_t idx;  // index into hit / boxes
+    };
     const std::vector<RefBox> &boxes;
-    std::vector<uint32_t> idx;   // permutation of [0, n), sorted range by range
-    std::vector<uint32_t> &out;  // out[k] = hit[idx[k]] once the recursion is done
-    std::atomic<int> bad{0};     // 1: NaN extent, 2: NaN centroid
+    std::vector<Item> items;  // permutation of [0, n), sorted range by range
+    std::atomic<int> bad{0};  // 1: NaN extent, 2: NaN centroid
 
     void rec(size_t first, size_t n, int depth) {
         if (n <= 1 || bad.load(std::memory_order_relaxed)) return;
+        // bvh.rs:33-48; plain comparisons instead of fmin / fmax (libm calls at -O2): a NaN bound is
+        // skipped either way, and a NaN key is caught below
+        double bmin[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, bmax[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+        for (size_t i = first; i < first + n; ++i) {
+            const RefBox &b = boxes[items[i].idx];
+            for (int a = 0; a < 3; ++a) {
+                bmin[a] = b.lo[a] < bmin[a] ? b.lo[a] : bmin[a];
+                bmax[a] = b.hi[a] > bmax[a] ? b.hi[a] : bmax[a];
+            }
+        }
         int axis = 0;
         double range[3];
-        for (int a = 0; a < 3; ++a) {  // bvh.rs:33-48
-            double bmin = DBL_MAX, bmax = -DBL_MAX;
-            for (size_t i = first; i < first + n; ++i) {
-                bmin = std::fmin(bmin, boxes[idx[i]].lo[a]);
-                bmax = std::fmax(bmax, boxes[idx[i]].hi[a]);
-            }
-            range[a] = bmax - bmin;
+        for (int a = 0; a < 3; ++a) {
+            range[a] = bmax[a] - bmin[a];
             if (range[a] != range[a]) {  // partial_cmp().unwrap(), bvh.rs:47
                 bad.store(1);
                 return;
@@ -506,17 +513,17 @@ struct RefOrder {
         if (range[1] > range[axis]) axis = 1;
         if (range[2] > range[axis]) axis = 2;
         for (size_t i = first; i < first + n; ++i) {
-            const RefBox &b = boxes[idx[i]];
-            if (b.lo[axis] + b.hi[axis] != b.lo[axis] + b.hi[axis]) {  // partial_cmp().unwrap(), bvh.rs:26
+            const RefBox &b = boxes[items[i].idx];
+            const double key = b.lo[axis] + b.hi[axis];
+            if (key != key) {  // partial_cmp().unwrap(), bvh.rs:26
                 bad.store(2);
                 return;
             }
+            items[i].key = key;
         }
         // bvh.rs:51 sort_unstable_by: the order of equal keys is unspecified in the reference;
         // a stable sort fixes it (same choice as the oracle)
-        std::stable_sort(idx.begin() + first, idx.begin() + first + n, [&](uint32_t x, uint32_t y) {
-            return boxes[x].lo[axis] + boxes[x].hi[axis] < boxes[y].lo[axis] + boxes[y].hi[axis];
-        });
+        std::stable_sort(items.begin() + first, items.begin() + first + n, [](const Item &x, const Item &y) { return x.key < y.key; });
         const size_t half = n / 2;
         if (n >= 16384 && depth < 5) {
             auto left = std::async(std::launch::async, [&] { rec(first, half, depth + 1); });
@@ -541,14 +548,15 @@ bool ref_bvh_order(const RtSceneDesc &d, const std::vector<uint32_t> &hit, doubl
             err = "no bounding box in bvh node";  // bvh.rs:28,61
             return false;
         }
-    RefOrder ro{hit, boxes, std::vector<uint32_t>(hit.size()), out};
-    for (size_t i = 0; i < hit.size(); ++i) ro.idx[i] = (uint32_t)i;
+    RefOrder ro{boxes, std::vector<RefOrder::Item>(hit.size())};
+    for (size_t i = 0; i < hit.size(); ++i) ro.items[i] = RefOrder::Item{0.0, (uint32_t)i};
     ro.rec(0, hit.size(), 0);
     if (ro.bad.load()) {
         err = ro.bad.load() == 1 ? "NaN extent in BVH build" : "NaN centroid in BVH build";
         return false;
     }
-    for (size_t i = 0; i < hit.size(); ++i) out.push_back(hit[ro.idx[i]]);
+    out.reserve(out.size() + hit.size());
+    for (size_t i = 0; i < hit.size(); ++i) out.push_back(hit[ro.items[i].idx]);
     return true;
 }
 
@@ -591,8 +599,22 @@ struct Walker {
         if (m >= d.n_materials) return fail(RT_ERR_BAD_ARGUMENT, "material index out of range");
         return true;
     }
+    // The wrapper stack only changes between siblings of a wrapper node; a mesh emits hundreds of
+    // thousands of primitives under one stack, so the (chain, group) lookup is cached per stack state.
+    size_t cached_depth = (size_t)-1;
+    const void *cached_groups = nullptr;
+    uint32_t cached_chain = 0;
+    size_t cached_group = 0;
     void emit(DPrim p, uint32_t node_id) {
-        p.chain = intern_chain(stack);
+        if (!(cache_valid && cached_depth == stack.size() && cached_groups == (const void *)groups)) {
+            cached_chain = intern_chain(stack);
+            GroupBuild &g = group_for_stack();
+            cached_group = (size_t)(&g - groups->data());
+            cached_depth = stack.size();
+            cached_groups = (const void *)groups;
+            cache_valid = true;
+        }
+        p.chain = cached_chain;
         p.node = (int32_t)node_id;
         p.rank = rank++;
         p.pad0 = p.pad1 = 0;
@@ -601,8 +623,9 @@ struct Walker {
                 fail(RT_ERR_BAD_ARGUMENT, "NaN primitive parameter");
                 return;
             }
-        group_for_stack().prims.push_back(p);
+        (*groups)[cached_group].prims.push_back(p);
     }
+    bool cache_valid = false;
     bool walk(uint32_t id, uint32_t depth) {
         if (status != RT_OK) return false;
         if (id >= d.n_nodes) return fail(RT_ERR_BAD_ARGUMENT, "node index out of range");
@@ -682,8 +705,10 @@ struct Walker {
                 op.kind = OP_TRANSLATE;
                 for (int a = 0; a < 3; ++a) op.offset[a] = n.v[a];
                 stack.push_back(op);
+                cache_valid = false;
                 bool ok = walk(n.child, depth + 1);
                 stack.pop_back();
+                cache_valid = false;
                 if (!ok) return false;
                 break;
             }
@@ -697,8 +722,10 @@ struct Walker {
                 op.sin_theta = std::sin(radiants);
                 op.cos_theta = std::cos(radiants);
                 stack.push_back(op);
+                cache_valid = false;
                 bool ok = walk(n.child, depth + 1);
                 stack.pop_back();
+                cache_valid = false;
                 if (!ok) return false;
                 break;
             }
@@ -707,8 +734,10 @@ struct Walker {
                 std::memset(&op, 0, sizeof(op));
                 op.kind = OP_FLIP;
                 stack.push_back(op);
+                cache_valid = false;
                 bool ok = walk(n.child, depth + 1);
                 stack.pop_back();
+                cache_valid = false;
                 if (!ok) return false;
                 break;
             }
@@ -916,6 +945,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     std::vector<PendingMedium> pending;
     w.groups = &world_groups;
     w.media = &pending;
+    w.cache_valid = false;
     if (!w.walk(d.world, 0)) return w.status;
     lap("walk");
     if (!finalize_groups(out, world_groups, err)) return RT_ERR_BAD_ARGUMENT;
@@ -932,6 +962,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         w.groups = &bgroups;
         w.media = nullptr;
         w.stack = pm.stack;
+        w.cache_valid = false;
         if (!w.walk(n.child, 0)) return w.status;
         DMedium dm;
         std::memset(&dm, 0, sizeof(dm));
