@@ -390,25 +390,40 @@ RtStatus finish_render(RtScene &s, cudaStream_t st, RtStats *stats, uint64_t d2h
     return RT_OK;
 }
 
-// rt_render's first half: parameters, scratch, kernels enqueued on the scene's own stream into its own
-// resident image (s.out_dev).  rt_render_multi runs this once per GPU.
-RtStatus start_render_own(RtScene &s, const RtCamera &camera, uint32_t width, uint32_t height, uint32_t spp,
-                          uint32_t max_depth, const RtRenderOpts *opts) {
+// rt_render's first half in two steps.  prepare: parameters and scratch memory (may allocate or free, which
+// can synchronise with other devices of the process when peer mappings exist); launch: the kernels, enqueued
+// on the scene's own stream into its own resident image (s.out_dev).  rt_render_multi prepares every GPU
+// before it launches on any, so that no allocation falls between two launches.
+struct PreparedRender {
+    RenderParams P;
+    bool wavefront = false;
+};
+RtStatus prepare_render_own(RtScene &s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                            const RtRenderOpts *opts, PreparedRender &pr) {
+    CU(cudaSetDevice(s.device));
+    pr.wavefront = use_wavefront(s, opts, max_depth);
+    RtStatus st = make_params(s, width, height, spp, max_depth, opts, pr.P);
+    if (st != RT_OK) return st;
+    st = ensure_scratch(s, pr.P, true);
+    if (st == RT_OK && pr.wavefront) st = ensure_wavefront_pool(s, pr.P);
+    return st;
+}
+RtStatus launch_render_own(RtScene &s, const RtCamera &camera, const PreparedRender &pr) {
     s.t_call0 = now_ms();
     CU(cudaSetDevice(s.device));
-    RenderParams P;
-    const bool wavefront = use_wavefront(s, opts, max_depth);
-    RtStatus st = make_params(s, width, height, spp, max_depth, opts, P);
-    if (st != RT_OK) return st;
-    st = ensure_scratch(s, P, true);
-    if (st == RT_OK && wavefront) st = ensure_wavefront_pool(s, P);
-    if (st != RT_OK) return st;
     s.out_width = s.out_height = 0;
-    st = enqueue_render(s, camera, P, wavefront, s.out_dev, s.stream);
+    RtStatus st = enqueue_render(s, camera, pr.P, pr.wavefront, s.out_dev, s.stream);
     if (st != RT_OK) return st;
-    s.out_width = width;
-    s.out_height = height;
+    s.out_width = pr.P.width;
+    s.out_height = pr.P.height;
     return RT_OK;
+}
+RtStatus start_render_own(RtScene &s, const RtCamera &camera, uint32_t width, uint32_t height, uint32_t spp,
+                          uint32_t max_depth, const RtRenderOpts *opts) {
+    PreparedRender pr;
+    RtStatus st = prepare_render_own(s, width, height, spp, max_depth, opts, pr);
+    if (st != RT_OK) return st;
+    return launch_render_own(s, camera, pr);
 }
 
 // Upload a compiled scene to one device (the second half of rt_scene_create; a scene group compiles
@@ -677,10 +692,11 @@ RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint
     const uint32_t n = (uint32_t)g.scenes.size();
     RtScene &root = *g.scenes[0];
     const size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
-    CU(cudaSetDevice(root.device));
-    CU(cudaEventRecord(g.g0, root.stream));
-    // every GPU gets its block; the calls only enqueue, so the GPUs run side by side
+    // every GPU gets its block.  First all parameters and scratch memory, then the launches: those only
+    // enqueue, so the GPUs run side by side
+    const bool timing = std::getenv("RTB200_MULTI_TIMING") != nullptr;
     std::vector<uint32_t> active;
+    std::vector<PreparedRender> prepared;
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t b, len;
         sample_block(count, i, n, &b, &len);
@@ -688,14 +704,35 @@ RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint
         RtRenderOpts oi = o;
         oi.sample_begin = begin + b;
         oi.sample_count = len;
-        RtScene &s = *g.scenes[i];
-        RtStatus st = start_render_own(s, *camera, width, height, spp, max_depth, &oi);
-        if (st == RT_OK && cudaEventRecord(g.done[i], s.stream) != cudaSuccess) st = fail(RT_ERR_CUDA, "cudaEventRecord");
+        PreparedRender pr;
+        RtStatus st = prepare_render_own(*g.scenes[i], width, height, spp, max_depth, &oi, pr);
+        if (st != RT_OK) return st;
+        active.push_back(i);
+        prepared.push_back(pr);
+    }
+    CU(cudaSetDevice(root.device));
+    for (uint32_t i : active) {  // staging buffers on the root for peers it cannot map
+        if (g.mapped[i]) continue;
+        if (g.staging_bytes < out_bytes) {
+            for (float *&p : g.staging) {
+                if (p) cudaFree(p);
+                p = nullptr;
+            }
+            g.staging_bytes = out_bytes;
+        }
+        if (!g.staging[i]) CU(cudaMalloc((void **)&g.staging[i], g.staging_bytes));
+    }
+    if (timing) std::fprintf(stderr, "[multi] prepared %zu devices at %.3f ms\n", active.size(), now_ms() - t0);
+    CU(cudaEventRecord(g.g0, root.stream));
+    for (size_t k = 0; k < active.size(); ++k) {
+        RtScene &s = *g.scenes[active[k]];
+        RtStatus st = launch_render_own(s, *camera, prepared[k]);
+        if (st == RT_OK && cudaEventRecord(g.done[active[k]], s.stream) != cudaSuccess) st = fail(RT_ERR_CUDA, "cudaEventRecord");
         if (st != RT_OK) {
-            for (uint32_t k : active) cudaStreamSynchronize(g.scenes[k]->stream);
+            for (size_t j = 0; j <= k; ++j) cudaStreamSynchronize(g.scenes[active[j]]->stream);
             return st;
         }
-        active.push_back(i);
+        if (timing) std::fprintf(stderr, "[multi] device %d enqueued at %.3f ms\n", s.device, now_ms() - t0);
     }
     // combine on the root: one kernel, the peers' images read in place over NVLink
     CU(cudaSetDevice(root.device));
@@ -706,14 +743,6 @@ RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint
         CU(cudaStreamWaitEvent(root.stream, g.done[i], 0));
         const float *src = s.out_dev;
         if (!g.mapped[i]) {  // no peer mapping between the two devices: stage the image on the root
-            if (g.staging_bytes < out_bytes) {
-                for (float *&p : g.staging) {
-                    if (p) cudaFree(p);
-                    p = nullptr;
-                }
-                g.staging_bytes = out_bytes;
-            }
-            if (!g.staging[i]) CU(cudaMalloc((void **)&g.staging[i], g.staging_bytes));
             CU(cudaMemcpyPeerAsync(g.staging[i], root.device, s.out_dev, s.device, out_bytes, root.stream));
             src = g.staging[i];
         }
@@ -729,6 +758,8 @@ RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint
         RtStats one{};
         RtStatus st = finish_render(s, s.stream, &one, 0);
         if (st != RT_OK) return st;
+        if (timing) std::fprintf(stderr, "[multi] device %d: %.3f ms on device, %llu paths, done at %.3f ms\n", s.device, one.render_ms,
+                                 (unsigned long long)one.paths, now_ms() - t0);
         total.paths += one.paths;
         total.rays += one.rays;
         total.nonfinite_samples += one.nonfinite_samples;

@@ -30,10 +30,17 @@ for name, spp in cases:
     root.render(hs.camera, W, H, max(spp // 8, 1), depth, opts, want_sums=False)
     one, s1 = root.render(hs.camera, W, H, spp, depth, opts)
     rel = float(np.abs(img - one).max() / max(1.0, float(np.abs(one).max())))
+    last = None
+    if n > 1:  # the last GPU on its own, half the samples: is it as fast as the root?
+        peer = group.scene(n - 1)
+        half = rt.render_opts(seed=1, integrator=hs.integrator, sample_begin=0, sample_count=max(spp // n, 1))
+        peer.render(hs.camera, W, H, spp, depth, half, want_sums=False)
+        _, sl = peer.render(hs.camera, W, H, spp, depth, half, want_sums=False)
+        last = round(sl.render_ms, 2)
     print(json.dumps({"scene": name, "spp": spp, "n_gpus": n, "group_create_s": round(t_create, 3),
                       "multi_render_ms": round(st.render_ms, 2), "multi_wall_ms": round(t_wall * 1e3, 2),
                       "one_gpu_render_ms": round(s1.render_ms, 2), "speed_up": round(s1.render_ms / st.render_ms, 3),
                       "mpaths_per_s": round(st.paths / st.render_ms / 1e3, 1), "mrays_per_s": round(st.rays / st.render_ms / 1e3, 1),
-                      "rays_equal": int(st.rays) == int(s1.rays), "max_rel_diff_vs_one_gpu": rel,
+                      "last_gpu_alone_block_ms": last, "rays_equal": int(st.rays) == int(s1.rays), "max_rel_diff_vs_one_gpu": rel,
                       "info": root.render_info}), flush=True)
     group.close()

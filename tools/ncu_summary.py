@@ -42,6 +42,42 @@ def main():
     for k in KEYS:
         if k in m:
             print("%-70s %18s %s" % (k, m[k][0], m[k][1]))
+    # achieved bandwidth per level against the B200 peaks (BASELINE: "achieved L2/HBM GB/s ... against B200 peak")
+    def val(k):
+        try:
+            return float(m[k][0])
+        except (KeyError, ValueError):
+            return None
+    dur_ns = val("gpu__time_duration.sum")
+    if dur_ns is not None and m["gpu__time_duration.sum"][1] in ("us", "usecond"):
+        dur_ns *= 1e3
+    elif dur_ns is not None and m["gpu__time_duration.sum"][1] in ("ms", "msecond"):
+        dur_ns *= 1e6
+    elif dur_ns is not None and m["gpu__time_duration.sum"][1] in ("s", "second"):
+        dur_ns *= 1e9
+    print("\n## achieved bandwidth (whole launch)")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    rd, wr = val("dram__bytes_read.sum"), val("dram__bytes_write.sum")
+    if rd is not None and wr is not None and dur_ns:
+        b = rd * scale.get(m["dram__bytes_read.sum"][1], 1.0) + wr * scale.get(m["dram__bytes_write.sum"][1], 1.0)
+        peak = 6536.4  # MEASURED_PEAKS.json hbm_gbs of this pool's B200s
+        print("HBM   %10.1f GB/s   %5.2f %% of the measured copy peak (%.0f GB/s); ncu: %s %% of its own peak" % (
+            b / dur_ns, 100.0 * b / dur_ns / peak, peak, m.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", ("?",))[0]))
+    sec = val("lts__t_sectors.sum")
+    if sec is not None and dur_ns:
+        print("L2    %10.1f GB/s   (lts__t_sectors x 32 B; %s %% of ncu's L2 sector peak, lts__throughput %s %%)" % (
+            sec * 32.0 / dur_ns, m.get("lts__t_sectors.sum.pct_of_peak_sustained_elapsed", ("?",))[0],
+            m.get("lts__throughput.avg.pct_of_peak_sustained_elapsed", ("?",))[0]))
+    if "l1tex__throughput.avg.pct_of_peak_sustained_elapsed" in m:
+        print("L1    l1tex__throughput %s %% of peak, hit rate %s %%" % (
+            m["l1tex__throughput.avg.pct_of_peak_sustained_elapsed"][0], m.get("l1tex__t_sector_hit_rate.pct", ("?",))[0]))
+    print("FP32  pipe_fma %s %% (FFMA/FMUL/FADD), ALU %s %% (FMNMX, integer), FP64 %s %%, issue slots %s %%, SIMT %s of 32 threads" % (
+        m.get("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", ("?",))[0],
+        m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", ("?",))[0],
+        m.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", ("?",))[0],
+        m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", ("?",))[0],
+        m.get("smsp__thread_inst_executed_per_inst_executed.ratio", ("?",))[0]))
+
     print("\n## warp stall reasons (cycles per issued instruction)")
     st = [(k, float(v[0])) for k, v in m.items() if k.startswith("smsp__average_warps_issue_stalled_") and k.endswith("_per_issue_active.ratio")]
     for k, v in sorted(st, key=lambda x: -x[1])[:8]:
