@@ -44,9 +44,6 @@ constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
 constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
 constexpr uint32_t kMediumFlag = 0x80000000u;
 constexpr int kStackSize = 64;
-#ifndef RT_INNER_BELOW
-#define RT_INNER_BELOW 0
-#endif
 #define RT_INF (__longlong_as_double(0x7FF0000000000000ll))
 
 // ---------------------------------------------------------------------------
@@ -63,11 +60,7 @@ RT_DEV V3 operator*(double s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
 RT_DEV V3 operator*(V3 a, V3 b) { return mk(a.x * b.x, a.y * b.y, a.z * b.z); }
 // IEEE a/b.  nvcc's inline division sequence leaves its fast path for a zero numerator and
 // calls a ~70-instruction subroutine; 0/b is +-0 = 0*b for finite non-zero b, so take it directly.
-#ifdef RT_NOINLINE_DDIV
-static __device__ __noinline__ double ddiv(double a, double b) {
-#else
 RT_DEV double ddiv(double a, double b) {
-#endif
     if (a == 0.0) {
         double z = a * b;
         if (z == 0.0 && b != 0.0) return z;
@@ -412,11 +405,6 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double
             } else {
                 node = sp ? stack[--sp] : kDone;
             }
-#if RT_INNER_BELOW > 0
-            // lanes that hold a leaf wait here for the ones still descending: once only a few of those are
-            // left, test the leaves first and come back (a reordering; the result does not depend on it)
-            if ((unsigned)__popc(__ballot_sync(__activemask(), node >= 0)) < (unsigned)RT_INNER_BELOW) break;
-#endif
         }
         if (node < 0 && node != kDone) {
             uint32_t code = ~(uint32_t)node;
