@@ -29,9 +29,10 @@ struct WfCtl {
 
 // One 128-byte record per slot = one L2 line, eight 128-bit units; a lane moves a unit with one
 // 128-bit access.  Path state lives in its slot for the whole life of a (chunk, pixel) work item.
-// The stages walk the pool in slot order - no index queues: every slot is LIVE in steady state, so
+// The stages walk the pool in slot order - no global index queues: every slot is LIVE in steady state, so
 // a queue would be the identity, and each same-address atomic a warp spends on queue positions
 // costs ~4 ns of serialised L2 time (measured: 64k of them per round were the whole shade stage).
+// Reordering happens inside a block's tile of slots, in shared memory (the shade pass's class sort).
 // Sectors 0-1: the ray, state, depth (all extend reads); sector 2: throughput + Philox keys;
 // sector 3: what extend found + the work item.
 struct alignas(128) WfSlot {
@@ -58,7 +59,8 @@ static_assert(sizeof(WfSlot) == 128, "one slot per 128-byte line");
 struct WfPool {
     WfSlot *slots;
     double4 *sum;       // per slot: the item's radiance sum (x,y,z), samples added in sample order
-    uint32_t *state;    // per slot: WfState, apart from the record so that sparse rounds stay cheap
+    uint32_t *state;    // per slot: WfState in bits 0-7 (apart from the record so that sparse rounds stay cheap);
+                        // bits 8-10: class of what extend found (wavefront.inl: hit_class), the shade pass's sort key
     uint32_t *defer_q;  // shade pass 2: slots whose hit material is costly (Perlin noise, image textures)
     WfCtl *ctl;
     uint32_t capacity;  // slots allocated
