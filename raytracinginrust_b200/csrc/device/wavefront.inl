@@ -41,6 +41,20 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kShadeTile = RT_WF_SHADE_TILE * kWfBlock;
 static_assert(kShadeTile <= 4096, "local slot index and class share 16 bits");
 enum : uint32_t { WF_CLS_MISS = 0, WF_CLS_MEDIUM = 1, WF_CLS_MATERIAL = 2, WF_CLS_COSTLY = 7, WF_N_CLASSES = 8, WF_CLS_NONE = 0xFFu };
+// Bits 11-31 of the state word: where the slot's next ray starts, as the index of the primitive it leaves
+// (primitives are stored in BVH leaf order, so close indices are close in space); camera rays get the last key.
+// The simple extend stage sorts its tiles by it (RT_WF_EXT_TILE).  An octant-major key (direction octant, then 32
+// origin bins) was measured too: 134.0 ms against 131.9 ms for the origin alone on the final scene.
+__device__ __forceinline__ uint32_t hit_class(const DScene &sc, uint32_t prim);
+constexpr uint32_t kOriginKeyMax = 0x1FFFFFu;
+__device__ __forceinline__ uint32_t origin_key(uint32_t prim) {
+    if (prim == kNoPrim) return kOriginKeyMax;                  // (the path ends in shade)
+    if (prim & kMediumFlag) return kOriginKeyMax - 1u;          // scattered inside a medium
+    return prim < kOriginKeyMax - 2u ? prim : kOriginKeyMax - 2u;
+}
+__device__ __forceinline__ uint32_t live_state(const DScene &sc, uint32_t prim) {
+    return WF_LIVE | (hit_class(sc, prim) << 8) | (origin_key(prim) << 11);
+}
 __device__ __forceinline__ uint32_t hit_class(const DScene &sc, uint32_t prim) {
     if (prim == kNoPrim) return WF_CLS_MISS;
     if (prim & kMediumFlag) return WF_CLS_MEDIUM;
@@ -356,7 +370,7 @@ wf_generate_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__
             w[1] = make_double2(r.o.z, r.d.x);
             w[2] = make_double2(r.d.y, r.d.z);
             st_u4(w + 3, pack_time_state(r.time, WF_LIVE, P.max_depth));
-            pool.state[slot] = WF_LIVE;
+            pool.state[slot] = WF_LIVE | (kOriginKeyMax << 11);  // a camera ray
             w[4] = make_double2(1.0, 1.0);
             st_u4(w + 5, pack_bz_keys(1.0, rng_pixel, sample));
             st_u4(w + 7, make_uint4(out_pixel, s_end, chunk, 0u));
@@ -549,7 +563,7 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
                 if (MEDIA && q < nq && ((q - 1u) & 1u) != 0u && !have_t1) ++q;  // no first boundary hit: skip the second query
                 if (q >= nq) {
                     st_u4(slot_d2w(pool, slot) + 6, make_uint4(win.prim, (uint32_t)win.face, (uint32_t)__double2loint(closest), (uint32_t)__double2hiint(closest)));
-                    pool.state[slot] = WF_LIVE | (hit_class(sc, win.prim) << 8);  // what shade sorts its tiles by
+                    pool.state[slot] = live_state(sc, win.prim);  // what shade (and extend) sort their tiles by
                     has_ray = false;
                     break;
                 }
@@ -608,11 +622,15 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
 #ifndef RT_WF_SIMPLE_MIN_BLOCKS
 #define RT_WF_SIMPLE_MIN_BLOCKS 8
 #endif
+// RT_WF_EXT_TILE = N > 0: a block takes a tile of N x 128 slots and traces them sorted by where their rays start
+// (origin_key, 256 bins, counting sort in shared memory), so that a warp's rays begin in the same part of the BVH.
+#ifndef RT_WF_EXT_TILE
+#define RT_WF_EXT_TILE 4  // measured on the final scene: off 140.6 ms, 2 -> 132.8, 4 -> 132.0, 8 -> 137.2
+#endif
+constexpr int kExtTile = (RT_WF_EXT_TILE > 0 ? RT_WF_EXT_TILE : 1) * kWfBlock;
+
 template <bool MEDIA>
-__global__ void __launch_bounds__(kWfBlock, RT_WF_SIMPLE_MIN_BLOCKS)
-wf_extend_simple_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth) {
-    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= pool.n_slots || (pool.state[slot] & 0xFFu) != WF_LIVE) return;
+__device__ __forceinline__ void extend_slot(const DScene &sc, const WfPool &pool, uint32_t slot, uint32_t seed, uint32_t max_depth) {
     const double2 *u = slot_d2(pool, slot);
     const double2 r0 = u[0], r1 = u[1], r2 = u[2];
     const uint4 u3 = ld_u4(u + 3);
@@ -631,7 +649,77 @@ wf_extend_simple_kernel(const __grid_constant__ DScene sc, const __grid_constant
     double closest;
     world_search<MEDIA>(sc, ray, rng, win, closest);
     st_u4(slot_d2w(pool, slot) + 6, make_uint4(win.prim, (uint32_t)win.face, (uint32_t)__double2loint(closest), (uint32_t)__double2hiint(closest)));
-    pool.state[slot] = WF_LIVE | (hit_class(sc, win.prim) << 8);  // what shade sorts its tiles by
+    pool.state[slot] = live_state(sc, win.prim);  // what shade (and extend) sort their tiles by
+}
+
+template <bool MEDIA>
+__global__ void __launch_bounds__(kWfBlock, RT_WF_SIMPLE_MIN_BLOCKS)
+wf_extend_simple_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth) {
+#if RT_WF_EXT_TILE > 0
+    __shared__ unsigned s_bin[256];
+    __shared__ unsigned s_warp[kWfBlock / 32];
+    __shared__ unsigned s_live;
+    __shared__ unsigned short s_order[kExtTile];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t tile0 = blockIdx.x * (uint32_t)kExtTile;
+    // keys span [0, n_prims) plus the three special ones at the top: 256 bins over that range
+    const uint32_t top = sc.n_prims + 3u;
+    const int bits = 32 - __clz((int)(top | 1u));
+    const int shift = bits > 8 ? bits - 8 : 0;
+    s_bin[threadIdx.x] = 0u;
+    s_bin[threadIdx.x + kWfBlock] = 0u;
+    __syncthreads();
+    uint32_t key[RT_WF_EXT_TILE], pos[RT_WF_EXT_TILE];
+#pragma unroll
+    for (int i = 0; i < RT_WF_EXT_TILE; ++i) {
+        const uint32_t slot = tile0 + (uint32_t)i * kWfBlock + threadIdx.x;
+        key[i] = 0xFFFFFFFFu;
+        pos[i] = 0u;
+        if (slot < pool.n_slots) {
+            const uint32_t st = pool.state[slot];
+            if ((st & 0xFFu) == WF_LIVE) {
+                uint32_t k = st >> 11;
+                k = k >= kOriginKeyMax - 2u ? sc.n_prims + (k - (kOriginKeyMax - 2u)) : k;  // the special keys follow the primitives
+                key[i] = min(k >> shift, 255u);
+                pos[i] = atomicAdd(&s_bin[key[i]], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    {  // exclusive scan of the 256 bins: two bins per thread, warp scan, four warp totals
+        const unsigned a = s_bin[2u * threadIdx.x], b2 = s_bin[2u * threadIdx.x + 1u];
+        unsigned inc = a + b2;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(kFull, inc, d);
+            if (lane >= (unsigned)d) inc += o;
+        }
+        if (lane == 31u) s_warp[warp] = inc;
+        __syncthreads();
+        unsigned base = 0u, all = 0u;
+#pragma unroll
+        for (unsigned w = 0; w < kWfBlock / 32; ++w) {
+            const unsigned t = s_warp[w];
+            if (w < warp) base += t;
+            all += t;
+        }
+        const unsigned excl = base + inc - (a + b2);
+        s_bin[2u * threadIdx.x] = excl;
+        s_bin[2u * threadIdx.x + 1u] = excl + a;
+        if (threadIdx.x == 0) s_live = all;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RT_WF_EXT_TILE; ++i)
+        if (key[i] != 0xFFFFFFFFu) s_order[s_bin[key[i]] + pos[i]] = (unsigned short)((uint32_t)i * kWfBlock + threadIdx.x);
+    __syncthreads();
+    const unsigned n_live = s_live;
+    for (unsigned k = threadIdx.x; k < n_live; k += kWfBlock) extend_slot<MEDIA>(sc, pool, tile0 + s_order[k], seed, max_depth);
+#else
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= pool.n_slots || (pool.state[slot] & 0xFFu) != WF_LIVE) return;
+    extend_slot<MEDIA>(sc, pool, slot, seed, max_depth);
+#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -692,8 +780,9 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
     }
     wf_generate_kernel<<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(cam, P, pool, planes, counters);
     if (leave_threshold == 33u) {  // the simple form: one slot per thread
-        if (media) wf_extend_simple_kernel<true><<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
-        else wf_extend_simple_kernel<false><<<per_slot ? per_slot : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+        const unsigned per_ext = (pool.n_slots + kExtTile - 1) / kExtTile;
+        if (media) wf_extend_simple_kernel<true><<<per_ext ? per_ext : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
+        else wf_extend_simple_kernel<false><<<per_ext ? per_ext : 1u, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth);
     } else if (media) {
         wf_extend_kernel<true><<<ext_grid, kWfBlock, 0, stream>>>(sc, pool, P.seed, P.max_depth, leave_threshold);
     } else {
