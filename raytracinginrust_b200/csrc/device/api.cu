@@ -166,17 +166,29 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.tiles_x = (width + 7) / 8;
     P.tiles_y = (height + 3) / 4;
     P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
-    // Enough (chunk, pixel) items that the tail of the persistent grid / of the wavefront pool is a
-    // small fraction of the run.  The partition depends only on the image and the sample range, not
-    // on the pipeline or the GPU, so the f64 summation order - and with it every bit of the image -
-    // is the same whichever way it is rendered.
-    uint64_t target_items = 1ull << 26;
-    uint64_t chunks = (target_items + P.items_per_chunk - 1) / P.items_per_chunk;
-    uint64_t plane_cap = (4ull << 30) / ((uint64_t)width * height * 3 * sizeof(double));  // at most 4 GiB of planes
+    // Work items are (chunk of consecutive samples, pixel).  Small items keep the end of a render short: the last item
+    // of every lane / pool slot is run to its end while the others idle (measured on the wavefront pipeline, final
+    // scene at 2048 spp: 20 samples per item 1114 ms, 8 per item 1063 ms); items that are too small hammer the one
+    // work counter (an atomic per item) and multiply the f64 planes.  So: about 8 samples per item, but at least 2^23
+    // items when the image is small or the render short, and never more planes than 4 GiB / 1024 (16 GiB of planes
+    // bought the final scene at 10000 spp another 3 % of device time and cost as much again in cudaMalloc).
+    // The partition depends only on the image and the sample range, not on the pipeline or the GPU, so the f64
+    // summation order - and with it every bit of the image - is the same whichever way it is rendered.
+    const uint64_t kSamplesPerItem = 8, kMinItems = 1ull << 23;
+    uint64_t chunks = (count + kSamplesPerItem - 1) / kSamplesPerItem;
+    const uint64_t for_balance = (kMinItems + P.items_per_chunk - 1) / P.items_per_chunk;
+    if (chunks < for_balance) chunks = for_balance;
+    uint64_t plane_cap = (4ull << 30) / ((uint64_t)width * height * 3 * sizeof(double));
+    if (plane_cap < 1) plane_cap = 1;
     if (chunks > plane_cap) chunks = plane_cap;
-    if (chunks < 1) chunks = 1;
+    if (chunks > 1024) chunks = 1024;
     if (chunks > count) chunks = count;
-    if (chunks > 256) chunks = 256;
+    if (chunks < 1) chunks = 1;
+    if (const char *v = std::getenv("RTB200_CHUNKS")) {  // tuning: force the number of sample chunks
+        long long n = std::atoll(v);
+        if (n >= 1) chunks = (uint64_t)n < count ? (uint64_t)n : count;
+        if (chunks > plane_cap) chunks = plane_cap;
+    }
     P.chunk_size = (uint32_t)((count + chunks - 1) / chunks);
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;

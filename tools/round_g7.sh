@@ -2,10 +2,12 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-rm -f $O/g7_ab.txt
-for v in new nid nip nil niall; do
-  d=variants_build/$v; [ $v = new ] && d=raytracinginrust_b200/lib
-  echo "== $v" >> $O/g7_ab.txt
-  RTB200_LIB_DIR=$d timeout 240 python tools/wf_probe2.py final:256 cornell:250 random:128 >> $O/g7_ab.txt 2>&1 || echo "   (failed: rc=$?)" >> $O/g7_ab.txt
-done
-cat $O/g7_ab.txt
+timeout 400 python tools/wf_probe2.py final:2048 cornell:1000 cornell_smoke:1000 random:800 mesh:64 > $O/g7_newchunks.txt 2>&1
+cat $O/g7_newchunks.txt
+timeout 900 python -m pytest tests -x -q -m gpu > $O/g7_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/g7_pytest.log
+timeout 600 python bench.py --workload final --steps 2 --warmup 3 > $O/g7_bench_final.json 2> $O/g7_bench_final.err; echo "bench final rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/g7_bench_final.json').read().strip().split("\n")[-1])
+print("final", d["value"], d["mrays_per_s"], d["ms_per_step"], d["e2e"]["value"], d["gpu_launches"])
+PY
