@@ -100,7 +100,10 @@ class ClockSampler:
         # "under load": the upper half of the samples (idle gaps between steps pull the plain median down)
         load = sm[len(sm) // 2:] if sm else []
         return {"sm_mhz": load[len(load) // 2] if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                # the whole distribution inside the timed window (idle gaps between steps included)
+                "sm_mhz_min": sm[0] if sm else None, "sm_mhz_p10": sm[len(sm) // 10] if sm else None,
+                "sm_mhz_median_all": sm[len(sm) // 2] if sm else None}
 
 
 def algorithmic_work(counters):
