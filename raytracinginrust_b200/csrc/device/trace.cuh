@@ -100,7 +100,11 @@ RT_DEV V3 refract(V3 v, V3 n, double etai_over_etat) {                  // vec.r
 // axis-parallel rays order correctly in the slab tests; infinities and NaN only ever reject).
 RT_DEV double rcp_fast(double x) {
     double r0;
+#ifdef __CUDACC__
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+#else  // g++ build of this header for the CPU test tier (tests/native): the exact reciprocal as the seed
+    r0 = 1.0 / x;
+#endif
     double e = fma(-x, r0, 1.0);
     double r = fma(r0, e, r0);
     e = fma(-x, r, 1.0);

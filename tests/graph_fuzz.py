@@ -1,0 +1,115 @@
+"""Seeded random scene graphs for the parity tests (CPU tier: test_scene_graph_fuzz.py; GPU: test_gpu_parity.py)."""
+import numpy as np
+
+
+class GraphMaker:
+    """A seeded random scene graph inside the cube [-10, 10]^3 with one rect light above it."""
+
+    def __init__(self, rt, seed):
+        self.rt, self.A = rt, rt._abi
+        self.rng = np.random.default_rng(seed)
+        self.b = rt.SceneBuilder()
+        b = self.b
+        grey = b.constant_texture((0.6, 0.6, 0.6))
+        check = b.check_texture(b.constant_texture((0.2, 0.3, 0.1)), b.constant_texture((0.9, 0.9, 0.9)))
+        self.materials = [b.lambertian(grey), b.lambertian(check), b.lambertian(b.constant_texture((0.7, 0.2, 0.2))),
+                          b.metal((0.8, 0.85, 0.88), 0.0), b.metal((0.7, 0.6, 0.5), 0.3), b.dielectric(1.5)]
+        self.light_material = b.diffuse_light(b.constant_texture((7.0, 7.0, 7.0)))
+
+    def u(self, lo, hi, n=None):
+        return self.rng.uniform(lo, hi, n)
+
+    def material(self):
+        return self.materials[int(self.rng.integers(len(self.materials)))]
+
+    def primitive(self, under_bvh, scale=1.0):
+        b, A = self.b, self.A
+        c = self.u(-8, 8, 3) * scale
+        kind = int(self.rng.integers(5))
+        if kind == 0:
+            return b.sphere(c, self.u(0.3, 2.0) * scale, self.material())
+        if kind == 1:
+            return b.moving_sphere(c, c + self.u(-0.5, 0.5, 3), 0.0, 1.0, self.u(0.3, 1.5) * scale, self.material())
+        if kind == 2:
+            a0, b0 = self.u(-8, 6, 2) * scale
+            # §Q5: AARect::bounding_box ignores the plane (rect.rs:83-89), so the reference's own BVH culls XZ / YZ
+            # rects it should hit; the compiler builds correct bounds on purpose.  Below a BVH only XY
+            # rects - where the reference's box is right - are comparable.
+            plane = A.PLANE_XY if under_bvh else int(self.rng.integers(3))
+            return b.rect(plane, a0, a0 + self.u(0.5, 4) * scale, b0, b0 + self.u(0.5, 4) * scale,
+                          self.u(-8, 8) * scale, self.material())
+        if kind == 3:
+            return b.triangle(c, c + self.u(-3, 3, 3) * scale, c + self.u(-3, 3, 3) * scale, self.material())
+        return b.cube(c, c + self.u(0.3, 3, 3) * scale, self.material())
+
+    def wrap(self, node):
+        """Zero to three wrappers in random order (translate.rs, rotate.rs, hit.rs:99-133)."""
+        b = self.b
+        for _ in range(int(self.rng.integers(4))):
+            w = int(self.rng.integers(3))
+            if w == 0:
+                node = b.translate(node, self.u(-3, 3, 3))
+            elif w == 1:
+                node = b.rotate(int(self.rng.integers(3)), node, self.u(-180, 180))
+            else:
+                node = b.flip(node)
+        return node
+
+    def subtree(self, depth, under_bvh):
+        b = self.b
+        r = self.rng.random()
+        if depth >= 3 or r < 0.35:
+            return self.wrap(self.primitive(under_bvh))
+        n = int(self.rng.integers(1, 9))
+        is_bvh = r < 0.7
+        kids = [self.subtree(depth + 1, under_bvh or is_bvh) for _ in range(n)]
+        node = b.bvh(kids, 0.0, 1.0) if is_bvh else b.list(kids)
+        return self.wrap(node)
+
+    def medium(self):
+        b = self.b
+        c = self.u(-5, 5, 3)
+        kind = int(self.rng.integers(3))
+        if kind == 0:
+            boundary = b.sphere(c, self.u(1.0, 3.0), self.materials[0])
+        elif kind == 1:
+            boundary = b.cube(c, c + self.u(1.0, 4.0, 3), self.materials[0])
+        else:  # the Cornell smoke construction: Translate(Rotate(Cube)) (main.rs:330-343)
+            boundary = b.translate(b.rotate(self.A.AXIS_Y, b.cube((0, 0, 0), self.u(1.0, 4.0, 3), self.materials[0]),
+                                            self.u(-40, 40)), c)
+        return b.medium(boundary, self.u(0.05, 0.6), b.constant_texture(self.u(0.1, 1.0, 3)))
+
+    def make(self):
+        b, A = self.b, self.A
+        world_is_bvh = self.rng.random() < 0.4
+        top = [self.subtree(0, world_is_bvh) for _ in range(int(self.rng.integers(2, 7)))]
+        if self.rng.random() < 0.5:
+            top += [self.medium() for _ in range(int(self.rng.integers(1, 3)))]
+        light = b.flip(b.rect(A.PLANE_XZ, -3, 3, -3, 3, 11.0, self.light_material))
+        lights, emitters = [light], [light]
+        if self.rng.random() < 0.3:  # a sphere light next to it (sphere.rs:27-36,104-119)
+            sl = b.sphere((6.0, 9.0, -4.0), 1.2, self.light_material)
+            emitters.append(sl)
+            lights.append(sl)
+        self.rng.shuffle(top)
+        # the XZ light rect stays outside any BVH (§Q5), like in every scene of main.rs
+        world = b.list([b.bvh(top, 0.0, 1.0)] + emitters) if world_is_bvh else b.list(top + emitters)
+        if self.rng.random() < 0.3:
+            world = b.list([world])
+        bg = (0.0, 0.0, 0.0) if self.rng.random() < 0.5 else (0.7, 0.8, 1.0)
+        return b.finish(world, b.list(lights), background=bg)
+
+    def rays(self, n):
+        """Origins around and inside the scene, un-normalised directions, times in [0, 1)."""
+        rays = np.zeros(n, dtype=self.A.RAY_DTYPE)
+        o = self.u(-14, 14, (n, 3))
+        target = self.u(-8, 8, (n, 3))
+        rays["origin"] = o
+        rays["direction"] = (target - o) * self.u(0.05, 2.0, (n, 1))
+        rays["time"] = self.rng.random(n)
+        return rays
+
+
+def fuzz_camera(rt):
+    """Looks at the cube the graphs live in from outside it."""
+    return rt.camera_new((0.0, 3.0, -26.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 40.0, 1.0, 0.1, 26.0, 0.0, 1.0)

@@ -127,6 +127,24 @@ def test_product_does_not_reference_the_oracle():
                 assert "oracle" not in open(path).read(), path
 
 
+def test_product_does_not_reference_test_infrastructure(rt):
+    """tests/native builds the device source for the host so that the CPU tier can check its logic; it is not a
+    CPU path of the product: no product source, Makefile or library refers to it, and bench.py never loads it."""
+    pkg = os.path.join(ROOT, "raytracinginrust_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h", ".hpp", ".inl")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "trace_on_host" not in text and "toh_" not in text, os.path.join(dirpath, f)
+                assert not re.search(r"#\s*include[^\n]*tests/", text), os.path.join(dirpath, f)
+    for f in ("bench.py", "include/rtb200.h"):
+        text = open(os.path.join(ROOT, f)).read()
+        assert "trace_on_host" not in text and "toh_" not in text and "tests/native" not in text, f
+    for lib in (rt._dev, rt._host):
+        for sym in ("toh_scene_create", "toh_render", "toh_trace_first_hit", "toh_path_radiance"):
+            assert not hasattr(lib, sym), sym
+
+
 def test_group_and_encode_argument_checks(rt):
     """The multi-GPU and output entry points validate without a GPU and never compute on the CPU."""
     b, s, light = _simple(rt)
