@@ -555,8 +555,18 @@ bool ref_bvh_order(const RtSceneDesc &d, const std::vector<uint32_t> &hit, doubl
         err = ro.bad.load() == 1 ? "NaN extent in BVH build" : "NaN centroid in BVH build";
         return false;
     }
+    // Every object of a reference BVH sits in a Leaf node of its own whose box is tested first
+    // (bvh.rs:56-63,77-78), and AABB::hit rejects with `t_out <= t_in` (aabb.rs:31): a box without
+    // extent along some axis has t0 == t1 there and is never entered.  So an axis-aligned flat
+    // triangle (or a list of them) directly under a BVH - an OBJ cube through mesh.rs and
+    // main.rs:442, say - is invisible in the reference, and it is left out here.  (The one ray that
+    // gets through has a zero direction component and its origin exactly in that plane: 0 * inf = NaN,
+    // which f64::max / min skip.)  The object still took part in the ordering above.
     out.reserve(out.size() + hit.size());
-    for (size_t i = 0; i < hit.size(); ++i) out.push_back(hit[ro.items[i].idx]);
+    for (size_t i = 0; i < hit.size(); ++i) {
+        const RefBox &b = boxes[ro.items[i].idx];
+        if (b.lo[0] < b.hi[0] && b.lo[1] < b.hi[1] && b.lo[2] < b.hi[2]) out.push_back(hit[ro.items[i].idx]);
+    }
     return true;
 }
 

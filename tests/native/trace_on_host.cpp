@@ -269,6 +269,7 @@ struct TableCheck {
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char *toh_last_error() { return g_err.c_str(); }
@@ -441,3 +442,4 @@ int toh_render(void *h, const RtCamera *cam, uint32_t width, uint32_t height, ui
 }
 
 }  // extern "C"
+#pragma GCC visibility pop

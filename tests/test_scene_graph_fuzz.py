@@ -58,3 +58,39 @@ def test_random_scene_graph(rt, orc, toh, seed):
         assert ok.mean() >= 0.999
     comp.close()
     osc.close()
+
+
+def test_flat_boxes_under_a_bvh_are_never_entered(rt, orc, toh):
+    """bvh.rs:56-63 gives every object a Leaf node whose box is tested first, and AABB::hit (aabb.rs:31) rejects with
+    `t_out <= t_in`: an axis-aligned flat triangle directly under a BVH (an OBJ cube loaded by mesh.rs and wrapped by
+    main.rs:442) has a box without extent on one axis and is invisible in the reference.  The scene compiler leaves
+    such objects out, so the CUDA path shows the same hole; the same triangles in a plain list are hit by both."""
+    A = rt._abi
+
+    def scene(container):
+        b = rt.SceneBuilder()
+        m = b.lambertian(b.constant_texture((0.5, 0.5, 0.5)))
+        quad = [b.triangle((-2, 1, -2), (2, 1, -2), (2, 1, 2), m), b.triangle((-2, 1, -2), (2, 1, 2), (-2, 1, 2), m)]  # flat in y
+        tilted = b.triangle((-2, 0, -2), (2, 0.5, -2), (0, 0.25, 2), m)
+        ball = b.sphere((0, -3, 0), 1.0, m)
+        light = b.flip(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 9, b.diffuse_light(b.constant_texture((4, 4, 4)))))
+        kids = quad + [tilted, ball]
+        world = b.list([getattr(b, container)(kids), light])
+        return b.finish(world, b.list([light])), quad, tilted
+
+    rng = np.random.default_rng(3)
+    n = 4000
+    rays = np.zeros(n, dtype=A.RAY_DTYPE)
+    rays["origin"] = np.stack([rng.uniform(-1.5, 1.5, n), np.full(n, 6.0), rng.uniform(-1.5, 1.5, n)], axis=1)
+    rays["direction"] = np.stack([rng.uniform(-0.05, 0.05, n), np.full(n, -1.0), rng.uniform(-0.05, 0.05, n)], axis=1)
+    for container in ("bvh", "list"):
+        sd, quad, tilted = scene(container)
+        comp, osc = toh.CompiledOnHost(sd), orc.OracleScene(sd)
+        comp.check_tables()
+        hd, ho = comp.trace_first_hit(rays), osc.trace_first_hit(rays)
+        assert np.array_equal(hd["node"], ho["node"]) and np.array_equal(hd["t"], ho["t"])
+        on_quad = np.isin(ho["node"], quad)
+        if container == "bvh":
+            assert not on_quad.any() and (ho["node"] == tilted).sum() > n // 4  # the rays fall through the flat quad
+        else:
+            assert on_quad.all()
