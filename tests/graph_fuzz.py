@@ -5,8 +5,9 @@ import numpy as np
 class GraphMaker:
     """A seeded random scene graph inside the cube [-10, 10]^3 with one rect light above it."""
 
-    def __init__(self, rt, seed):
-        self.rt, self.A = rt, rt._abi
+    def __init__(self, rt, seed, rich=False):
+        self.rt, self.A, self.rich = rt, rt._abi, rich
+        self.has_default_light = False
         self.rng = np.random.default_rng(seed)
         self.b = rt.SceneBuilder()
         b = self.b
@@ -14,6 +15,16 @@ class GraphMaker:
         check = b.check_texture(b.constant_texture((0.2, 0.3, 0.1)), b.constant_texture((0.9, 0.9, 0.9)))
         self.materials = [b.lambertian(grey), b.lambertian(check), b.lambertian(b.constant_texture((0.7, 0.2, 0.2))),
                           b.metal((0.8, 0.85, 0.88), 0.0), b.metal((0.7, 0.6, 0.5), 0.3), b.dielectric(1.5)]
+        if rich:
+            # Perlin::new (perlin.rs:5-24): in-ball gradients, three shuffled permutations; an 8x4 image; textures
+            # nested in a checker; the Disney-style material (mat.rs:86-197) with PDF::BRDF
+            r = self.rng
+            ranvec = r.uniform(-1, 1, (256, 3)) * r.uniform(0.2, 1.0, (256, 1))
+            marble = b.noise_texture(float(r.uniform(0.1, 4.0)), ranvec, r.permutation(256), r.permutation(256), r.permutation(256))
+            image = b.image_texture(r.integers(0, 256, 8 * 4 * 3, dtype=np.uint8).tobytes(), 8, 4)
+            self.materials += [b.lambertian(marble), b.lambertian(image), b.lambertian(b.check_texture(marble, image)),
+                               b.pbr(grey, metallic=0.3, specular=0.5, roughness=0.4, clearcoat=0.2, clearcoat_gloss=0.7),
+                               b.pbr(image, metallic=0.0, subsurface=0.2, roughness=0.8, anisotropic=0.5, sheen=0.3)]
         self.light_material = b.diffuse_light(b.constant_texture((7.0, 7.0, 7.0)))
 
     def u(self, lo, hi, n=None):
@@ -91,6 +102,15 @@ class GraphMaker:
             sl = b.sphere((6.0, 9.0, -4.0), 1.2, self.light_material)
             emitters.append(sl)
             lights.append(sl)
+        if self.rich and self.rng.random() < 0.5:
+            # Lights the reference's pdf cannot sample: only AARect and Sphere implement pdf_value / random and only
+            # FlipNormal forwards them (hit.rs:126-132); a Cube or a translated rect in the light list falls back to
+            # the trait defaults (hit.rs:29-30: pdf 0, direction (1,0,0)).
+            odd = b.cube((-7.0, 8.0, 5.0), (-5.0, 9.0, 7.0), self.light_material) if self.rng.random() < 0.5 else \
+                b.translate(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 10.0, self.light_material), (4.0, 0.0, 4.0))
+            emitters.append(odd)
+            lights.append(odd)
+            self.has_default_light = True
         self.rng.shuffle(top)
         # the XZ light rect stays outside any BVH (§Q5), like in every scene of main.rs
         world = b.list([b.bvh(top, 0.0, 1.0)] + emitters) if world_is_bvh else b.list(top + emitters)

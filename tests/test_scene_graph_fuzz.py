@@ -29,7 +29,9 @@ def toh():
 
 @pytest.mark.parametrize("seed", range(N_GRAPHS))
 def test_random_scene_graph(rt, orc, toh, seed):
-    g = GraphMaker(rt, 1000 + seed)
+    # the second half of the graphs adds Perlin / image / nested textures, the PBR material and light lists with
+    # objects the reference cannot sample
+    g = GraphMaker(rt, 1000 + seed, rich=seed >= N_GRAPHS // 2)
     sd = g.make()
     comp, osc = toh.CompiledOnHost(sd), orc.OracleScene(sd)
     counts = comp.check_tables()
@@ -55,7 +57,11 @@ def test_random_scene_graph(rt, orc, toh, seed):
         err = rel_err(np.nan_to_num(rd), np.nan_to_num(ro), floor=1e-9).max(axis=1)
         ok = ((err <= 1e-4) & ~nan_d & ~nan_o) | (nan_d & nan_o)
         print(seed, "integrator", integrator, "ok %.5f max err %.2e segments %.3f / %.3f" % (ok.mean(), err.max(), segd.mean(), sego.mean()))
-        assert ok.mean() >= 0.999
+        # A light the reference cannot sample sends its rays along exactly (1, 0, 0) (hit.rs:29-30).  From a point
+        # that lies exactly in an axis-aligned face such a ray meets the reference's unguarded arithmetic - 0/0 in
+        # AARect::hit passes every rejecting comparison (rect.rs:51-58) - which the search code does not follow
+        # (DESIGN.md "Known deviations"); those paths are already inf / NaN in both.
+        assert ok.mean() >= (0.99 if g.has_default_light and integrator == rt.INTEGRATOR_HEAD else 0.999)
     comp.close()
     osc.close()
 
