@@ -316,7 +316,8 @@ def test_random_scene_graphs_on_device(rt, orc, seed):
     emit, media bounded by instanced boxes, both integrators) through the CUDA path: same object as the oracle's
     literal object tree on identical rays, same radiance per path, and both pipelines rendering the same image."""
     from graph_fuzz import GraphMaker, fuzz_camera
-    g = GraphMaker(rt, 1000 + seed)
+    # seeds 4-7: Perlin / image / nested textures, PBR, light lists with objects the reference cannot sample
+    g = GraphMaker(rt, 1000 + seed, rich=seed >= 4)
     sd = g.make()
     dev, osc = rt.DeviceScene(sd, device=0), orc.OracleScene(sd)
     rays = g.rays(30000)
@@ -339,7 +340,8 @@ def test_random_scene_graphs_on_device(rt, orc, seed):
         err = rel_err(np.nan_to_num(rd), np.nan_to_num(ro), floor=1e-9).max(axis=1)
         ok = ((err <= 1e-4) & ~nan_d & ~nan_o) | (nan_d & nan_o)
         print(seed, "integrator", integrator, "ok %.5f median err %.2e" % (ok.mean(), np.median(err)))
-        assert ok.mean() >= 0.998
+        # (1, 0, 0) rays of an unsampleable light: see test_scene_graph_fuzz.py and DESIGN.md "Known deviations"
+        assert ok.mean() >= (0.99 if g.has_default_light and integrator == rt.INTEGRATOR_HEAD else 0.998)
     a, sa = dev.render(cam, 40, 30, 6, 50, rt.render_opts(seed=3, flags=rt._abi.FLAG_MEGAKERNEL))
     b, sb = dev.render(cam, 40, 30, 6, 50, rt.render_opts(seed=3, flags=rt._abi.FLAG_WAVEFRONT))
     assert np.array_equal(a, b, equal_nan=True) and sa.rays == sb.rays
