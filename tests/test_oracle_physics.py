@@ -1,0 +1,138 @@
+"""CPU tier: the oracle (and the g++ build of the device source) against closed-form radiometry.
+
+The reference has no test vectors, so beyond its one table the oracle is pinned by restating the cited
+lines faithfully.  These tests add an independent anchor: small scenes whose expected radiance has a closed form, so
+that the integrator, the mixture-PDF light sampling (pdf.rs, rect.rs:91-111, sphere.rs:27-36,104-119), the material
+pdfs and the medium's free-path sampling (medium.rs:42-45) are checked against physics, not against themselves.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "native"))
+
+
+@pytest.fixture(scope="module")
+def toh():
+    import trace_on_host as m
+    return m
+
+
+def both(rt, orc, toh, sd):
+    return [("oracle", orc.OracleScene(sd)), ("device source on host", toh.CompiledOnHost(sd))]
+
+
+def centre_paths(n, W, H):
+    return (np.full(n, W // 2, dtype=np.uint32), np.full(n, H // 2, dtype=np.uint32), np.arange(n, dtype=np.uint32))
+
+
+def rect_form_factor(a, b, h):
+    """Differential element -> parallel rectangle [-a/2,a/2]x[-b/2,b/2] at height h above it (four corner terms)."""
+    x, y = a / 2.0, b / 2.0
+    corner = (x / math.hypot(x, h) * math.atan(y / math.hypot(x, h)) + y / math.hypot(y, h) * math.atan(x / math.hypot(y, h))) / (2.0 * math.pi)
+    return 4.0 * corner
+
+
+def test_furnace_legacy_integrator_returns_the_albedo(rt, orc, toh):
+    """main.rs:84-85 on a convex Lambertian sphere in a uniform white environment: the scattered ray leaves the sphere
+    and meets the background, so EVERY path that hits returns exactly albedo * 1 - no variance at all."""
+    b = rt.SceneBuilder()
+    rho = (0.25, 0.5, 0.75)
+    s = b.sphere((0, 0, 0), 1.0, b.lambertian(b.constant_texture(rho)))
+    sd = b.finish(b.list([s]), b.list([]), background=(1.0, 1.0, 1.0))
+    cam = rt.camera_new((0, 0, -5), (0, 0, 0), (0, 1, 0), 10.0, 1.0, 0.0, 5.0)
+    px, py, smp = centre_paths(2000, 33, 33)
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, seg = sc.path_radiance(cam, 33, 33, 50, rt.render_opts(seed=7, integrator=rt.INTEGRATOR_LEGACY), px, py, smp)
+        assert np.array_equal(seg, np.full(2000, 2)), name
+        assert np.array_equal(rgb, np.tile(np.array(rho), (2000, 1))), name
+
+
+def test_rect_light_over_a_diffuse_floor_matches_the_form_factor(rt, orc, toh):
+    """main.rs:92-98: a Lambertian floor (albedo rho) under a flipped XZ rect light of radiance E, black background.
+    The only light path is floor -> light, so L = rho * E * F with F the point-to-rectangle form factor.  The mixture
+    of the light pdf (rect.rs:91-101) and the cosine pdf must average to it whatever the weights."""
+    A = rt._abi
+    rho, E, a, c, h = 0.6, 5.0, 3.0, 2.0, 2.5
+    b = rt.SceneBuilder()
+    floor = b.rect(A.PLANE_XZ, -500, 500, -500, 500, 0.0, b.lambertian(b.constant_texture((rho, rho, rho))))
+    light = b.flip(b.rect(A.PLANE_XZ, -a / 2, a / 2, -c / 2, c / 2, h, b.diffuse_light(b.constant_texture((E, E, E)))))
+    sd = b.finish(b.list([floor, light]), b.list([light]))
+    # looks at the floor point under the centre of the light from the side, below the light's plane
+    cam = rt.camera_new((6.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0, 1, 0), 0.05, 1.0, 0.0, 6.0)
+    n = 60000
+    px, py, smp = centre_paths(n, 3, 3)
+    expect = rho * E * rect_form_factor(a, c, h)
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, seg = sc.path_radiance(cam, 3, 3, 50, rt.render_opts(seed=3, integrator=rt.INTEGRATOR_HEAD), px, py, smp)
+        assert np.isfinite(rgb).all(), name
+        mean, sem = rgb[:, 0].mean(), rgb[:, 0].std() / math.sqrt(n)
+        print(name, "L = %.5f +- %.5f, closed form %.5f" % (mean, sem, expect))
+        assert abs(mean - expect) < 4.0 * sem + 1e-3 * expect, name
+        assert sem < 0.01 * expect, name  # importance sampling keeps the variance low
+
+
+def test_sphere_light_over_a_diffuse_floor(rt, orc, toh):
+    """Sphere::pdf_value / random (sphere.rs:27-36,104-119; random_to_sphere): irradiance of a floor point from a
+    uniform sphere of radiance E whose centre is straight above it is pi * E * (r/d)^2 - so L = rho * E * (r/d)^2."""
+    A = rt._abi
+    rho, E, r, d = 0.8, 4.0, 1.0, 3.0
+    b = rt.SceneBuilder()
+    floor = b.rect(A.PLANE_XZ, -500, 500, -500, 500, 0.0, b.lambertian(b.constant_texture((rho, rho, rho))))
+    lamp = b.sphere((0.0, d, 0.0), r, b.diffuse_light(b.constant_texture((E, E, E))))
+    sd = b.finish(b.list([floor, lamp]), b.list([lamp]))
+    cam = rt.camera_new((6.0, 1.0, 0.0), (0.0, 0.0, 0.0), (0, 1, 0), 0.05, 1.0, 0.0, 6.0)
+    n = 60000
+    px, py, smp = centre_paths(n, 3, 3)
+    expect = rho * E * (r / d) ** 2
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, _ = sc.path_radiance(cam, 3, 3, 50, rt.render_opts(seed=5, integrator=rt.INTEGRATOR_HEAD), px, py, smp)
+        mean, sem = rgb[:, 0].mean(), rgb[:, 0].std() / math.sqrt(n)
+        print(name, "L = %.5f +- %.5f, closed form %.5f" % (mean, sem, expect))
+        assert abs(mean - expect) < 4.0 * sem + 1e-3 * expect, name
+
+
+def test_medium_transmittance_is_beer_lambert(rt, orc, toh):
+    """medium.rs:42-45: hit_distance = -(1/density) ln(xi) against the chord through the boundary.  With a black
+    phase-function albedo under the legacy integrator a path returns the white background iff it crosses the slab
+    unscattered, so the mean is exp(-density * thickness)."""
+    density, thickness = 0.35, 2.0
+    b = rt.SceneBuilder()
+    slab = b.cube((-50, -50, 0.0), (50, 50, thickness), b.lambertian(b.constant_texture((1, 1, 1))))
+    fog = b.medium(slab, density, b.constant_texture((0.0, 0.0, 0.0)))
+    sd = b.finish(b.list([fog]), b.list([]), background=(1.0, 1.0, 1.0))
+    cam = rt.camera_new((0, 0, -10), (0, 0, 0), (0, 1, 0), 0.05, 1.0, 0.0, 10.0)
+    n = 40000
+    px, py, smp = centre_paths(n, 3, 3)
+    expect = math.exp(-density * thickness)
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, seg = sc.path_radiance(cam, 3, 3, 50, rt.render_opts(seed=9, integrator=rt.INTEGRATOR_LEGACY), px, py, smp)
+        assert set(np.unique(rgb[:, 0])) <= {0.0, 1.0}, name
+        mean = rgb[:, 0].mean()
+        sem = math.sqrt(expect * (1 - expect) / n)
+        print(name, "T = %.5f +- %.5f, Beer-Lambert %.5f" % (mean, sem, expect))
+        assert abs(mean - expect) < 4.0 * sem, name
+
+
+def test_mirror_and_glass_conserve_a_uniform_environment(rt, orc, toh):
+    """Specular arms (main.rs:89-91; mat.rs:280-293, :343-374): in a uniform white environment a fuzz-free mirror
+    returns exactly its albedo and a glass sphere exactly 1 (attenuation 1 at every interface), whatever the path."""
+    b = rt.SceneBuilder()
+    mirror = b.sphere((-1.5, 0, 0), 1.0, b.metal((0.8, 0.6, 0.4), 0.0))
+    glass = b.sphere((1.5, 0, 0), 1.0, b.dielectric(1.5))
+    lamp = b.flip(b.rect(rt._abi.PLANE_XZ, -0.1, 0.1, -0.1, 0.1, 50.0, b.diffuse_light(b.constant_texture((1, 1, 1)))))
+    sd = b.finish(b.list([mirror, glass, lamp]), b.list([lamp]), background=(1.0, 1.0, 1.0))
+    n = 3000
+    smp = np.arange(n, dtype=np.uint32)
+    for name, sc in both(rt, orc, toh, sd):
+        for target, expect in (((-1.5, 0, 0), (0.8, 0.6, 0.4)), ((1.5, 0, 0), (1.0, 1.0, 1.0))):
+            cam = rt.camera_new((target[0], 0.0, -6.0), target, (0, 1, 0), 6.0, 1.0, 0.0, 6.0)
+            px, py, _ = centre_paths(n, 5, 5)
+            rgb, seg = sc.path_radiance(cam, 5, 5, 100, rt.render_opts(seed=2, integrator=rt.INTEGRATOR_HEAD), px, py, smp)
+            assert (seg >= 2).all(), name
+            done = seg < 100  # total internal reflection can trap a path until the depth limit (returns black)
+            assert done.mean() > 0.99, name
+            assert np.allclose(rgb[done], np.array(expect), rtol=0, atol=1e-12), (name, target)
