@@ -574,6 +574,7 @@ struct Walker {
     const RtSceneDesc &d;
     CompiledScene &out;
     std::string &err;
+    Walker(const RtSceneDesc &desc, CompiledScene &compiled, std::string &message) : d(desc), out(compiled), err(message) {}
     RtStatus status = RT_OK;
     std::vector<DOp> stack;
     std::vector<std::vector<DOp>> chain_ops;  // interned chains
@@ -950,7 +951,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     // ---- world ----
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[compile] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
-    Walker w{d, out, err};
+    Walker w(d, out, err);
     std::vector<GroupBuild> world_groups;
     std::vector<PendingMedium> pending;
     w.groups = &world_groups;
