@@ -38,9 +38,17 @@ class GraphMaker:
         c = self.u(-8, 8, 3) * scale
         kind = int(self.rng.integers(5))
         if kind == 0:
-            return b.sphere(c, self.u(0.3, 2.0) * scale, self.material())
+            # a negative radius is the RTiOW hollow-glass trick: the normal points inwards (sphere.rs:75-76), and the
+            # inverted box c -+ r keeps the sphere out of any BVH (aabb.rs:31)
+            # (below a BVH its inverted box also shrinks the union box of a list around it: the §Q5 class again)
+            sign = -1.0 if self.rich and not under_bvh and self.rng.random() < 0.15 else 1.0
+            return b.sphere(c, sign * self.u(0.3, 2.0) * scale, self.material())
         if kind == 1:
-            return b.moving_sphere(c, c + self.u(-0.5, 0.5, 3), 0.0, 1.0, self.u(0.3, 1.5) * scale, self.material())
+            # center(time) extrapolates outside [time0, time1] (sphere.rs:144-146, §Q18); camera times are in [0, 1)
+            # (MovingSphere::bounding_box only covers center0 / center1, sphere.rs:191-201: below a BVH the
+            # extrapolated sphere sticks out of the reference's box, so the time range stays [0, 1] there)
+            t0, t1 = (0.0, 1.0) if (under_bvh or not self.rich) else (float(self.u(-0.5, 0.4)), float(self.u(0.6, 1.5)))
+            return b.moving_sphere(c, c + self.u(-0.5, 0.5, 3), t0, t1, self.u(0.3, 1.5) * scale, self.material())
         if kind == 2:
             a0, b0 = self.u(-8, 6, 2) * scale
             # §Q5: AARect::bounding_box ignores the plane (rect.rs:83-89), so the reference's own BVH culls XZ / YZ
