@@ -15,7 +15,9 @@
 #include <cmath>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <queue>
+#include <thread>
 
 namespace rtb200dev {
 namespace {
@@ -25,6 +27,26 @@ const uint32_t LINEAR_MAX = 6;  // groups with at most this many primitives are 
 const uint32_t LEAF_MAX = 2;    // primitives per BVH leaf
 const int N_BINS = 16;
 const int FORCE_MEDIAN_DEPTH = 32;  // bounds the tree depth (traversal stack is 64 entries)
+
+// Splits [0, n) into contiguous blocks over the host threads (large meshes only; the result never depends on
+// the split: every index is written by exactly one thread).
+template <class F>
+void parallel_for(size_t n, F f) {
+    size_t threads = std::thread::hardware_concurrency();
+    if (threads > 16) threads = 16;
+    if (n < 65536 || threads < 2) {
+        f(0, n);
+        return;
+    }
+    const size_t per = (n + threads - 1) / threads;
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < threads; ++t) {
+        const size_t a = t * per, b = std::min(n, a + per);
+        if (a < b) pool.emplace_back([=, &f] { f(a, b); });
+    }
+    f(0, std::min(n, per));
+    for (std::thread &th : pool) th.join();
+}
 
 struct Box {
     double lo[3], hi[3];
@@ -177,10 +199,11 @@ struct Builder {
     std::vector<double> cx[3];
 
     Builder(const std::vector<Box> &b, std::vector<uint32_t> &o) : boxes(b), order(o) {
-        for (int a = 0; a < 3; ++a) {
-            cx[a].resize(b.size());
-            for (size_t i = 0; i < b.size(); ++i) cx[a][i] = 0.5 * (b[i].lo[a] + b[i].hi[a]);
-        }
+        for (int a = 0; a < 3; ++a) cx[a].resize(b.size());
+        parallel_for(b.size(), [&](size_t i0, size_t i1) {
+            for (int a = 0; a < 3; ++a)
+                for (size_t i = i0; i < i1; ++i) cx[a][i] = 0.5 * (b[i].lo[a] + b[i].hi[a]);
+        });
     }
 
     // The two halves of a node own disjoint ranges of order[] and disjoint node ids, so large
@@ -311,12 +334,14 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING") && count > 10000) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[bvh %u] %s %.3f s\n", count, what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     std::vector<Box> boxes(count);
-    for (uint32_t i = 0; i < count; ++i) {
-        boxes[i] = prim_box(out.prims[first + i]);
-        boxes[i].pad();
-    }
     std::vector<uint32_t> order(count);
-    for (uint32_t i = 0; i < count; ++i) order[i] = i;
+    parallel_for(count, [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; ++i) {
+            boxes[i] = prim_box(out.prims[first + i]);
+            boxes[i].pad();
+            order[i] = (uint32_t)i;
+        }
+    });
     lap("boxes");
     Builder b(boxes, order);
     b.nodes.resize(2 * (size_t)count);
@@ -326,9 +351,13 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     b.nodes.resize((size_t)b.next.load());
     out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth.load());
     // permute the primitives into leaf order
-    std::vector<DPrim> tmp(count);
-    for (uint32_t i = 0; i < count; ++i) tmp[i] = out.prims[first + order[i]];
-    std::copy(tmp.begin(), tmp.end(), out.prims.begin() + first);
+    {
+        std::unique_ptr<DPrim[]> tmp(new DPrim[count]);  // not value-initialised: every record is overwritten below
+        parallel_for(count, [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1; ++i) tmp[i] = out.prims[first + order[i]];
+        });
+        parallel_for(count, [&](size_t i0, size_t i1) { std::copy(tmp.get() + i0, tmp.get() + i1, out.prims.begin() + first + i0); });
+    }
     lap("permute");
     // breadth-first emission of the inner nodes
     uint32_t base = (uint32_t)out.nodes.size();
@@ -352,20 +381,22 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
         uint32_t code = ((first + n.first) << 3) | (n.count - 1);
         return (int32_t)~code;
     };
-    for (size_t h = 0; h < bfs.size(); ++h) {
-        const TNode &n = b.nodes[bfs[h]];
-        DBvhNode &dn = out.nodes[base + h];
-        const Box &b0 = b.nodes[n.left].box, &b1 = b.nodes[n.right].box;
-        for (int a = 0; a < 3; ++a) {
-            dn.lo0[a] = f32_down(b0.lo[a]);
-            dn.hi0[a] = f32_up(b0.hi[a]);
-            dn.lo1[a] = f32_down(b1.lo[a]);
-            dn.hi1[a] = f32_up(b1.hi[a]);
+    parallel_for(bfs.size(), [&](size_t h0, size_t h1) {
+        for (size_t h = h0; h < h1; ++h) {
+            const TNode &n = b.nodes[bfs[h]];
+            DBvhNode &dn = out.nodes[base + h];
+            const Box &b0 = b.nodes[n.left].box, &b1 = b.nodes[n.right].box;
+            for (int a = 0; a < 3; ++a) {
+                dn.lo0[a] = f32_down(b0.lo[a]);
+                dn.hi0[a] = f32_up(b0.hi[a]);
+                dn.lo1[a] = f32_down(b1.lo[a]);
+                dn.hi1[a] = f32_up(b1.hi[a]);
+            }
+            dn.child0 = encode(n.left);
+            dn.child1 = encode(n.right);
+            dn.pad0 = dn.pad1 = 0;
         }
-        dn.child0 = encode(n.left);
-        dn.child1 = encode(n.right);
-        dn.pad0 = dn.pad1 = 0;
-    }
+    });
     lap("emit");
     return (int32_t)base;
 }
@@ -542,15 +573,23 @@ bool ref_bvh_order(const RtSceneDesc &d, const std::vector<uint32_t> &hit, doubl
         err = "no object in the scene";  // bvh.rs:55
         return false;
     }
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING") && hit.size() > 10000) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[ref order %zu] %s %.3f s\n", hit.size(), what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
     std::vector<RefBox> boxes(hit.size());
-    for (size_t i = 0; i < hit.size(); ++i)
-        if (!ref_bbox(d, hit[i], t0, t1, boxes[i], 0)) {
-            err = "no bounding box in bvh node";  // bvh.rs:28,61
-            return false;
-        }
+    std::atomic<int> no_box{0};
+    parallel_for(hit.size(), [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; ++i)
+            if (!ref_bbox(d, hit[i], t0, t1, boxes[i], 0)) no_box.store(1);
+    });
+    if (no_box.load()) {
+        err = "no bounding box in bvh node";  // bvh.rs:28,61
+        return false;
+    }
+    lap("boxes");
     RefOrder ro{boxes, std::vector<RefOrder::Item>(hit.size())};
     for (size_t i = 0; i < hit.size(); ++i) ro.items[i] = RefOrder::Item{0.0, (uint32_t)i};
     ro.rec(0, hit.size(), 0);
+    lap("sort");
     if (ro.bad.load()) {
         err = ro.bad.load() == 1 ? "NaN extent in BVH build" : "NaN centroid in BVH build";
         return false;
@@ -616,7 +655,7 @@ struct Walker {
     const void *cached_groups = nullptr;
     uint32_t cached_chain = 0;
     size_t cached_group = 0;
-    void emit(DPrim p, uint32_t node_id) {
+    void group_of_stack() {
         if (!(cache_valid && cached_depth == stack.size() && cached_groups == (const void *)groups)) {
             cached_chain = intern_chain(stack);
             GroupBuild &g = group_for_stack();
@@ -625,6 +664,9 @@ struct Walker {
             cached_groups = (const void *)groups;
             cache_valid = true;
         }
+    }
+    void emit(DPrim p, uint32_t node_id) {
+        group_of_stack();
         p.chain = cached_chain;
         p.node = (int32_t)node_id;
         p.rank = rank++;
@@ -637,37 +679,29 @@ struct Walker {
         (*groups)[cached_group].prims.push_back(p);
     }
     bool cache_valid = false;
-    bool walk(uint32_t id, uint32_t depth) {
-        if (status != RT_OK) return false;
-        if (id >= d.n_nodes) return fail(RT_ERR_BAD_ARGUMENT, "node index out of range");
-        if (depth > d.n_nodes + 1) return fail(RT_ERR_BAD_ARGUMENT, "cycle in scene graph");
-        const RtNode &n = d.nodes[id];
-        DPrim p;
+
+    // The record of a primitive node (everything but chain / node / rank).  false: not a primitive, or a
+    // parameter walk() reports an error for.
+    bool prim_record(const RtNode &n, DPrim &p) const {
         std::memset(&p, 0, sizeof(p));
         p.material = n.material;
+        if (n.material >= d.n_materials) return false;
         switch (n.kind) {
             case RT_NODE_SPHERE:
-                if (!check_material(n.material)) return false;
                 p.kind = PRIM_SPHERE;
                 for (int i = 0; i < 4; ++i) p.d[i] = n.v[i];
-                emit(p, id);
-                break;
+                return true;
             case RT_NODE_MOVING_SPHERE:
-                if (!check_material(n.material)) return false;
                 p.kind = PRIM_MSPHERE;
                 for (int i = 0; i < 9; ++i) p.d[i] = n.v[i];
-                emit(p, id);
-                break;
+                return true;
             case RT_NODE_RECT:
-                if (!check_material(n.material)) return false;
-                if (n.axis > 2) return fail(RT_ERR_BAD_ARGUMENT, "bad rect plane");
+                if (n.axis > 2) return false;
                 p.kind = PRIM_RECT;
                 p.axis = n.axis;
                 for (int i = 0; i < 5; ++i) p.d[i] = n.v[i];
-                emit(p, id);
-                break;
+                return true;
             case RT_NODE_TRIANGLE: {
-                if (!check_material(n.material)) return false;
                 p.kind = PRIM_TRI;
                 // tri.rs:27-28: e1 = v1 - v0, e2 = v2 - v0 ; tri.rs:41: normal = normalize(e1 x e2)
                 double e1[3], e2[3];
@@ -683,13 +717,66 @@ struct Walker {
                 // A degenerate triangle gives a NaN normal in the reference too; keep the
                 // primitive (its hit test uses only v0,e1,e2) but store a zero normal marker.
                 for (int a = 0; a < 3; ++a) p.d[9 + a] = len > 0.0 ? c[a] / len : 0.0;
-                emit(p, id);
-                break;
+                return true;
             }
             case RT_NODE_CUBE:
-                if (!check_material(n.material)) return false;
                 p.kind = PRIM_BOX;
                 for (int i = 0; i < 6; ++i) p.d[i] = n.v[i];
+                return true;
+            default:
+                return false;
+        }
+    }
+
+    // A large BVH over bare primitives (a mesh: main.rs:442) is emitted in parallel: the i-th child in reference
+    // order gets rank0 + i, exactly what the serial walk hands out.  Anything else - a wrapper or container among
+    // the children, a parameter that is an error - returns false with nothing changed, and the serial walk runs
+    // (and reports).
+    bool emit_many(const std::vector<uint32_t> &order) {
+        if (order.size() < 65536 || std::getenv("RTB200_COMPILE_SERIAL")) return false;  // the switch is for the tests
+        group_of_stack();
+        std::vector<DPrim> &dst = (*groups)[cached_group].prims;
+        const size_t base = dst.size();
+        dst.resize(base + order.size());
+        const uint32_t rank0 = rank, chain = cached_chain;
+        std::atomic<int> bad{0};
+        parallel_for(order.size(), [&](size_t i0, size_t i1) {
+            for (size_t i = i0; i < i1 && !bad.load(std::memory_order_relaxed); ++i) {
+                const uint32_t id = order[i];
+                DPrim p;
+                bool ok = id < d.n_nodes && prim_record(d.nodes[id], p);
+                for (int k = 0; ok && k < 12; ++k) ok = p.d[k] == p.d[k];
+                if (!ok) {
+                    bad.store(1);
+                    return;
+                }
+                p.chain = chain;
+                p.node = (int32_t)id;
+                p.rank = rank0 + (uint32_t)i;
+                dst[base + i] = p;
+            }
+        });
+        if (bad.load()) {
+            dst.resize(base);
+            return false;
+        }
+        rank = rank0 + (uint32_t)order.size();
+        return true;
+    }
+    bool walk(uint32_t id, uint32_t depth) {
+        if (status != RT_OK) return false;
+        if (id >= d.n_nodes) return fail(RT_ERR_BAD_ARGUMENT, "node index out of range");
+        if (depth > d.n_nodes + 1) return fail(RT_ERR_BAD_ARGUMENT, "cycle in scene graph");
+        const RtNode &n = d.nodes[id];
+        DPrim p;
+        switch (n.kind) {
+            case RT_NODE_SPHERE:
+            case RT_NODE_MOVING_SPHERE:
+            case RT_NODE_RECT:
+            case RT_NODE_TRIANGLE:
+            case RT_NODE_CUBE:
+                if (!check_material(n.material)) return false;
+                if (!prim_record(n, p)) return fail(RT_ERR_BAD_ARGUMENT, "bad rect plane");
                 emit(p, id);
                 break;
             case RT_NODE_LIST:
@@ -702,6 +789,10 @@ struct Walker {
                     std::string e;
                     if (!ref_bvh_order(d, kids, n.v[0], n.v[1], order, e))
                         return fail(n.count == 0 ? RT_ERR_EMPTY_SCENE : RT_ERR_BAD_ARGUMENT, e);
+                    auto TE = std::chrono::steady_clock::now();
+                    bool many = emit_many(order);
+                    if (getenv("RTB200_COMPILE_TIMING") && order.size() > 10000) fprintf(stderr, "[walk] emit_many(%zu) = %d: %.3f s\n", order.size(), (int)many, std::chrono::duration<double>(std::chrono::steady_clock::now() - TE).count());
+                    if (many) break;
                     for (uint32_t id2 : order)
                         if (!walk(id2, depth + 1)) return false;
                 } else {

@@ -267,6 +267,12 @@ struct TableCheck {
     }
 };
 
+// FNV-1a over every compiled table: two compiles of one description must agree byte for byte (the build is parallel)
+template <class T>
+static void fnv(uint64_t &h, const std::vector<T> &v) {
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(v.data());
+    for (size_t i = 0, n = v.size() * sizeof(T); i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+}
 }  // namespace
 
 #pragma GCC visibility push(default)
@@ -308,6 +314,14 @@ int toh_scene_create(const RtSceneDesc *desc, void **out) {
 }
 
 void toh_scene_destroy(void *h) { delete (HostTables *)h; }
+
+uint64_t toh_tables_hash(void *h) {
+    const CompiledScene &cs = ((HostTables *)h)->cs;
+    uint64_t x = 1469598103934665603ull;
+    fnv(x, cs.prims); fnv(x, cs.ops); fnv(x, cs.chains); fnv(x, cs.groups); fnv(x, cs.nodes); fnv(x, cs.media);
+    fnv(x, cs.lights); fnv(x, cs.materials); fnv(x, cs.textures); fnv(x, cs.images); fnv(x, cs.perlin); fnv(x, cs.texels);
+    return x;
+}
 
 // counts[0..7]: prims, groups, world groups, nodes, media, lights, chains, deepest BVH level
 int toh_check_tables(void *h, uint64_t *counts) {

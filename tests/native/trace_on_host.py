@@ -28,6 +28,8 @@ def _lib():
     lib.toh_scene_destroy.argtypes = [C.c_void_p]
     lib.toh_scene_destroy.restype = None
     lib.toh_check_tables.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.toh_tables_hash.argtypes = [C.c_void_p]
+    lib.toh_tables_hash.restype = C.c_uint64
     lib.toh_trace_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.toh_camera_rays.argtypes = [C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -76,6 +78,11 @@ class CompiledOnHost:
         counts = (C.c_uint64 * 8)()
         _check(lib.toh_check_tables(self._h, counts))
         return dict(zip(TABLE_COUNTS, (int(c) for c in counts)))
+
+    def tables_hash(self):
+        """FNV-1a over every compiled table (padding bytes are zeroed by the compiler, so it is a pure function of the
+        description)."""
+        return int(lib.toh_tables_hash(self._h))
 
     def trace_first_hit(self, rays):
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)

@@ -158,3 +158,47 @@ def test_render_on_host_matches_oracle_image(rt, orc, toh, name):
     lo, _ = comp.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=0, sample_count=3))
     hi, _ = comp.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=3, sample_count=5))
     assert rel_err(lo + hi, img, floor=1e-9).max() < 1e-12
+
+
+def _big_triangle_bvh(rt, n, spoil=None):
+    """n random triangles under one BVH::new (a mesh, main.rs:442) + a light; spoil(b, nodes) may break one."""
+    A = rt._abi
+    rng = np.random.default_rng(11)
+    b = rt.SceneBuilder()
+    m = b.lambertian(b.constant_texture((0.5, 0.5, 0.5)))
+    c = rng.uniform(-50, 50, (n, 3))
+    e = rng.uniform(-1, 1, (n, 2, 3))
+    tris = [b.triangle(c[i], c[i] + e[i, 0], c[i] + e[i, 1], m) for i in range(n)]
+    if spoil:
+        spoil(b, tris)
+    light = b.flip(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 60, b.diffuse_light(b.constant_texture((4, 4, 4)))))
+    return b.finish(b.list([b.bvh(tris), light]), b.list([light]))
+
+
+def test_parallel_compile_equals_serial_compile(rt, orc, toh, monkeypatch):
+    """Large primitive BVHs are emitted, boxed, permuted and encoded by several host threads (compile.cpp:
+    parallel_for, emit_many): the tables are the ones the serial walk produces, byte for byte, and two compiles agree."""
+    sd = _big_triangle_bvh(rt, 70000)
+    a = toh.CompiledOnHost(sd)
+    n = a.check_tables()
+    assert n["prims"] == 70001 and n["nodes"] > 8000
+    b = toh.CompiledOnHost(sd)
+    monkeypatch.setenv("RTB200_COMPILE_SERIAL", "1")
+    c = toh.CompiledOnHost(sd)
+    monkeypatch.delenv("RTB200_COMPILE_SERIAL")
+    assert a.tables_hash() == b.tables_hash() == c.tables_hash()
+
+
+def test_parallel_compile_reports_the_errors_of_the_serial_walk(rt, orc, toh):
+    A = rt._abi
+
+    def bad_material(b, tris):
+        b.nodes[tris[40000]].material = 99
+
+    def nan_vertex(b, tris):
+        b.nodes[tris[12345]].v[4] = float("nan")
+
+    for spoil, word in ((bad_material, "material"), (nan_vertex, "NaN")):
+        with pytest.raises(toh.TraceOnHostError) as ei:
+            toh.CompiledOnHost(_big_triangle_bvh(rt, 70000, spoil))
+        assert ei.value.status == A.RT_ERR_BAD_ARGUMENT and word in str(ei.value)
