@@ -305,7 +305,7 @@ def main():
         # few 100 ms (profiles/r1_h_whole_job_phases_cornell.txt: 150 ms wall for 126 ms on the device).
         try:
             child = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ppm_phase_probe.py"), args.workload,
-                                    str(W), str(H), str(spp), str(depth), "3"], capture_output=True, text=True, timeout=1800)
+                                    str(W), str(H), str(spp), str(depth), "3"], capture_output=True, text=True, timeout=600)
             res = json.loads(child.stdout.strip().splitlines()[-1])
             runs = sorted(float(x) for x in res["ms"])
             med = runs[len(runs) // 2]
