@@ -136,3 +136,35 @@ def test_mirror_and_glass_conserve_a_uniform_environment(rt, orc, toh):
             done = seg < 100  # total internal reflection can trap a path until the depth limit (returns black)
             assert done.mean() > 0.99, name
             assert np.allclose(rgb[done], np.array(expect), rtol=0, atol=1e-12), (name, target)
+
+
+def test_thin_lens_camera_geometry(rt, orc, toh):
+    """camera.rs:19-59: every ray starts on the lens disk (radius aperture/2, perpendicular to the view axis), passes
+    at parameter 1 through the focal plane at focus_dist, inside its pixel's footprint there, and carries a shutter
+    time uniform in [time0, time1)."""
+    lookfrom, lookat = np.array([3.0, 2.0, -7.0]), np.array([0.5, 0.0, 1.0])
+    vfov, aspect, aperture, focus, t0, t1 = 35.0, 1.5, 0.8, 6.5, 0.25, 0.75
+    cam = rt.camera_new(lookfrom, lookat, (0, 1, 0), vfov, aspect, aperture, focus, t0, t1)
+    W, H, n = 90, 60, 40000
+    rng = np.random.default_rng(1)
+    px, py, s = rng.integers(0, W, n, dtype=np.uint32), rng.integers(0, H, n, dtype=np.uint32), np.arange(n, dtype=np.uint32)
+    w = (lookfrom - lookat) / np.linalg.norm(lookfrom - lookat)
+    u = np.cross((0, 1, 0), w)
+    u /= np.linalg.norm(u)
+    v = np.cross(w, u)
+    half_h = focus * math.tan(math.radians(vfov) / 2.0)
+    half_w = aspect * half_h
+    opts = rt.render_opts(seed=4)
+    for name, rays in (("oracle", orc.camera_rays(cam, W, H, opts, px, py, s)), ("device source on host", toh.camera_rays(cam, W, H, opts, px, py, s))):
+        off = rays["origin"] - lookfrom
+        assert np.abs(off @ w).max() < 1e-12, name                       # the lens lies in the plane through lookfrom
+        r = np.hypot(off @ u, off @ v)
+        assert r.max() <= aperture / 2 + 1e-12 and r.max() > 0.49 * aperture, name
+        assert abs((r ** 2).mean() - (aperture / 2) ** 2 / 2) < 0.01 * (aperture / 2) ** 2, name  # uniform on the disk: E r^2 = R^2/2
+        p = rays["origin"] + rays["direction"] - lookfrom                 # parameter 1: the focal plane
+        assert np.abs(p @ w + focus).max() < 1e-10, name
+        sx, sy = (p @ u + half_w) / (2 * half_w), (p @ v + half_h) / (2 * half_h)   # (s, t) of main.rs:817-818
+        assert ((sx * (W - 1) >= px - 1e-9) & (sx * (W - 1) < px + 1 + 1e-9)).all(), name
+        assert ((sy * (H - 1) >= py - 1e-9) & (sy * (H - 1) < py + 1 + 1e-9)).all(), name
+        t = rays["time"]
+        assert t.min() >= t0 and t.max() < t1 and abs(t.mean() - 0.5 * (t0 + t1)) < 0.005, name
