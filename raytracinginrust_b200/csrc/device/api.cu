@@ -129,7 +129,7 @@ bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_dept
     if (flags & RT_FLAG_MEGAKERNEL) return false;
     if (const char *v = std::getenv("RTB200_PIPELINE")) {
         if (!std::strcmp(v, "wavefront")) return true;
-        if (!std::strcmp(v, "megakernel")) return false;
+        if (!std::strcmp(v, "megakernel") || !std::strcmp(v, "sorted")) return false;  // sorted: the experiment of sorted.inl
     }
     return s.wavefront_default;
 }
@@ -367,10 +367,16 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         RtStatus w = run_wavefront(s, pv, cam, P, st);
         if (w != RT_OK) return w;
     } else {
+        // RTB200_PIPELINE=sorted: the experiment of sorted.inl (the megakernel with its lanes re-sorted by hit class
+        // once per segment).  Same work items, planes and reduction; never a default.
+        const char *pipe_env = std::getenv("RTB200_PIPELINE");
+        const bool sorted = pipe_env && !std::strcmp(pipe_env, "sorted") && P.max_depth > 0;
+        const int variant = s.render_variant | (sorted ? 8 : 0);
         int blocks = 0;
-        CU(pv.render_grid_size(s.device, s.render_variant, &blocks));
-        s.render_info = std::string("pipeline=megakernel variant=") + pv.name + " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
-        CU(pv.launch_render(s.ds, cam, P, s.render_variant, blocks, s.planes, s.counters, st));
+        CU(pv.render_grid_size(s.device, variant, &blocks));
+        s.render_info = std::string(sorted ? "pipeline=sorted variant=" : "pipeline=megakernel variant=") + pv.name +
+                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
+        CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));

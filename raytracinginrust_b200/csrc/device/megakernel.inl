@@ -69,8 +69,17 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
 // 2: 12 (40).  Measured per scene class (profiles/r1_e_launch_bounds.md): flat scenes peak at 6, media
 // and triangle-BVH scenes at 8, sphere-BVH scenes (cheap leaves, latency-bound) at 12.
 // variant bit 2: the scene has media (the kernel carries the boundary-query loop of medium.rs)
+// variant bit 3: the experiment of sorted.inl (lanes re-sorted by hit class once per segment; RTB200_PIPELINE=sorted)
 template <class F>
 static cudaError_t with_render_kernel(int variant, F f) {
+    if (variant & 8) {
+        switch (variant & 7) {
+            case 0: return f(render_sorted_kernel<6, false>);
+            case 1: case 2: case 3: return f(render_sorted_kernel<8, false>);
+            case 4: return f(render_sorted_kernel<6, true>);
+            default: return f(render_sorted_kernel<8, true>);
+        }
+    }
     switch (variant & 7) {
         case 0: return f(render_kernel<6, false>);
         case 1: return f(render_kernel<8, false>);

@@ -22,8 +22,9 @@
 namespace rtb200dev {
 inline namespace RT_VARIANT_NS {
 
-#include "megakernel.inl"
 #include "wavefront.inl"
+#include "sorted.inl"
+#include "megakernel.inl"
 
 }  // namespace RT_VARIANT_NS
 

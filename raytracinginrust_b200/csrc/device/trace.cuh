@@ -1187,5 +1187,18 @@ __device__ __forceinline__ bool item_pixel(uint32_t tiles_x, uint32_t width, uin
     return i < width && row < height;
 }
 
+// What a ray found, as the class the sorting stages group by (wavefront.inl: shade tiles; sorted.inl: the lanes of a
+// block): miss, medium, one class per material kind, and the costly materials (Perlin noise, image textures).
+enum : uint32_t { WF_CLS_MISS = 0, WF_CLS_MEDIUM = 1, WF_CLS_MATERIAL = 2, WF_CLS_COSTLY = 7, WF_N_CLASSES = 8, WF_CLS_NONE = 0xFFu };
+RT_DEV uint32_t hit_class(const DScene &sc, uint32_t prim) {
+    if (prim == kNoPrim) return WF_CLS_MISS;
+    if (prim & kMediumFlag) return WF_CLS_MEDIUM;
+    const DMaterial &m = sc.materials[sc.prims[prim].material];
+    if (feat(F_TEX) && m.costly != 0u) return WF_CLS_COSTLY;
+    const uint32_t k = m.kind;  // RtMaterialKind: lambertian, metal, dielectric, light, isotropic | PBR
+    return WF_CLS_MATERIAL + (k < 4u ? k : 4u);
+}
+
+
 }  // namespace RT_VARIANT_NS
 }  // namespace rtb200dev

@@ -40,12 +40,11 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 #endif
 constexpr int kShadeTile = RT_WF_SHADE_TILE * kWfBlock;
 static_assert(kShadeTile <= 4096, "local slot index and class share 16 bits");
-enum : uint32_t { WF_CLS_MISS = 0, WF_CLS_MEDIUM = 1, WF_CLS_MATERIAL = 2, WF_CLS_COSTLY = 7, WF_N_CLASSES = 8, WF_CLS_NONE = 0xFFu };
+// (the classes and hit_class live in trace.cuh: the sorted megakernel shares them)
 // Bits 11-31 of the state word: where the slot's next ray starts, as the index of the primitive it leaves
 // (primitives are stored in BVH leaf order, so close indices are close in space); camera rays get the last key.
 // The simple extend stage sorts its tiles by it (RT_WF_EXT_TILE).  An octant-major key (direction octant, then 32
 // origin bins) was measured too: 134.0 ms against 131.9 ms for the origin alone on the final scene.
-__device__ __forceinline__ uint32_t hit_class(const DScene &sc, uint32_t prim);
 constexpr uint32_t kOriginKeyMax = 0x1FFFFFu;
 __device__ __forceinline__ uint32_t origin_key(uint32_t prim) {
     if (prim == kNoPrim) return kOriginKeyMax;                  // (the path ends in shade)
@@ -54,14 +53,6 @@ __device__ __forceinline__ uint32_t origin_key(uint32_t prim) {
 }
 __device__ __forceinline__ uint32_t live_state(const DScene &sc, uint32_t prim) {
     return WF_LIVE | (hit_class(sc, prim) << 8) | (origin_key(prim) << 11);
-}
-__device__ __forceinline__ uint32_t hit_class(const DScene &sc, uint32_t prim) {
-    if (prim == kNoPrim) return WF_CLS_MISS;
-    if (prim & kMediumFlag) return WF_CLS_MEDIUM;
-    const DMaterial &m = sc.materials[sc.prims[prim].material];
-    if (feat(F_TEX) && m.costly != 0u) return WF_CLS_COSTLY;
-    const uint32_t k = m.kind;  // RtMaterialKind: lambertian, metal, dielectric, light, isotropic | PBR
-    return WF_CLS_MATERIAL + (k < 4u ? k : 4u);
 }
 
 

@@ -55,6 +55,18 @@ using std::min;
 #include "../../raytracinginrust_b200/csrc/device/kernels.h"
 #include "../../raytracinginrust_b200/csrc/device/trace.cuh"
 
+// the work counter of the persistent kernels: lanes are simulated one after the other here
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = *p;
+    *p += v;
+    return old;
+}
+namespace rtb200dev {
+inline namespace RT_VARIANT_NS {
+#include "../../raytracinginrust_b200/csrc/device/sorted_phases.cuh"
+}
+}  // namespace rtb200dev
+
 using namespace rtb200dev;
 
 namespace {
@@ -446,6 +458,92 @@ int toh_render(void *h, const RtCamera *cam, uint32_t width, uint32_t height, ui
             dst[1] = sum.y;
             dst[2] = sum.z;
         }
+    }
+    if (stats) {
+        stats[0] = n_paths;
+        stats[1] = n_rays;
+        stats[2] = n_bad;
+    }
+    return 0;
+}
+
+// sorted.inl: render_sorted_kernel over simulated blocks.  The per-lane phases are the device's own
+// (sorted_phases.cuh); the block-level part - the counting sort by hit class and the barriers - is restated: blocks
+// take turns, one segment at a time, and inside a block the phases run lane after lane.  Work items, planes and the
+// plane reduction are those of api.cu (make_params / reduce_planes_kernel) with `n_chunks` chunks of samples.
+// out: H x W x 3 f64 (plane sums added in chunk order), rows top-down.
+int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                      const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks, double *out, uint64_t *stats) {
+    const HostTables &t = *(HostTables *)h;
+    RenderParams P = params(t, width, height, max_depth, opts);
+    if (P.integrator == RT_INTEGRATOR_HEAD && t.cs.lights.empty()) return fail("HEAD integrator needs a non-empty light list");
+    if (max_depth == 0 || n_chunks == 0 || n_blocks == 0) return fail("bad argument");
+    const uint32_t begin = opts ? opts->sample_begin : 0u;
+    const uint32_t count = (opts && opts->sample_count) ? opts->sample_count : (spp > begin ? spp - begin : 0u);
+    if (count == 0) return fail("empty sample range");
+    P.sample_begin = begin;
+    P.sample_end = begin + count;
+    P.tiles_x = (width + 7) / 8;
+    P.tiles_y = (height + 3) / 4;
+    P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
+    if (n_chunks > count) n_chunks = count;
+    P.chunk_size = (count + n_chunks - 1) / n_chunks;
+    P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
+    P.n_items = P.items_per_chunk * P.n_chunks;
+    constexpr int B = kRenderBlock;
+    struct Block {
+        SortedLane lane[B];
+        SortedShared<B> sh;
+        bool running = true;
+    };
+    std::vector<std::unique_ptr<Block>> blocks;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        blocks.emplace_back(new Block());
+        for (int k = 0; k < B; ++k) sorted_lane_init(blocks.back()->lane[k], P.seed);
+    }
+    const size_t n_values = (size_t)width * height * 3;
+    std::vector<double> planes((size_t)P.n_chunks * n_values, 0.0);
+    unsigned long long counters[kNumCounters] = {0, 0, 0, 0};
+    const bool media = !t.cs.media.empty();
+    for (bool any = true; any;) {
+        any = false;
+        for (auto &bp : blocks) {
+            Block &blk = *bp;
+            if (!blk.running) continue;
+            any = true;
+            uint32_t cls[B];
+            unsigned bin[kSortedClasses] = {0}, pos[B];
+            for (int k = 0; k < B; ++k) {  // phase A + the count
+                cls[k] = media ? sorted_generate_search<true>(t.ds, *cam, P, planes.data(), counters, blk.lane[k])
+                               : sorted_generate_search<false>(t.ds, *cam, P, planes.data(), counters, blk.lane[k]);
+                pos[k] = bin[cls[k]]++;
+            }
+            for (int k = 0; k < B; ++k) {  // phase B
+                unsigned dst = pos[k];
+                for (uint32_t c = 0; c < cls[k]; ++c) dst += bin[c];
+                sorted_file(blk.sh, dst, blk.lane[k]);
+            }
+            if (bin[kSortedIdle] == (unsigned)B) {
+                blk.running = false;
+                continue;
+            }
+            for (int k = 0; k < B; ++k) {  // phase C
+                sorted_pickup(blk.sh, (unsigned)k, P, blk.lane[k]);
+                sorted_shade(t.ds, P, blk.lane[k]);
+            }
+        }
+    }
+    unsigned long long n_paths = 0, n_rays = 0, n_bad = 0;
+    for (auto &bp : blocks)
+        for (int k = 0; k < B; ++k) {
+            n_paths += bp->lane[k].n_paths;
+            n_rays += bp->lane[k].n_rays;
+            n_bad += bp->lane[k].n_bad;
+        }
+    for (size_t k = 0; k < n_values; ++k) {  // reduce_planes_kernel: chunks in ascending order
+        double acc = 0.0;
+        for (uint32_t c = 0; c < P.n_chunks; ++c) acc += planes[(size_t)c * n_values + k];
+        out[k] = acc;
     }
     if (stats) {
         stats[0] = n_paths;

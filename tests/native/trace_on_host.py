@@ -38,6 +38,8 @@ def _lib():
                                       C.c_void_p, C.c_void_p]
     lib.toh_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.toh_render_sorted.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                      C.POINTER(RtRenderOpts), C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -109,6 +111,19 @@ class CompiledOnHost:
         _check(lib.toh_render(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
                               out.ctypes.data_as(C.c_void_p), stats))
         return out, {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
+
+
+def _render_sorted(self, camera, width, height, spp, max_depth, opts, n_chunks=1, n_blocks=2):
+    """render_sorted_kernel (csrc/device/sorted.inl) over simulated blocks of 128 lanes: the device's per-lane phases,
+    the block-level sort restated.  Returns (f64 plane sums HxWx3 rows top-down, {paths, rays, non_finite})."""
+    out = np.zeros((height, width, 3), dtype=np.float64)
+    stats = (C.c_uint64 * 3)()
+    _check(lib.toh_render_sorted(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts), n_chunks, n_blocks,
+                                 out.ctypes.data_as(C.c_void_p), stats))
+    return out, {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
+
+
+CompiledOnHost.render_sorted = _render_sorted
 
 
 def camera_rays(camera, width, height, opts, px, py, sample):

@@ -347,3 +347,20 @@ def test_random_scene_graphs_on_device(rt, orc, seed):
     assert np.array_equal(a, b, equal_nan=True) and sa.rays == sb.rays
     dev.close()
     osc.close()
+
+
+@pytest.mark.skipif(os.environ.get("RTB200_TEST_SORTED") != "1", reason="experimental kernel: set RTB200_TEST_SORTED=1 (run it under a timeout)")
+@pytest.mark.parametrize("name", SCENES)
+def test_sorted_megakernel_equals_megakernel(rt, orc, name, monkeypatch):
+    """csrc/device/sorted.inl (RTB200_PIPELINE=sorted, not a default): bit-identical images and counters."""
+    hs, dev, _ = scenes(rt, orc, name)
+    W, H, spp, depth = 97, 61, 20, 100
+    opts = rt.render_opts(seed=6, integrator=hs.integrator, flags=rt._abi.FLAG_MEGAKERNEL)
+    monkeypatch.delenv("RTB200_PIPELINE", raising=False)
+    a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
+    monkeypatch.setenv("RTB200_PIPELINE", "sorted")
+    b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
+    assert dev.render_info["pipeline"] == "sorted"
+    monkeypatch.delenv("RTB200_PIPELINE", raising=False)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
