@@ -129,7 +129,7 @@ bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_dept
     if (flags & RT_FLAG_MEGAKERNEL) return false;
     if (const char *v = std::getenv("RTB200_PIPELINE")) {
         if (!std::strcmp(v, "wavefront")) return true;
-        if (!std::strcmp(v, "megakernel") || !std::strcmp(v, "sorted")) return false;  // sorted: the experiment of sorted.inl
+        if (!std::strcmp(v, "megakernel") || !std::strcmp(v, "sorted") || !std::strcmp(v, "sorted256")) return false;  // sorted: the experiment of sorted.inl
     }
     return s.wavefront_default;
 }
@@ -370,11 +370,12 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         // RTB200_PIPELINE=sorted: the experiment of sorted.inl (the megakernel with its lanes re-sorted by hit class
         // once per segment).  Same work items, planes and reduction; never a default.
         const char *pipe_env = std::getenv("RTB200_PIPELINE");
-        const bool sorted = pipe_env && !std::strcmp(pipe_env, "sorted") && P.max_depth > 0;
-        const int variant = s.render_variant | (sorted ? 8 : 0);
+        const bool sorted256 = pipe_env && !std::strcmp(pipe_env, "sorted256") && P.max_depth > 0;  // 256-thread blocks
+        const bool sorted = sorted256 || (pipe_env && !std::strcmp(pipe_env, "sorted") && P.max_depth > 0);
+        const int variant = s.render_variant | (sorted256 ? 16 : (sorted ? 8 : 0));
         int blocks = 0;
         CU(pv.render_grid_size(s.device, variant, &blocks));
-        s.render_info = std::string(sorted ? "pipeline=sorted variant=" : "pipeline=megakernel variant=") + pv.name +
+        s.render_info = std::string(sorted256 ? "pipeline=sorted256 variant=" : sorted ? "pipeline=sorted variant=" : "pipeline=megakernel variant=") + pv.name +
                         " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;

@@ -70,30 +70,36 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
 // and triangle-BVH scenes at 8, sphere-BVH scenes (cheap leaves, latency-bound) at 12.
 // variant bit 2: the scene has media (the kernel carries the boundary-query loop of medium.rs)
 // variant bit 3: the experiment of sorted.inl (lanes re-sorted by hit class once per segment; RTB200_PIPELINE=sorted)
+// variant bit 4: ... with 256-thread blocks (RTB200_PIPELINE=sorted256: eight warps to spread ~5 classes over)
+// f(kernel, threads per block)
 template <class F>
 static cudaError_t with_render_kernel(int variant, F f) {
+    if (variant & 16) {
+        if (variant & 4) return f(render_sorted_kernel<256, 3, true>, 256);
+        return f(render_sorted_kernel<256, 3, false>, 256);
+    }
     if (variant & 8) {
         switch (variant & 7) {
-            case 0: return f(render_sorted_kernel<6, false>);
-            case 1: case 2: case 3: return f(render_sorted_kernel<8, false>);
-            case 4: return f(render_sorted_kernel<6, true>);
-            default: return f(render_sorted_kernel<8, true>);
+            case 0: return f(render_sorted_kernel<kRenderBlock, 6, false>, kRenderBlock);
+            case 1: case 2: case 3: return f(render_sorted_kernel<kRenderBlock, 8, false>, kRenderBlock);
+            case 4: return f(render_sorted_kernel<kRenderBlock, 6, true>, kRenderBlock);
+            default: return f(render_sorted_kernel<kRenderBlock, 8, true>, kRenderBlock);
         }
     }
     switch (variant & 7) {
-        case 0: return f(render_kernel<6, false>);
-        case 1: return f(render_kernel<8, false>);
-        case 2: case 3: return f(render_kernel<12, false>);
-        case 4: return f(render_kernel<6, true>);
-        case 5: return f(render_kernel<8, true>);
-        default: return f(render_kernel<12, true>);
+        case 0: return f(render_kernel<6, false>, kRenderBlock);
+        case 1: return f(render_kernel<8, false>, kRenderBlock);
+        case 2: case 3: return f(render_kernel<12, false>, kRenderBlock);
+        case 4: return f(render_kernel<6, true>, kRenderBlock);
+        case 5: return f(render_kernel<8, true>, kRenderBlock);
+        default: return f(render_kernel<12, true>, kRenderBlock);
     }
 }
 static cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
     int sms = 0, per_sm = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    e = with_render_kernel(variant, [&](auto k) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, kRenderBlock, 0); });
+    e = with_render_kernel(variant, [&](auto k, int threads) { return cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0); });
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     *blocks_out = sms * per_sm;  // persistent: exactly one resident wave
@@ -102,8 +108,8 @@ static cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
 
 static cudaError_t launch_render(const DScene &sc, const RtCamera &cam, const RenderParams &P, int variant, int blocks,
                           double *planes, unsigned long long *counters, cudaStream_t stream) {
-    return with_render_kernel(variant, [&](auto k) {
-        k<<<blocks, kRenderBlock, 0, stream>>>(sc, cam, P, planes, counters);
+    return with_render_kernel(variant, [&](auto k, int threads) {
+        k<<<blocks, threads, 0, stream>>>(sc, cam, P, planes, counters);
         return cudaGetLastError();
     });
 }

@@ -15,12 +15,12 @@
 // tier); this file is the block-level part: the sort and the barriers.
 #include "sorted_phases.cuh"
 
-template <int MIN_BLOCKS, bool MEDIA>
-__global__ void __launch_bounds__(kRenderBlock, MIN_BLOCKS)
+template <int BLOCK, int MIN_BLOCKS, bool MEDIA>
+__global__ void __launch_bounds__(BLOCK, MIN_BLOCKS)
 render_sorted_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamera cam,
                      const __grid_constant__ RenderParams P, double *__restrict__ planes,
                      unsigned long long *__restrict__ counters) {
-    __shared__ SortedShared<kRenderBlock> sh;
+    __shared__ SortedShared<BLOCK> sh;
     __shared__ unsigned s_bin[2][kSortedClasses + 1];
     const unsigned tid = threadIdx.x, lane = tid & 31u;
     SortedLane L;
@@ -39,7 +39,7 @@ render_sorted_kernel(const __grid_constant__ DScene sc, const __grid_constant__ 
         unsigned dst = base + (unsigned)__popc(peers & ((1u << lane) - 1u));
         __syncthreads();
         for (uint32_t c = 0; c < cls; ++c) dst += bin[c];
-        const bool all_idle = bin[kSortedIdle] == (unsigned)kRenderBlock;  // block-uniform: every lane reads the same count
+        const bool all_idle = bin[kSortedIdle] == (unsigned)BLOCK;  // block-uniform: every lane reads the same count
         // the other set of bins is idle between these two barriers (read before the second barrier of the previous
         // segment, counted into after the second barrier of this one): clear it for the next segment
         if (tid < (unsigned)kSortedClasses + 1u) s_bin[(iter & 1u) ^ 1u][tid] = 0u;

@@ -358,9 +358,10 @@ def test_sorted_megakernel_equals_megakernel(rt, orc, name, monkeypatch):
     opts = rt.render_opts(seed=6, integrator=hs.integrator, flags=rt._abi.FLAG_MEGAKERNEL)
     monkeypatch.delenv("RTB200_PIPELINE", raising=False)
     a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
-    monkeypatch.setenv("RTB200_PIPELINE", "sorted")
-    b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
-    assert dev.render_info["pipeline"] == "sorted"
-    monkeypatch.delenv("RTB200_PIPELINE", raising=False)
-    assert np.array_equal(a, b, equal_nan=True)
-    assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
+    for pipeline in ("sorted", "sorted256"):
+        monkeypatch.setenv("RTB200_PIPELINE", pipeline)
+        b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
+        assert dev.render_info["pipeline"] == pipeline
+        monkeypatch.delenv("RTB200_PIPELINE", raising=False)
+        assert np.array_equal(a, b, equal_nan=True)
+        assert (sa.paths, sa.rays) == (sb.paths, sb.rays)

@@ -8,7 +8,7 @@ O=gpurun_out
 mkdir -p $O
 RTB200_TEST_SORTED=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -k sorted_megakernel > $O/h_sorted_pytest.log 2>&1
 echo "sorted parity rc=$?"; tail -3 $O/h_sorted_pytest.log
-for P in megakernel sorted; do
+for P in megakernel sorted sorted256; do
   echo "== RTB200_PIPELINE=$P"
   RTB200_PIPELINE=$P timeout 120 python tools/wf_probe2.py cornell:250 cornell_smoke:250 random:128 mesh:16 final:64 2>&1 | tee $O/h_sorted_ab_$P.txt
 done
