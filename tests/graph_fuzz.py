@@ -141,3 +141,63 @@ class GraphMaker:
 def fuzz_camera(rt):
     """Looks at the cube the graphs live in from outside it."""
     return rt.camera_new((0.0, 3.0, -26.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 40.0, 1.0, 0.1, 26.0, 0.0, 1.0)
+
+
+WEIRD_U32 = [0, 1, 2, 3, 5, 7, 0xFFFFFFFF, 0x7FFFFFFF, 0x80000000, 1000, 65535]
+WEIRD_F64 = [float("nan"), float("inf"), -float("inf"), 0.0, -0.0, 1e308, -1e308, 1e-320]
+
+
+def mutated_description(rt, seed):
+    """A random graph with one to five fields of its description overwritten by out-of-range indices, unknown kinds,
+    huge counts, NaN / inf parameters, and now and then a table declared shorter than it is: what a buggy flatten()
+    could hand to rt_scene_create.  The compiler has to answer with a status, whatever it gets."""
+    rng = np.random.default_rng(seed)
+    g = GraphMaker(rt, seed, rich=True)
+    g.make()
+    b = g.b
+    nodes, mats, texs = b.nodes, b.materials, b.textures
+    pick = lambda seq: seq[int(rng.integers(len(seq)))]  # noqa: E731
+    for _ in range(int(rng.integers(1, 6))):
+        what = int(rng.integers(9))
+        if what == 0:
+            pick(nodes).kind = int(pick(WEIRD_U32 + list(range(12))))
+        elif what == 1:
+            pick(nodes).material = int(pick(WEIRD_U32))
+        elif what == 2:
+            pick(nodes).child = int(pick(WEIRD_U32 + [int(rng.integers(len(nodes)))]))
+        elif what == 3:
+            pick(nodes).count = int(pick(WEIRD_U32))
+        elif what == 4:
+            pick(nodes).axis = int(pick(WEIRD_U32))
+        elif what == 5:
+            pick(nodes).v[int(rng.integers(10))] = float(pick(WEIRD_F64))
+        elif what == 6:
+            pick(mats).kind = int(pick(WEIRD_U32))
+        elif what == 7:
+            pick(mats).texture = int(pick(WEIRD_U32))
+        else:
+            t, f = pick(texs), int(rng.integers(3))
+            if f == 0:
+                t.kind = int(pick(WEIRD_U32))
+            elif f == 1:
+                t.a = int(pick(WEIRD_U32 + [int(rng.integers(len(texs)))]))
+            else:
+                t.b = int(pick(WEIRD_U32 + [int(rng.integers(len(texs)))]))
+    if rng.random() < 0.2 and b.child_index:
+        b.child_index[int(rng.integers(len(b.child_index)))] = int(pick(WEIRD_U32 + [int(rng.integers(len(nodes)))]))
+    # make() creates the world list second to last and the light list last
+    world = len(nodes) - 2 if rng.random() < 0.8 else int(pick([int(rng.integers(len(nodes))), 0xFFFFFFFF]))
+    sd = b.finish(world, len(nodes) - 1)
+    if rng.random() < 0.15:
+        d, f = sd.desc, int(rng.integers(5))
+        if f == 0:
+            d.n_nodes = int(rng.integers(0, d.n_nodes + 1))
+        elif f == 1:
+            d.n_child_index = int(rng.integers(0, d.n_child_index + 1))
+        elif f == 2:
+            d.n_materials = int(rng.integers(0, d.n_materials + 1))
+        elif f == 3:
+            d.n_textures = int(rng.integers(0, d.n_textures + 1))
+        else:
+            d.n_perlin = 0
+    return sd

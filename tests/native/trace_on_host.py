@@ -21,8 +21,10 @@ def build():
 
 
 def _lib():
-    build()
-    lib = C.CDLL(LIB_PATH)
+    override = os.environ.get("RTB200_TRACE_ON_HOST_LIB")  # e.g. an -fsanitize=address,undefined build of the same sources
+    if not override:
+        build()
+    lib = C.CDLL(override or LIB_PATH)
     lib.toh_last_error.restype = C.c_char_p
     lib.toh_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(C.c_void_p)]
     lib.toh_scene_destroy.argtypes = [C.c_void_p]
