@@ -282,10 +282,11 @@ Mesh::Mesh(const std::vector<Vec3> &positions, const std::vector<uint32_t> &indi
     }
 }
 
-static int resolve_index(long idx, size_t n_vertices) {
-    // OBJ indices are 1-based; negative indices count from the end.
-    if (idx > 0) return (int)(idx - 1);
-    if (idx < 0) return (int)((long)n_vertices + idx);
+static long resolve_index(long idx, size_t n_vertices) {
+    // OBJ indices are 1-based; negative indices count from the end.  (long all the way: an index beyond 2^31 must
+    // be out of range, not wrap onto a vertex.)
+    if (idx > 0) return idx - 1;
+    if (idx < 0) return (long)n_vertices + idx;
     return -1;
 }
 
@@ -314,7 +315,7 @@ void read_obj_first_model(const std::string &path, std::vector<float> &positions
             std::string tok;
             while (ss >> tok) {
                 long vi = std::strtol(tok.c_str(), nullptr, 10);  // "v", "v/vt", "v//vn", "v/vt/vn"
-                int r = resolve_index(vi, positions.size() / 3);
+                long r = resolve_index(vi, positions.size() / 3);
                 if (r < 0 || (size_t)r >= positions.size() / 3)
                     throw std::runtime_error("Failed to load obj file: face index out of range in " + path);
                 poly.push_back((uint32_t)r);

@@ -113,6 +113,11 @@ def test_obj_loader_rules(rt, tmp_path):
     p.write_text("# c\no first\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 1\nf 1//1 2//1 3//1 4//1\nf -4 -3 -2\n"
                  "o second\nv 5 5 5\nf 1 2 5\n")
     assert rt.obj_triangle_count(str(p)) == (4, 3)
+    for bad in ("v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 4294967297\n",
+                "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 -4\n", "v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2\n", "v 0 0 0\n", ""):
+        p.write_text(bad)
+        with pytest.raises(rt.RtError):  # mesh.rs:40: expect("Failed to load obj file") panics; here a status
+            rt.obj_triangle_count(str(p))
 
 
 def test_construction_seed_is_deterministic(rt):
