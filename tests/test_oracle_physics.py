@@ -168,3 +168,65 @@ def test_thin_lens_camera_geometry(rt, orc, toh):
         assert ((sy * (H - 1) >= py - 1e-9) & (sy * (H - 1) < py + 1 + 1e-9)).all(), name
         t = rays["time"]
         assert t.min() >= t0 and t.max() < t1 and abs(t.mean() - 0.5 * (t0 + t1)) < 0.005, name
+
+
+def _perlin_rs(p, scale, ranvec, px_, py_, pz_):
+    """perlin.rs:77-109 + :39-56 read anew in Python: Hermite smoothing applied in `perlin` AND again in
+    `perlin_interp`, weights from the already smoothed (u, v, w), `floor(x) as usize` saturating negatives to 0."""
+    def usize(x):
+        return 0 if (x != x or x <= 0.0) else int(x)
+    x, y, z = scale * p[0], scale * p[1], scale * p[2]
+    u, v, w = x - math.floor(x), y - math.floor(y), z - math.floor(z)
+    u, v, w = u * u * (3.0 - 2.0 * u), v * v * (3.0 - 2.0 * v), w * w * (3.0 - 2.0 * w)
+    i, j, k = usize(math.floor(x)), usize(math.floor(y)), usize(math.floor(z))
+    uu, vv, ww = u * u * (3.0 - 2.0 * u), v * v * (3.0 - 2.0 * v), w * w * (3.0 - 2.0 * w)
+    accum = 0.0
+    for di in range(2):
+        for dj in range(2):
+            for dk in range(2):
+                c = ranvec[px_[(i + di) & 255] ^ py_[(j + dj) & 255] ^ pz_[(k + dk) & 255]]
+                weight = (u - di, v - dj, w - dk)
+                dot = c[0] * weight[0] + c[1] * weight[1] + c[2] * weight[2]
+                accum += (di * uu + (1 - di) * (1.0 - uu)) * (dj * vv + (1 - dj) * (1.0 - vv)) * (dk * ww + (1 - dk) * (1.0 - ww)) * dot
+    return accum
+
+
+def _noise_texture_rs(p, scale, tables):
+    """texture.rs:77 over perlin.rs:111-121 (turb: seven octaves, the point doubled per octave, abs of the sum)."""
+    accum, weight, q = 0.0, 1.0, list(p)
+    for _ in range(7):
+        accum += weight * _perlin_rs(q, scale, *tables)
+        weight *= 0.5
+        q = [2.0 * c for c in q]
+    return 0.5 * (1.0 + math.sin(scale * p[2] + 10.0 * abs(accum)))
+
+
+def test_marble_texture_against_perlin_rs(rt, orc, toh):
+    """An independent restatement of perlin.rs / texture.rs:77 (above) against the oracle and the device source: a
+    marble sphere in a white furnace under the legacy integrator returns exactly the texture at the hit point."""
+    rng = np.random.default_rng(12)
+    ranvec = rng.uniform(-1, 1, (256, 3)) * rng.uniform(0.1, 1.0, (256, 1))
+    perms = [rng.permutation(256) for _ in range(3)]
+    scale = 1.7
+    b = rt.SceneBuilder()
+    marble = b.lambertian(b.noise_texture(scale, ranvec, *perms))
+    # the centre is chosen so that hit points have negative, small and large coordinates (the usize saturation at 0)
+    ball = b.sphere((1.0, -0.5, 2.0), 3.0, marble)
+    sd = b.finish(b.list([ball]), b.list([]), background=(1.0, 1.0, 1.0))
+    cam = rt.camera_new((1.0, -0.5, -9.0), (1.0, -0.5, 2.0), (0, 1, 0), 30.0, 1.0, 0.0, 9.0)
+    W = H = 48
+    ids = np.random.default_rng(3)
+    n = 600
+    px, py, s = ids.integers(8, 40, n, dtype=np.uint32), ids.integers(8, 40, n, dtype=np.uint32), np.arange(n, dtype=np.uint32)
+    opts = rt.render_opts(seed=21, integrator=rt.INTEGRATOR_LEGACY)
+    rays = orc.camera_rays(cam, W, H, opts, px, py, s)
+    tables = ([tuple(v) for v in ranvec], [int(x) for x in perms[0]], [int(x) for x in perms[1]], [int(x) for x in perms[2]])
+    for name, sc in both(rt, orc, toh, sd):
+        hits = sc.trace_first_hit(rays)
+        assert (hits["node"] >= 0).all(), name
+        assert (hits["position"].min(axis=0) < -0.5).all() and (hits["position"].max(axis=0) > 1).any()
+        rgb, seg = sc.path_radiance(cam, W, H, 50, opts, px, py, s)
+        want = np.array([_noise_texture_rs(p, scale, tables) for p in hits["position"]])
+        assert (seg == 2).all(), name
+        assert np.abs(rgb - want[:, None]).max() < 1e-13, (name, np.abs(rgb - want[:, None]).max())
+        assert want.min() >= 0.0 and want.max() <= 1.0 and want.std() > 0.05  # it is marble, not a constant
