@@ -78,13 +78,9 @@ static cudaError_t with_render_kernel(int variant, F f) {
         if (variant & 4) return f(render_sorted_kernel<256, 3, true>, 256);
         return f(render_sorted_kernel<256, 3, false>, 256);
     }
-    if (variant & 8) {
-        switch (variant & 7) {
-            case 0: return f(render_sorted_kernel<kRenderBlock, 6, false>, kRenderBlock);
-            case 1: case 2: case 3: return f(render_sorted_kernel<kRenderBlock, 8, false>, kRenderBlock);
-            case 4: return f(render_sorted_kernel<kRenderBlock, 6, true>, kRenderBlock);
-            default: return f(render_sorted_kernel<kRenderBlock, 8, true>, kRenderBlock);
-        }
+    if (variant & 8) {  // one register budget (6 blocks of 128 per SM) until the first measurements
+        if (variant & 4) return f(render_sorted_kernel<kRenderBlock, 6, true>, kRenderBlock);
+        return f(render_sorted_kernel<kRenderBlock, 6, false>, kRenderBlock);
     }
     switch (variant & 7) {
         case 0: return f(render_kernel<6, false>, kRenderBlock);
