@@ -294,7 +294,10 @@ uint32_t wf_leave_threshold(const RtScene &s) {
     // lockstep runs those steps with all lanes (measured: profiles/r1_f_pipeline_ab.md).
     uint32_t leave = (s.features & F_TRI) ? 16u : 33u;
     if (const char *v = std::getenv("RTB200_WF_LEAVE")) leave = (uint32_t)std::atoi(v);
-    return leave > 33u ? 33u : leave;  // 0: batch mode (refill only when the whole warp is idle); 33: the simple extend kernel
+    leave = leave > 33u ? 33u : leave;  // 0: batch mode (refill only when the whole warp is idle); 33: the simple extend kernel
+    if (const char *v = std::getenv("RTB200_WF_SHADE"))
+        if (!std::strcmp(v, "perclass")) leave |= kWfPerClassShade;  // experiment: one shade kernel per hit class (wavefront.inl)
+    return leave;
 }
 
 cudaError_t build_wavefront_graph(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P) {
@@ -326,7 +329,8 @@ cudaError_t build_wavefront_graph(RtScene &s, const PipelineVariant &pv, const R
 }
 
 RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
-    const int per_round = kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0);
+    int per_round = kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0);
+    if (wf_leave_threshold(s) & kWfPerClassShade) per_round += 5 + (s.has_media ? 1 : 0) + ((pv.mask & F_TEX) ? 1 : 0);
     CU(pv.wf_launch_init(s.wf, st));
     s.pending_launches += 1;
     const char *g = std::getenv("RTB200_WF_GRAPH");

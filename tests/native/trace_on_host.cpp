@@ -422,6 +422,47 @@ int toh_path_radiance(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
     return 0;
 }
 
+// wavefront.inl, wf_shade_class_kernel (experiment): a path whose every segment is shaded by the path_shade build of
+// its hit class (path_shade_k<kind>: the other materials folded away) - must be the generic path, bit for bit.
+int toh_path_radiance_by_class(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t max_depth,
+                               const RtRenderOpts *opts, const uint32_t *px, const uint32_t *py, const uint32_t *sample,
+                               uint64_t n, double *rgb, uint32_t *segments) {
+    const HostTables &t = *(HostTables *)h;
+    const RenderParams P = params(t, width, height, max_depth, opts);
+    if (P.integrator == RT_INTEGRATOR_HEAD && t.cs.lights.empty()) return fail("HEAD integrator needs a non-empty light list");
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = 0; k < (int64_t)n; ++k) {
+        PathState ps;
+        path_begin(ps, *cam, P.width, P.height, px[k], py[k], sample[k], P.seed, P.max_depth);
+        for (bool alive = ps.depth_left != 0; alive;) {
+            ps.segments += 1;
+            Best win;
+            double closest;
+            world_search<true>(t.ds, ps.ray, ps.rng, win, closest);
+            HitRec rec;
+            const uint32_t cls = hit_class(t.ds, win.prim);
+            const bool hit = cls != WF_CLS_MISS;
+            if (hit) {
+                win.t = closest;
+                if (cls == WF_CLS_MEDIUM) resolve_medium(t.ds, ps.ray, win, closest, rec);
+                else resolve_hit<false>(t.ds, ps.ray, win, closest, rec);
+            }
+            switch (cls) {
+                case WF_CLS_MATERIAL + 0u: alive = path_shade_k<0>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
+                case WF_CLS_MATERIAL + 1u: alive = path_shade_k<1>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
+                case WF_CLS_MATERIAL + 2u: alive = path_shade_k<2>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
+                case WF_CLS_MATERIAL + 3u: alive = path_shade_k<3>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
+                default: alive = path_shade_k<-1>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
+            }
+        }
+        rgb[3 * k] = ps.radiance.x;
+        rgb[3 * k + 1] = ps.radiance.y;
+        rgb[3 * k + 2] = ps.radiance.z;
+        if (segments) segments[k] = ps.segments;
+    }
+    return 0;
+}
+
 // megakernel.inl: what one lane does for its work items, for every pixel; samples [begin, begin+count) are
 // added in sample order in f64 (the device adds per-chunk sums in chunk order: same order, other grouping).
 // out: H x W x 3 f64 sums, rows top-down.  stats: paths, rays, non-finite paths.

@@ -38,6 +38,7 @@ def _lib():
     lib.toh_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.POINTER(RtRenderOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                       C.c_void_p, C.c_void_p]
+    lib.toh_path_radiance_by_class.argtypes = lib.toh_path_radiance.argtypes
     lib.toh_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(C.c_uint64)]
     lib.toh_render_sorted.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
@@ -104,6 +105,18 @@ class CompiledOnHost:
                                      px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
                                      sample.ctypes.data_as(C.c_void_p), n, rgb.ctypes.data_as(C.c_void_p),
                                      seg.ctypes.data_as(C.c_void_p)))
+        return rgb, seg
+
+    def path_radiance_by_class(self, camera, width, height, max_depth, opts, px, py, sample):
+        """path_radiance with every segment shaded by the path_shade build of its hit class (wf_shade_class_kernel)."""
+        px, py, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (px, py, sample))
+        n = px.shape[0]
+        rgb = np.zeros((n, 3), dtype=np.float64)
+        seg = np.zeros(n, dtype=np.uint32)
+        _check(lib.toh_path_radiance_by_class(self._h, C.byref(camera), width, height, max_depth, C.byref(opts),
+                                              px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                              sample.ctypes.data_as(C.c_void_p), n, rgb.ctypes.data_as(C.c_void_p),
+                                              seg.ctypes.data_as(C.c_void_p)))
         return rgb, seg
 
     def render(self, camera, width, height, spp, max_depth, opts):

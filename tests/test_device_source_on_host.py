@@ -223,3 +223,20 @@ def test_sorted_megakernel_phases_on_simulated_blocks(rt, orc, toh, name, shape)
     part, _ = comp.render_sorted(hs.camera, W, H, spp, 100, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=2, sample_count=3), n_chunks=1, n_blocks=1)
     want, _ = comp.render(hs.camera, W, H, spp, 100, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=2, sample_count=3))
     assert np.array_equal(part, want, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", SCENES + EXTRA_SCENES)
+def test_class_specialised_shading_is_the_generic_shading(rt, orc, toh, name):
+    """wavefront.inl, wf_shade_class_kernel (experiment, RTB200_WF_SHADE=perclass): every segment shaded by the
+    path_shade build of its hit class (the other materials folded away at compile time) gives the generic path's
+    radiance and segment count, bit for bit; and the search / resolve split of the wavefront stages (world_search +
+    resolve_hit) equals the megakernel's fused world_hit."""
+    hs, comp, _ = scenes(rt, orc, toh, name)
+    W, H, depth = 96, 96, 100
+    no_lights = name in ("random", "two_spheres", "two_perlin_spheres", "earth")  # HEAD needs a light list (§Q7)
+    for integrator in ((rt.INTEGRATOR_LEGACY,) if no_lights else (rt.INTEGRATOR_HEAD, rt.INTEGRATOR_LEGACY)):
+        opts = rt.render_opts(seed=17, integrator=integrator)
+        px, py, s = random_path_ids(4000, W, H, 128, seed=33)
+        a, sa = comp.path_radiance(hs.camera, W, H, depth, opts, px, py, s)
+        b, sb = comp.path_radiance_by_class(hs.camera, W, H, depth, opts, px, py, s)
+        assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb), (name, integrator)

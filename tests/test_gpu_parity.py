@@ -349,7 +349,11 @@ def test_random_scene_graphs_on_device(rt, orc, seed):
     osc.close()
 
 
-@pytest.mark.skipif(os.environ.get("RTB200_TEST_SORTED") != "1", reason="experimental kernel: set RTB200_TEST_SORTED=1 (run it under a timeout)")
+EXPERIMENTS = pytest.mark.skipif(os.environ.get("RTB200_TEST_EXPERIMENTS") != "1",
+                                 reason="experimental kernels that never ran on a GPU: set RTB200_TEST_EXPERIMENTS=1 and run under a timeout")
+
+
+@EXPERIMENTS
 @pytest.mark.parametrize("name", SCENES)
 def test_sorted_megakernel_equals_megakernel(rt, orc, name, monkeypatch):
     """csrc/device/sorted.inl (RTB200_PIPELINE=sorted, not a default): bit-identical images and counters."""
@@ -365,3 +369,21 @@ def test_sorted_megakernel_equals_megakernel(rt, orc, name, monkeypatch):
         monkeypatch.delenv("RTB200_PIPELINE", raising=False)
         assert np.array_equal(a, b, equal_nan=True)
         assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
+
+
+@EXPERIMENTS
+@pytest.mark.parametrize("name", SCENES + ["earth", "cornell_pbr"])
+def test_per_class_shade_kernels_equal_the_sorted_pass(rt, orc, name, monkeypatch):
+    """csrc/device/wavefront.inl, wf_shade_class_kernel (RTB200_WF_SHADE=perclass, not a default): one shade launch per
+    hit class instead of the one class-sorted pass - bit-identical images and counters."""
+    hs, dev, _ = scenes(rt, orc, name)
+    W, H, spp, depth = 97, 61, 20, 100
+    opts = rt.render_opts(seed=6, integrator=hs.integrator, flags=rt._abi.FLAG_WAVEFRONT)
+    monkeypatch.delenv("RTB200_WF_SHADE", raising=False)
+    a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
+    monkeypatch.setenv("RTB200_WF_SHADE", "perclass")
+    b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
+    monkeypatch.delenv("RTB200_WF_SHADE", raising=False)
+    assert np.array_equal(a, b, equal_nan=True)
+    assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
+    assert sb.kernel_launches > sa.kernel_launches
