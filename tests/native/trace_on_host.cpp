@@ -508,13 +508,20 @@ int toh_render(void *h, const RtCamera *cam, uint32_t width, uint32_t height, ui
     return 0;
 }
 
+}  // extern "C"
+#pragma GCC visibility pop
+
 // sorted.inl: render_sorted_kernel over simulated blocks.  The per-lane phases are the device's own
 // (sorted_phases.cuh); the block-level part - the counting sort by hit class and the barriers - is restated: blocks
 // take turns, one segment at a time, and inside a block the phases run lane after lane.  Work items, planes and the
 // plane reduction are those of api.cu (make_params / reduce_planes_kernel) with `n_chunks` chunks of samples.
 // out: H x W x 3 f64 (plane sums added in chunk order), rows top-down.
-int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-                      const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks, double *out, uint64_t *stats) {
+// stats[0..2]: paths, rays, non-finite paths; stats[3..6]: warp-segments with a live lane, live lanes in them, and the
+// number of (warp, class) pairs with the lanes in the order they arrive (what an unsorted warp shades: one pass per
+// class it holds) and in sorted order - live lanes / pairs is the average width of a shade pass
+template <int B>
+static int render_sorted_sim(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
+                             const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks, double *out, uint64_t *stats) {
     const HostTables &t = *(HostTables *)h;
     RenderParams P = params(t, width, height, max_depth, opts);
     if (P.integrator == RT_INTEGRATOR_HEAD && t.cs.lights.empty()) return fail("HEAD integrator needs a non-empty light list");
@@ -531,7 +538,6 @@ int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
     P.chunk_size = (count + n_chunks - 1) / n_chunks;
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;
-    constexpr int B = kRenderBlock;
     struct Block {
         SortedLane lane[B];
         SortedShared<B> sh;
@@ -545,6 +551,7 @@ int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
     const size_t n_values = (size_t)width * height * 3;
     std::vector<double> planes((size_t)P.n_chunks * n_values, 0.0);
     unsigned long long counters[kNumCounters] = {0, 0, 0, 0};
+    uint64_t purity[4] = {0, 0, 0, 0};
     const bool media = !t.cs.media.empty();
     for (bool any = true; any;) {
         any = false;
@@ -559,10 +566,29 @@ int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
                                : sorted_generate_search<false>(t.ds, *cam, P, planes.data(), counters, blk.lane[k]);
                 pos[k] = bin[cls[k]]++;
             }
+            uint32_t sorted_cls[B];
             for (int k = 0; k < B; ++k) {  // phase B
                 unsigned dst = pos[k];
                 for (uint32_t c = 0; c < cls[k]; ++c) dst += bin[c];
                 sorted_file(blk.sh, dst, blk.lane[k]);
+                sorted_cls[dst] = cls[k];
+            }
+            for (int w = 0; w < B / 32; ++w) {  // purity of the warps before and after the sort
+                unsigned seen_in = 0u, seen_out = 0u, live = 0u;
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t a = cls[w * 32 + l], b = sorted_cls[w * 32 + l];
+                    if (a != kSortedIdle) seen_in |= 1u << a;
+                    if (b != kSortedIdle) {
+                        seen_out |= 1u << b;
+                        live += 1u;
+                    }
+                }
+                if (seen_out) {
+                    purity[0] += 1;
+                    purity[1] += live;
+                    purity[3] += (uint64_t)__builtin_popcount(seen_out);
+                }
+                purity[2] += (uint64_t)__builtin_popcount(seen_in);
             }
             if (bin[kSortedIdle] == (unsigned)B) {
                 blk.running = false;
@@ -590,8 +616,19 @@ int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
         stats[0] = n_paths;
         stats[1] = n_rays;
         stats[2] = n_bad;
+        for (int k = 0; k < 4; ++k) stats[3 + k] = purity[k];
     }
     return 0;
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp,
+                                                             uint32_t max_depth, const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks,
+                                                             uint32_t block, double *out, uint64_t *stats) {
+    if (block == 256) return render_sorted_sim<256>(h, cam, width, height, spp, max_depth, opts, n_chunks, n_blocks, out, stats);
+    if (block == 128) return render_sorted_sim<128>(h, cam, width, height, spp, max_depth, opts, n_chunks, n_blocks, out, stats);
+    return fail("block must be 128 or 256");
 }
 
 }  // extern "C"

@@ -42,7 +42,8 @@ def _lib():
     lib.toh_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(C.c_uint64)]
     lib.toh_render_sorted.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                      C.POINTER(RtRenderOpts), C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(C.c_uint64)]
+                                      C.POINTER(RtRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
+                                      C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -128,14 +129,18 @@ class CompiledOnHost:
         return out, {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
 
 
-def _render_sorted(self, camera, width, height, spp, max_depth, opts, n_chunks=1, n_blocks=2):
-    """render_sorted_kernel (csrc/device/sorted.inl) over simulated blocks of 128 lanes: the device's per-lane phases,
-    the block-level sort restated.  Returns (f64 plane sums HxWx3 rows top-down, {paths, rays, non_finite})."""
+def _render_sorted(self, camera, width, height, spp, max_depth, opts, n_chunks=1, n_blocks=2, block=128, purity=False):
+    """render_sorted_kernel (csrc/device/sorted.inl) over simulated blocks of 128 or 256 lanes: the device's per-lane
+    phases, the block-level sort restated.  Returns (f64 plane sums HxWx3 rows top-down, {paths, rays, non_finite});
+    purity=True adds the width of a shade pass (live lanes per (warp, class) pair) before and after the sort."""
     out = np.zeros((height, width, 3), dtype=np.float64)
-    stats = (C.c_uint64 * 3)()
+    stats = (C.c_uint64 * 7)()
     _check(lib.toh_render_sorted(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts), n_chunks, n_blocks,
-                                 out.ctypes.data_as(C.c_void_p), stats))
-    return out, {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
+                                 block, out.ctypes.data_as(C.c_void_p), stats))
+    res = {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
+    if purity:
+        res.update(warp_segments=int(stats[3]), live_lanes=int(stats[4]), passes_unsorted=int(stats[5]), passes_sorted=int(stats[6]))
+    return out, res
 
 
 CompiledOnHost.render_sorted = _render_sorted
