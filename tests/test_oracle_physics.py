@@ -230,3 +230,48 @@ def test_marble_texture_against_perlin_rs(rt, orc, toh):
         assert (seg == 2).all(), name
         assert np.abs(rgb - want[:, None]).max() < 1e-13, (name, np.abs(rgb - want[:, None]).max())
         assert want.min() >= 0.0 and want.max() <= 1.0 and want.std() > 0.05  # it is marble, not a constant
+
+
+def test_legacy_lambertian_scatter_is_cosine_distributed(rt, orc, toh):
+    """mat.rs:213-223: normal + unit vector is a cosine-weighted direction.  Under the legacy integrator a floor of
+    albedo rho below a square lamp of radiance 1 (black sky) returns rho when the scattered ray reaches the lamp and 0
+    otherwise, so the mean is rho times the cosine-weighted solid angle of the lamp over pi - the form factor again,
+    this time reached by sampling the material instead of the light."""
+    A = rt._abi
+    rho, h, r = 0.7, 1.0, 2.0  # a disc-like square light straight above the shaded point
+    b = rt.SceneBuilder()
+    floor = b.rect(A.PLANE_XZ, -500, 500, -500, 500, 0.0, b.lambertian(b.constant_texture((rho, rho, rho))))
+    lamp = b.flip(b.rect(A.PLANE_XZ, -r, r, -r, r, h, b.diffuse_light(b.constant_texture((1.0, 1.0, 1.0)))))
+    sd = b.finish(b.list([floor, lamp]), b.list([lamp]))
+    cam = rt.camera_new((6.0, 0.5, 0.0), (0.0, 0.0, 0.0), (0, 1, 0), 0.05, 1.0, 0.0, 6.0)
+    n = 80000
+    px, py, smp = centre_paths(n, 3, 3)
+    expect = rho * rect_form_factor(2 * r, 2 * r, h)
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, seg = sc.path_radiance(cam, 3, 3, 50, rt.render_opts(seed=13, integrator=rt.INTEGRATOR_LEGACY), px, py, smp)
+        assert set(np.unique(np.round(rgb[:, 0], 12))) <= {0.0, round(rho, 12)}, name  # hit the lamp or the black sky
+        mean, sem = rgb[:, 0].mean(), rgb[:, 0].std() / math.sqrt(n)
+        print(name, "L = %.5f +- %.5f, closed form %.5f" % (mean, sem, expect))
+        assert abs(mean - expect) < 4.0 * sem, name
+
+
+def test_glass_reflectance_at_normal_incidence_is_schlick_r0(rt, orc, toh):
+    """mat.rs:343-374: a ray along the radius of a glass sphere meets the first interface at normal incidence and is
+    reflected with probability R0 = ((1 - n) / (1 + n))^2 (Schlick at cos = 1, mat.rs:303-307).  A reflected path is
+    the one with two segments (hit, then the sky); every path returns 1 in a white environment (attenuation 1)."""
+    ior = 1.5
+    b = rt.SceneBuilder()
+    ball = b.sphere((0, 0, 0), 1.0, b.dielectric(ior))
+    lamp = b.flip(b.rect(rt._abi.PLANE_XZ, -0.1, 0.1, -0.1, 0.1, 50.0, b.diffuse_light(b.constant_texture((1, 1, 1)))))
+    sd = b.finish(b.list([ball, lamp]), b.list([lamp]), background=(1.0, 1.0, 1.0))
+    cam = rt.camera_new((0.0, 0.0, -6.0), (0.0, 0.0, 0.0), (0, 1, 0), 0.01, 1.0, 0.0, 6.0)
+    n = 60000
+    px, py, smp = centre_paths(n, 3, 3)
+    r0 = ((1.0 - ior) / (1.0 + ior)) ** 2
+    for name, sc in both(rt, orc, toh, sd):
+        rgb, seg = sc.path_radiance(cam, 3, 3, 100, rt.render_opts(seed=19, integrator=rt.INTEGRATOR_HEAD), px, py, smp)
+        reflected = (seg == 2).mean()
+        sem = math.sqrt(r0 * (1 - r0) / n)
+        print(name, "first-interface reflectance %.5f +- %.5f, Schlick R0 %.5f" % (reflected, sem, r0))
+        assert abs(reflected - r0) < 4.0 * sem, name
+        assert np.allclose(rgb, 1.0, atol=1e-12), name  # attenuation 1 everywhere, white environment
