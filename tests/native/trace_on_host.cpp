@@ -119,10 +119,12 @@ Bounds prim_bounds(const DPrim &p) {
         case PRIM_SPHERE:
             for (int a = 0; a < 3; ++a) { b.lo[a] = d[a] - fabs(d[3]); b.hi[a] = d[a] + fabs(d[3]); }
             break;
-        case PRIM_MSPHERE:
+        case PRIM_MSPHERE:  // wherever center(time) puts it for a shutter time in [0, 1] (and at center0 / center1)
             for (int a = 0; a < 3; ++a) {
-                b.lo[a] = fmin(d[a], d[3 + a]) - fabs(d[8]);
-                b.hi[a] = fmax(d[a], d[3 + a]) + fabs(d[8]);
+                const double c_at_0 = d[a] + ((0.0 - d[6]) / (d[7] - d[6])) * (d[3 + a] - d[a]);
+                const double c_at_1 = d[a] + ((1.0 - d[6]) / (d[7] - d[6])) * (d[3 + a] - d[a]);
+                b.lo[a] = fmin(fmin(d[a], d[3 + a]), fmin(c_at_0, c_at_1)) - fabs(d[8]);
+                b.hi[a] = fmax(fmax(d[a], d[3 + a]), fmax(c_at_0, c_at_1)) + fabs(d[8]);
             }
             break;
         case PRIM_RECT: {

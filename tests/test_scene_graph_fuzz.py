@@ -122,3 +122,31 @@ def test_mutated_descriptions_are_answered_with_a_status(rt, orc, toh):
         comp.close()
         accepted += 1
     assert rejected > 40 and accepted > 10
+
+
+def test_moving_sphere_outside_its_time_range_is_not_culled(rt, orc, toh):
+    """sphere.rs:144-146: center(time) is a plain linear map, so a MovingSphere with (time0, time1) = (0.3, 0.7) seen at
+    shutter time 0.95 sits well beyond center1 - outside the box of sphere.rs:191-201.  In a list the reference has no
+    box to cull it with; the compiler's own bounds (group bounds, SAH boxes) have to cover it.  (Found by the random
+    scene graphs: 3 rays of 14 million.)"""
+    A = rt._abi
+    b = rt.SceneBuilder()
+    m = b.lambertian(b.constant_texture((0.5, 0.5, 0.5)))
+    rng = np.random.default_rng(5)
+    kids = [b.moving_sphere((0.0, 0.0, 0.0), (4.0, 0.0, 0.0), 0.3, 0.7, 0.5, m)]
+    kids += [b.sphere(c, 0.3, m) for c in rng.uniform(-6, 6, (20, 3)) + np.array([0.0, 100.0, 0.0])]  # > 8 primitives: a SAH BVH, the moving sphere alone in its leaf
+    light = b.flip(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 30, b.diffuse_light(b.constant_texture((4, 4, 4)))))
+    sd = b.finish(b.list(kids + [light]), b.list([light]))
+    comp, osc = toh.CompiledOnHost(sd), orc.OracleScene(sd)
+    comp.check_tables()
+    n = 3000
+    rays = np.zeros(n, dtype=A.RAY_DTYPE)
+    times = rng.uniform(0.0, 1.0, n)
+    centre_x = 4.0 * (times - 0.3) / 0.4  # from -3 at time 0 to +7 at time 1
+    rays["origin"] = np.stack([centre_x + rng.uniform(-0.3, 0.3, n), np.full(n, -0.0) + rng.uniform(-0.3, 0.3, n), np.full(n, -9.0)], axis=1)
+    rays["direction"] = np.array([0.001, 0.002, 1.0])  # (not axis-parallel: 0 * inf in a slab test only ever accepts)
+    rays["time"] = times
+    hd, ho = comp.trace_first_hit(rays), osc.trace_first_hit(rays)
+    assert (ho["node"] == kids[0]).mean() > 0.95  # the rays are aimed at where the sphere is at their time
+    assert ((times < 0.3) | (times > 0.7)).mean() > 0.5
+    assert np.array_equal(hd["node"], ho["node"]) and np.array_equal(hd["t"], ho["t"])
