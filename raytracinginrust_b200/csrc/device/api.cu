@@ -67,6 +67,7 @@ struct RtScene {
     unsigned *wf_status_host = nullptr;  // pinned
     int sms = 148;
     bool has_media = false;
+    bool shutter_limited = false;  // CompiledScene::shutter_limited
     bool wavefront_default = false;
     std::string render_info;
     cudaGraphExec_t wf_exec = nullptr;  // the wavefront round loop as a CUDA graph (kept alive until the next render)
@@ -193,6 +194,14 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;
     return RT_OK;
+}
+
+// The bounds of a MovingSphere whose centre extrapolates were built for shutter times in [0, 1] (compile.h).
+RtStatus check_shutter(const RtScene &s, const RtCamera &cam) {
+    if (!s.shutter_limited) return RT_OK;
+    const double lo = cam.time0 < cam.time1 ? cam.time0 : cam.time1, hi = cam.time0 < cam.time1 ? cam.time1 : cam.time0;
+    if (lo >= 0.0 && hi <= 1.0) return RT_OK;
+    return fail(RT_ERR_UNSUPPORTED, "a MovingSphere with (time0, time1) != (0, 1) needs a camera shutter inside [0, 1]");
 }
 
 uint32_t scene_features(const CompiledScene &cs) {
@@ -499,6 +508,7 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
     }
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();
+    s->shutter_limited = cs.shutter_limited;
     // Measured per scene class (profiles/r1_e_pipeline_ab.md): the wavefront stages beat the megakernel
     // only where world.hit is a long chain of queries - media over BVH scenes (the Next Week final
     // scene, +21 %); flat scenes and plain BVH scenes run faster with the path state in registers.
@@ -553,6 +563,7 @@ RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t
                           uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream) {
     if (!scene || !camera || !out_rgb_sum_device) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     RtScene &s = *const_cast<RtScene *>(scene);
+    if (check_shutter(s, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     s.t_call0 = now_ms();
     CU(cudaSetDevice(s.device));
     RenderParams P;
@@ -582,6 +593,7 @@ RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width,
                    uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum, RtStats *stats) {
     if (!scene || !camera) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     RtScene &s = *const_cast<RtScene *>(scene);
+    if (check_shutter(s, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     RtStatus st = start_render_own(s, *camera, width, height, spp, max_depth, opts);
     if (st != RT_OK) return st;
     size_t out_bytes = out_rgb_sum ? (size_t)width * height * 3 * sizeof(float) : 0;
@@ -714,6 +726,7 @@ RtStatus rt_render_multi(const RtSceneGroup *group, const RtCamera *camera, uint
     if (count == 0) return fail(RT_ERR_BAD_ARGUMENT, "empty sample range");
     const uint32_t n = (uint32_t)g.scenes.size();
     RtScene &root = *g.scenes[0];
+    if (check_shutter(root, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     const size_t out_bytes = (size_t)width * height * 3 * sizeof(float);
     // every GPU gets its block.  First all parameters and scratch memory, then the launches: those only
     // enqueue, so the GPUs run side by side
@@ -943,6 +956,7 @@ RtStatus rt_path_radiance(const RtScene *scene, const RtCamera *camera, uint32_t
     if (!scene || !camera || (n && (!px || !py || !sample || !rgb))) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     if (n == 0) return RT_OK;
     RtScene &s = *const_cast<RtScene *>(scene);
+    if (check_shutter(s, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     CU(cudaSetDevice(s.device));
     RenderParams P;
     RtStatus st = hook_params(s, width, height, max_depth, opts, true, P);

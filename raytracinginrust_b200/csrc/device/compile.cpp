@@ -1094,6 +1094,8 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         out.media.push_back(dm);
     }
     w.stack.clear();
+    for (const DPrim &pr : out.prims)
+        if (pr.kind == PRIM_MSPHERE && (pr.d[6] != 0.0 || pr.d[7] != 1.0)) out.shutter_limited = true;
     // ---- chains / ops ----
     for (const std::vector<DOp> &ops : w.chain_ops) {
         DChain c{(uint32_t)out.ops.size(), (uint32_t)ops.size()};

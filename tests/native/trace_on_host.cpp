@@ -337,6 +337,9 @@ uint64_t toh_tables_hash(void *h) {
     return x;
 }
 
+// CompiledScene::shutter_limited (compile.h): rt_render* refuse a camera whose shutter leaves [0, 1] for such a scene
+int toh_shutter_limited(void *h) { return ((HostTables *)h)->cs.shutter_limited ? 1 : 0; }
+
 // counts[0..7]: prims, groups, world groups, nodes, media, lights, chains, deepest BVH level
 int toh_check_tables(void *h, uint64_t *counts) {
     const HostTables &t = *(HostTables *)h;

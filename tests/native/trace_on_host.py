@@ -30,6 +30,7 @@ def _lib():
     lib.toh_scene_destroy.argtypes = [C.c_void_p]
     lib.toh_scene_destroy.restype = None
     lib.toh_check_tables.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    lib.toh_shutter_limited.argtypes = [C.c_void_p]
     lib.toh_tables_hash.argtypes = [C.c_void_p]
     lib.toh_tables_hash.restype = C.c_uint64
     lib.toh_trace_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
@@ -84,6 +85,10 @@ class CompiledOnHost:
         counts = (C.c_uint64 * 8)()
         _check(lib.toh_check_tables(self._h, counts))
         return dict(zip(TABLE_COUNTS, (int(c) for c in counts)))
+
+    @property
+    def shutter_limited(self):
+        return bool(lib.toh_shutter_limited(self._h))
 
     def tables_hash(self):
         """FNV-1a over every compiled table (padding bytes are zeroed by the compiler, so it is a pure function of the

@@ -387,3 +387,22 @@ def test_per_class_shade_kernels_equal_the_sorted_pass(rt, orc, name, monkeypatc
     assert np.array_equal(a, b, equal_nan=True)
     assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
     assert sb.kernel_launches > sa.kernel_launches
+
+
+def test_shutter_outside_unit_range_is_refused_for_extrapolating_spheres(rt, orc):
+    """A MovingSphere with (time0, time1) != (0, 1) extrapolates (sphere.rs:144-146); the compiled bounds cover shutter
+    times in [0, 1], so another shutter is refused (RT_ERR_UNSUPPORTED) instead of culling the sphere wrongly."""
+    A = rt._abi
+    b = rt.SceneBuilder()
+    m = b.lambertian(b.constant_texture((0.5, 0.5, 0.5)))
+    ball = b.moving_sphere((0.0, 0.0, 0.0), (4.0, 0.0, 0.0), 0.3, 0.7, 0.5, m)
+    light = b.flip(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 30, b.diffuse_light(b.constant_texture((4, 4, 4)))))
+    dev = rt.DeviceScene(b.finish(b.list([ball, light]), b.list([light])), device=0)
+    ok_cam = rt.camera_new((0, 0, -9), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 9.0, 0.0, 1.0)
+    bad_cam = rt.camera_new((0, 0, -9), (0, 0, 0), (0, 1, 0), 40.0, 1.0, 0.0, 9.0, 0.0, 2.0)
+    img, _ = dev.render(ok_cam, 16, 16, 2, 10, rt.render_opts(seed=1))
+    assert np.isfinite(img).all()
+    with pytest.raises(rt.RtError) as ei:
+        dev.render(bad_cam, 16, 16, 2, 10, rt.render_opts(seed=1))
+    assert ei.value.status == A.RT_ERR_UNSUPPORTED and "shutter" in str(ei.value)
+    dev.close()

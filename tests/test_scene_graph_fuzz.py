@@ -139,6 +139,12 @@ def test_moving_sphere_outside_its_time_range_is_not_culled(rt, orc, toh):
     sd = b.finish(b.list(kids + [light]), b.list([light]))
     comp, osc = toh.CompiledOnHost(sd), orc.OracleScene(sd)
     comp.check_tables()
+    # the bounds are built for shutter times in [0, 1]: rt_render* refuse another shutter for such a scene (api.cu:
+    # check_shutter), and no scene of main.rs is one
+    from util import host_scene
+    assert comp.shutter_limited
+    assert not toh.CompiledOnHost(host_scene(rt, "final").scene_desc).shutter_limited
+    assert not toh.CompiledOnHost(host_scene(rt, "random").scene_desc).shutter_limited
     n = 3000
     rays = np.zeros(n, dtype=A.RAY_DTYPE)
     times = rng.uniform(0.0, 1.0, n)
