@@ -258,7 +258,10 @@ uint64_t rt_scene_device_bytes(const RtScene *scene);
  * (first row is j = H-1, src/main.rs:772), columns left to right, RGB
  * interleaved.  The host divides by spp, applies format_color
  * (src/vec.rs:125-131) and writes the PPM.  out_rgb_sum may be NULL: the image then
- * only stays resident on the device, for rt_encode_rgb8 / rt_encode_ppm. */
+ * only stays resident on the device, for rt_encode_rgb8 / rt_encode_ppm.
+ * RT_ERR_UNSUPPORTED: the scene has a MovingSphere with (time0, time1) != (0, 1) - its
+ * centre extrapolates, src/sphere.rs:144-146 - and the camera's shutter leaves [0, 1],
+ * the range the culling bounds were built for (every camera of src/main.rs is 0..1). */
 RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width, uint32_t height,
                    uint32_t spp, uint32_t max_depth, const RtRenderOpts *opts,
                    float *out_rgb_sum, RtStats *stats);
