@@ -785,11 +785,45 @@ struct Walker {
         const RtNode &n = d.nodes[id];
         DPrim p;
         switch (n.kind) {
+            case RT_NODE_CUBE: {
+                // Cube::new (cube.rs:14-30) is six AARects, and a rect whose range is inverted never passes
+                // `a < a0 || a > a1` (rect.rs:55).  A cube with min > max on one axis therefore shows only the two
+                // faces perpendicular to that axis, and none with two inverted axes; the slab test of the device's
+                // box primitive would show a whole box.  (Found by fuzzing degenerate parameters; such a cube under a
+                // BVH is never entered at all - ref_bvh_order.)
+                if (!check_material(n.material)) return false;
+                int inverted = 0, axis = -1;
+                for (int a = 0; a < 3; ++a)
+                    if (n.v[a] > n.v[3 + a]) {
+                        ++inverted;
+                        axis = a;
+                    }
+                if (inverted == 0) {
+                    if (!prim_record(n, p)) return fail(RT_ERR_BAD_ARGUMENT, "bad cube");
+                    emit(p, id);
+                } else if (inverted == 1) {
+                    // the two faces at max[axis] and min[axis], in the order of cube.rs (the parity hook reports
+                    // face 0 for them: DPrim has no face field for a rect)
+                    const int a0 = axis == 0 ? 1 : 0, a1 = axis == 2 ? 1 : 2;  // x: (y, z)  y: (x, z)  z: (x, y)
+                    for (int side = 0; side < 2; ++side) {
+                        std::memset(&p, 0, sizeof(p));
+                        p.material = n.material;
+                        p.kind = PRIM_RECT;
+                        p.axis = axis == 0 ? RT_PLANE_YZ : (axis == 1 ? RT_PLANE_XZ : RT_PLANE_XY);
+                        p.d[0] = n.v[a0];
+                        p.d[1] = n.v[3 + a0];
+                        p.d[2] = n.v[a1];
+                        p.d[3] = n.v[3 + a1];
+                        p.d[4] = side == 0 ? n.v[3 + axis] : n.v[axis];
+                        emit(p, id);
+                    }
+                }
+                break;
+            }
             case RT_NODE_SPHERE:
             case RT_NODE_MOVING_SPHERE:
             case RT_NODE_RECT:
             case RT_NODE_TRIANGLE:
-            case RT_NODE_CUBE:
                 if (!check_material(n.material)) return false;
                 if (!prim_record(n, p)) return fail(RT_ERR_BAD_ARGUMENT, "bad rect plane");
                 emit(p, id);

@@ -156,3 +156,33 @@ def test_moving_sphere_outside_its_time_range_is_not_culled(rt, orc, toh):
     assert (ho["node"] == kids[0]).mean() > 0.95  # the rays are aimed at where the sphere is at their time
     assert ((times < 0.3) | (times > 0.7)).mean() > 0.5
     assert np.array_equal(hd["node"], ho["node"]) and np.array_equal(hd["t"], ho["t"])
+
+
+def test_inverted_cubes_show_what_six_rects_show(rt, orc, toh):
+    """cube.rs:14-30 builds six AARects, and a rect with an inverted range never passes `a < a0 || a > a1` (rect.rs:55):
+    a cube with min > max on one axis shows two faces, on two or three axes nothing.  The compiler turns such a cube
+    into those rects (or nothing) instead of a box primitive: same object, t, normal and uv as the reference; only the
+    parity hook's face number is lost (0).  Found by fuzzing degenerate parameters."""
+    A = rt._abi
+    seen_inverted = [0, 0, 0, 0]
+    for seed in range(12):
+        rng = np.random.default_rng(100 + seed)
+        b = rt.SceneBuilder()
+        m = b.lambertian(b.constant_texture((0.5, 0.5, 0.5)))
+        kids = []
+        for c in rng.uniform(-5, 5, (int(rng.integers(3, 14)), 3)):
+            e = rng.uniform(-2, 2, 3)
+            seen_inverted[int((e < 0).sum())] += 1
+            kids.append(b.cube(c, c + e, m))
+        light = b.flip(b.rect(A.PLANE_XZ, -1, 1, -1, 1, 9, b.diffuse_light(b.constant_texture((4, 4, 4)))))
+        sd = b.finish(b.list(kids + [light]), b.list([light]))
+        comp, osc = toh.CompiledOnHost(sd), orc.OracleScene(sd)
+        comp.check_tables()
+        n = 20000
+        rays = np.zeros(n, dtype=A.RAY_DTYPE)
+        o = rng.uniform(-9, 9, (n, 3))
+        rays["origin"], rays["direction"] = o, rng.uniform(-5, 5, (n, 3)) - o
+        hd, ho = comp.trace_first_hit(rays), osc.trace_first_hit(rays)
+        for f in ("node", "t", "normal", "front_face", "u", "v", "material"):
+            assert np.array_equal(hd[f], ho[f]), (seed, f)
+    assert min(seen_inverted) > 5
