@@ -566,15 +566,34 @@ static int render_sorted_sim(void *h, const RtCamera *cam, uint32_t width, uint3
             any = true;
             uint32_t cls[B];
             unsigned bin[kSortedClasses] = {0}, pos[B];
-            for (int k = 0; k < B; ++k) {  // phase A + the count
+            for (int k = 0; k < B; ++k)  // phase A
                 cls[k] = media ? sorted_generate_search<true>(t.ds, *cam, P, planes.data(), counters, blk.lane[k])
                                : sorted_generate_search<false>(t.ds, *cam, P, planes.data(), counters, blk.lane[k]);
-                pos[k] = bin[cls[k]]++;
+            // the count, as the kernel does it: per warp, __match_any_sync -> the first lane of every class adds the
+            // class's lane count to the bin once, every lane takes base + its rank among its peers.  The warps arrive
+            // in some order at the shared atomics: last warp first here.
+            for (int w = B / 32 - 1; w >= 0; --w) {
+                unsigned base_of_class[kSortedClasses];
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t c = cls[w * 32 + l];
+                    unsigned peers = 0u;
+                    for (int m = 0; m < 32; ++m)
+                        if (cls[w * 32 + m] == c) peers |= 1u << m;
+                    const unsigned leader = (unsigned)__builtin_ffs((int)peers) - 1u;
+                    if ((unsigned)l == leader) {
+                        base_of_class[c] = bin[c];
+                        bin[c] += (unsigned)__builtin_popcount(peers);
+                    }
+                    pos[w * 32 + l] = base_of_class[c] + (unsigned)__builtin_popcount(peers & ((1u << l) - 1u));
+                }
             }
             uint32_t sorted_cls[B];
+            bool taken[B] = {false};
             for (int k = 0; k < B; ++k) {  // phase B
                 unsigned dst = pos[k];
                 for (uint32_t c = 0; c < cls[k]; ++c) dst += bin[c];
+                if (dst >= (unsigned)B || taken[dst]) return fail("the sort is not a permutation");
+                taken[dst] = true;
                 sorted_file(blk.sh, dst, blk.lane[k]);
                 sorted_cls[dst] = cls[k];
             }
