@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call of round 1-g: tests, smoke, bench, smem-stack A/B, ncu of the wavefront stages.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 nvidia-smi -L > $O/g_gpus.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU call of round 1-g: the single-process multi-GPU entry over real NVLink peers, next to the torchrun + NCCL path.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 nvidia-smi -L > $O/g2_gpus.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # 2-GPU diagnosis of rt_render_multi on the mesh scene (did not scale in round_g2): host timeline and per-device times
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 RTB200_MULTI_TIMING=1 timeout 300 python tools/multi_probe.py mesh:32 cornell:1000 > $O/g3_probe_peer.jsonl 2> $O/g3_probe_peer.err; echo "rc=$?"

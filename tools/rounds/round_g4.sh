@@ -1,7 +1,7 @@
 #!/bin/bash
 # 1-GPU call: traversal inner-loop break A/B, pipeline A/B on the mesh scene, kernel times of the output stage,
 # steady-state captures of the wavefront stages and of the mesh megakernel.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 for v in base ib8 ib16 ib24 ndiv; do

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 1-GPU call: instruction-fetch experiment on the megakernel: all warps of a block start a segment together
 # (RT_MK_SYNC) at several block sizes.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 rm -f $O/g5_ab.txt

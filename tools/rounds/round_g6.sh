@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1-GPU call: class-sorted shade tiles (wavefront) against the previous shade pass; images must keep their CRC.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 rm -f $O/g6_ab.txt

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 timeout 400 python tools/wf_probe2.py final:2048 cornell:1000 cornell_smoke:1000 random:800 mesh:64 > $O/g7_newchunks.txt 2>&1

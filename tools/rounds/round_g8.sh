@@ -1,6 +1,6 @@
 #!/bin/bash
 # 1-GPU call: validation of the sorted wavefront stages: full GPU suite, bench lines, steady-state captures.
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 RTB200_PIPELINE=wavefront timeout 200 python tools/wf_probe2.py mesh:16 > $O/g8_mesh_wavefront.txt 2>&1

@@ -1,6 +1,6 @@
 #!/bin/bash
 # final validation of round 1-g: GPU suite, smoke, bench lines (Cornell default, final, mesh)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 timeout 900 python -m pytest tests -x -q -m gpu > $O/g9_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 $O/g9_pytest.log
