@@ -130,7 +130,7 @@ bool use_wavefront(const RtScene &s, const RtRenderOpts *opts, uint32_t max_dept
     if (flags & RT_FLAG_MEGAKERNEL) return false;
     if (const char *v = std::getenv("RTB200_PIPELINE")) {
         if (!std::strcmp(v, "wavefront")) return true;
-        if (!std::strcmp(v, "megakernel") || !std::strcmp(v, "sorted") || !std::strcmp(v, "sorted256")) return false;  // sorted: the experiment of sorted.inl
+        if (!std::strcmp(v, "megakernel")) return false;
     }
     return s.wavefront_default;
 }
@@ -304,8 +304,6 @@ uint32_t wf_leave_threshold(const RtScene &s) {
     uint32_t leave = (s.features & F_TRI) ? 16u : 33u;
     if (const char *v = std::getenv("RTB200_WF_LEAVE")) leave = (uint32_t)std::atoi(v);
     leave = leave > 33u ? 33u : leave;  // 0: batch mode (refill only when the whole warp is idle); 33: the simple extend kernel
-    if (const char *v = std::getenv("RTB200_WF_SHADE"))
-        if (!std::strcmp(v, "perclass")) leave |= kWfPerClassShade;  // experiment: one shade kernel per hit class (wavefront.inl)
     return leave;
 }
 
@@ -339,7 +337,6 @@ cudaError_t build_wavefront_graph(RtScene &s, const PipelineVariant &pv, const R
 
 RtStatus run_wavefront(RtScene &s, const PipelineVariant &pv, const RtCamera &cam, const RenderParams &P, cudaStream_t st) {
     int per_round = kWfLaunchesPerRound + ((pv.mask & F_TEX) ? 1 : 0);
-    if (wf_leave_threshold(s) & kWfPerClassShade) per_round += 5 + (s.has_media ? 1 : 0) + ((pv.mask & F_TEX) ? 1 : 0);
     CU(pv.wf_launch_init(s.wf, st));
     s.pending_launches += 1;
     const char *g = std::getenv("RTB200_WF_GRAPH");
@@ -380,15 +377,10 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         RtStatus w = run_wavefront(s, pv, cam, P, st);
         if (w != RT_OK) return w;
     } else {
-        // RTB200_PIPELINE=sorted: the experiment of sorted.inl (the megakernel with its lanes re-sorted by hit class
-        // once per segment).  Same work items, planes and reduction; never a default.
-        const char *pipe_env = std::getenv("RTB200_PIPELINE");
-        const bool sorted256 = pipe_env && !std::strcmp(pipe_env, "sorted256") && P.max_depth > 0;  // 256-thread blocks
-        const bool sorted = sorted256 || (pipe_env && !std::strcmp(pipe_env, "sorted") && P.max_depth > 0);
-        const int variant = s.render_variant | (sorted256 ? 16 : (sorted ? 8 : 0));
+        const int variant = s.render_variant;
         int blocks = 0;
         CU(pv.render_grid_size(s.device, variant, &blocks));
-        s.render_info = std::string(sorted256 ? "pipeline=sorted256 variant=" : sorted ? "pipeline=sorted variant=" : "pipeline=megakernel variant=") + pv.name +
+        s.render_info = std::string("pipeline=megakernel variant=") + pv.name +
                         " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;

@@ -69,19 +69,9 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
 // 2: 12 (40).  Measured per scene class (profiles/r1_e_launch_bounds.md): flat scenes peak at 6, media
 // and triangle-BVH scenes at 8, sphere-BVH scenes (cheap leaves, latency-bound) at 12.
 // variant bit 2: the scene has media (the kernel carries the boundary-query loop of medium.rs)
-// variant bit 3: the experiment of sorted.inl (lanes re-sorted by hit class once per segment; RTB200_PIPELINE=sorted)
-// variant bit 4: ... with 256-thread blocks (RTB200_PIPELINE=sorted256: eight warps to spread ~5 classes over)
 // f(kernel, threads per block)
 template <class F>
 static cudaError_t with_render_kernel(int variant, F f) {
-    if (variant & 16) {
-        if (variant & 4) return f(render_sorted_kernel<256, 3, true>, 256);
-        return f(render_sorted_kernel<256, 3, false>, 256);
-    }
-    if (variant & 8) {  // one register budget (6 blocks of 128 per SM) until the first measurements
-        if (variant & 4) return f(render_sorted_kernel<kRenderBlock, 6, true>, kRenderBlock);
-        return f(render_sorted_kernel<kRenderBlock, 6, false>, kRenderBlock);
-    }
     switch (variant & 7) {
         case 0: return f(render_kernel<6, false>, kRenderBlock);
         case 1: return f(render_kernel<8, false>, kRenderBlock);

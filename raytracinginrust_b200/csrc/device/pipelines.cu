@@ -23,7 +23,6 @@ namespace rtb200dev {
 inline namespace RT_VARIANT_NS {
 
 #include "wavefront.inl"
-#include "sorted.inl"
 #include "megakernel.inl"
 
 }  // namespace RT_VARIANT_NS

@@ -1067,10 +1067,7 @@ RT_DEV bool path_step(const DScene &sc, PathState &ps, uint32_t integrator, uint
 }
 
 // Everything ray_color does after world.hit returned (main.rs:62-119).
-// ONLY_KIND >= 0: the caller knows the material kind of what was hit (the per-class shade kernels of the wavefront
-// pipeline sort by it), so the other materials' code folds away; -1: read it from the material.
-template <int ONLY_KIND>
-RT_DEV bool path_shade_k(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags) {
+RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags) {
     // Every factor of the recursion L = emitted + f * L_next is zero-emission until the path ends
     // (only DiffuseLight emits, and it never scatters), so the camera ray's radiance is written
     // once, by the last segment: 0 + beta * emitted.  It is not carried from segment to segment.
@@ -1080,7 +1077,7 @@ RT_DEV bool path_shade_k(const DScene &sc, PathState &ps, bool hit, const HitRec
         return false;
     }
     const DMaterial &m = sc.materials[rec.material];
-    uint32_t mkind = ONLY_KIND >= 0 ? (uint32_t)ONLY_KIND : m.kind;
+    uint32_t mkind = m.kind;
     // Material::emitted (mat.rs:70-72, :395-401)
     if (mkind == RT_MAT_DIFFUSE_LIGHT) {
         // DiffuseLight never scatters (mat.rs:391-393 / default scatter_mc_method): return emitted
@@ -1150,10 +1147,6 @@ RT_DEV bool path_shade_k(const DScene &sc, PathState &ps, bool hit, const HitRec
         return false;  // §Q11: the reference keeps tracing; the contribution is zero either way
     if (ps.depth_left == 0) return path_end_black(ps);  // the next call is ray_color(depth = 0): black (main.rs:42-45)
     return true;
-}
-
-RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &rec, uint32_t integrator, uint32_t flags) {
-    return path_shade_k<-1>(sc, ps, hit, rec, integrator, flags);
 }
 
 // The sample closure of main.rs:811-829: pixel jitter + Camera::get_ray (camera.rs:51-59)

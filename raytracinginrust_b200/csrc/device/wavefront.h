@@ -69,8 +69,5 @@ struct WfPool {
 
 // (launchers: per pipeline variant, see variants.h)
 constexpr int kWfLaunchesPerRound = 4;  // + 1 (shade pass 2) in the variants with textures
-// wf_launch_round's leave_threshold | kWfPerClassShade: the per-class shade kernels (experiment, RTB200_WF_SHADE=perclass)
-// instead of the one sorted pass: 6 launches (+1 with media, +1 with textures) where the sorted pass is 1
-constexpr uint32_t kWfPerClassShade = 0x10000u;
 
 }  // namespace rtb200dev

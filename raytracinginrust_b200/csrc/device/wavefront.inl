@@ -120,10 +120,7 @@ __global__ void wf_init_kernel(const __grid_constant__ WfPool pool) {
 // their own that pass 1 does not shade but COMPACTS into a queue (__ballot_sync/__popc, one
 // atomic per warp that has any); pass 2 walks that queue, so those paths fill whole warps from all
 // over the pool, not just from one tile.
-// CLS: the hit class the caller sorted by (WF_CLS_NONE: any) - a compile-time class folds the other materials,
-// the miss branch and the medium branch away (the per-class shade kernels below).
-template <uint32_t CLS>
-__device__ __forceinline__ void shade_slot_c(const DScene &sc, const RenderParams &P, const WfPool &pool, uint32_t slot,
+__device__ __forceinline__ void shade_slot(const DScene &sc, const RenderParams &P, const WfPool &pool, uint32_t slot,
                                              const uint4 u3, const uint4 u6, bool &alive, bool &bad) {
     const double2 *u = slot_d2(pool, slot);
     const double2 u0 = u[0], u1 = u[1], u2 = u[2], u4 = u[4];
@@ -140,17 +137,13 @@ __device__ __forceinline__ void shade_slot_c(const DScene &sc, const RenderParam
     const uint32_t prim = u6.x;
     const double t = __hiloint2double((int)u6.w, (int)u6.z);
     HitRec rec;
-    const bool hit = CLS == WF_CLS_NONE ? prim != kNoPrim : CLS != WF_CLS_MISS;
+    const bool hit = prim != kNoPrim;
     if (hit) {
         Best win{t, prim, 0u, (int)u6.y};
-        const bool medium = CLS == WF_CLS_NONE ? (prim & kMediumFlag) != 0u : CLS == WF_CLS_MEDIUM;
-        if (medium) resolve_medium(sc, ps.ray, win, t, rec);
+        if (prim & kMediumFlag) resolve_medium(sc, ps.ray, win, t, rec);
         else resolve_hit<false>(sc, ps.ray, win, t, rec);
     }
-    // classes WF_CLS_MATERIAL + 0..3 are one material kind each (hit_class); a medium carries whatever material its
-    // node names (the reference always builds Isotropic, the boundary does not insist), so that one stays generic
-    constexpr int kind = (CLS >= WF_CLS_MATERIAL && CLS < WF_CLS_MATERIAL + 4u) ? (int)(CLS - WF_CLS_MATERIAL) : -1;
-    alive = path_shade_k<kind>(sc, ps, hit, rec, P.integrator, P.flags);
+    alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
     double2 *w = slot_d2w(pool, slot);
     if (alive) {
         w[0] = make_double2(ps.ray.o.x, ps.ray.o.y);
@@ -172,11 +165,6 @@ __device__ __forceinline__ void shade_slot_c(const DScene &sc, const RenderParam
             pool.sum[slot] = s;
         }
     }
-}
-
-__device__ __forceinline__ void shade_slot(const DScene &sc, const RenderParams &P, const WfPool &pool, uint32_t slot,
-                                           const uint4 u3, const uint4 u6, bool &alive, bool &bad) {
-    shade_slot_c<WF_CLS_NONE>(sc, P, pool, slot, u3, u6, alive, bad);
 }
 
 __global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
@@ -256,73 +244,6 @@ wf_shade_kernel(const __grid_constant__ DScene sc, const __grid_constant__ Rende
     if (__syncthreads_or(bad_n != 0u)) {
         const unsigned nb = __reduce_add_sync(kFull, bad_n);
         if (lane == 0u && nb) atomicAdd(&counters[kCounterNonFinite], (unsigned long long)nb);
-    }
-}
-
-// EXPERIMENT (RTB200_WF_SHADE=perclass; not a default until measured on the B200): one shade kernel per hit class.
-// The sorted pass above runs ~23 lanes wide but only a fifth of its issue slots are busy: its largest stall is
-// instruction fetch - 108 KB of SASS with every material in it, and the warps of a block walk different parts of it
-// (profiles/r1_g_sorted_stages.md).  Here each launch carries ONE class's code: a block reads the state words of its
-// tile (4 bytes per slot, again for every class), compacts the slots of its class in shared memory and shades them;
-// shade leaves the class bits of a slot alone, so a slot shaded by one launch is not touched by the next.
-// CLS == WF_CLS_COSTLY only files the slots in the deferred queue (pass 2 below shades them, unchanged).
-template <uint32_t CLS>
-__global__ void __launch_bounds__(kWfBlock, RT_WF_SHADE_MIN_BLOCKS)
-wf_shade_class_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RenderParams P,
-                      const __grid_constant__ WfPool pool, unsigned long long *__restrict__ counters) {
-    __shared__ unsigned s_n;
-    __shared__ unsigned short s_list[kShadeTile];  // index in the tile of every slot of this class
-    const unsigned cur = pool.ctl->round & 1u;
-    const unsigned lane = threadIdx.x & 31u;
-    const uint32_t tile0 = blockIdx.x * (uint32_t)kShadeTile;
-    if (threadIdx.x == 0) s_n = 0u;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < RT_WF_SHADE_TILE; ++i) {
-        const uint32_t slot = tile0 + (uint32_t)i * kWfBlock + threadIdx.x;
-        bool mine = false;
-        if (slot < pool.n_slots) {
-            const uint32_t st = pool.state[slot];
-            mine = (st & 0xFFu) == WF_LIVE && ((st >> 8) & 7u) == CLS;
-        }
-        const unsigned m = __ballot_sync(kFull, mine);
-        if (m != 0u) {  // warp-uniform
-            unsigned base = 0u;
-            if (lane == 0u) base = atomicAdd(&s_n, (unsigned)__popc(m));
-            base = __shfl_sync(kFull, base, 0);
-            if (mine) s_list[base + (unsigned)__popc(m & ((1u << lane) - 1u))] = (unsigned short)((uint32_t)i * kWfBlock + threadIdx.x);
-        }
-    }
-    __syncthreads();
-    const unsigned n = s_n;
-    unsigned alive_n = 0u, bad_n = 0u;
-    for (unsigned k0 = 0; k0 < n; k0 += kWfBlock) {  // the same trip count for the whole block
-        const unsigned k = k0 + threadIdx.x;
-        if (CLS == WF_CLS_COSTLY) {
-            const bool defer = k < n;
-            const uint32_t slot = defer ? tile0 + s_list[k] : 0u;
-            const unsigned m = __ballot_sync(kFull, defer);
-            if (m != 0u) {
-                unsigned base = 0u;
-                if (lane == 0u) base = atomicAdd(&pool.ctl->defer_n, (unsigned)__popc(m));
-                base = __shfl_sync(kFull, base, 0);
-                if (defer) pool.defer_q[base + __popc(m & ((1u << lane) - 1u))] = slot;
-            }
-        } else if (k < n) {
-            const uint32_t slot = tile0 + s_list[k];
-            const double2 *u = slot_d2(pool, slot);
-            bool alive = false, bad = false;
-            shade_slot_c<CLS>(sc, P, pool, slot, ld_u4(u + 3), ld_u4(u + 6), alive, bad);
-            alive_n += alive ? 1u : 0u;
-            bad_n += bad ? 1u : 0u;  // §Q10: counted, not guarded
-        }
-    }
-    if (CLS != WF_CLS_COSTLY) {
-        block_count_add(&pool.ctl->live[cur], alive_n);
-        if (__syncthreads_or(bad_n != 0u)) {
-            const unsigned nb = __reduce_add_sync(kFull, bad_n);
-            if (lane == 0u && nb) atomicAdd(&counters[kCounterNonFinite], (unsigned long long)nb);
-        }
     }
 }
 
@@ -825,8 +746,6 @@ static cudaError_t wf_launch_init(const WfPool &pool, cudaStream_t stream) {
 static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const RenderParams &P, const WfPool &pool,
                             double *planes, unsigned long long *counters, bool media, int sms, uint32_t leave_threshold,
                             unsigned long long cond_handle, cudaStream_t stream) {
-    const bool per_class = (leave_threshold & kWfPerClassShade) != 0u;  // the switch rides on the threshold word
-    leave_threshold &= 0xFFFFu;
     static int ext_per_sm[2] = {0, 0};
     if (ext_per_sm[0] == 0) {
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ext_per_sm[0], wf_extend_kernel<false>, kWfBlock, 0);
@@ -846,18 +765,7 @@ static cudaError_t wf_launch_round(const DScene &sc, const RtCamera &cam, const 
     if (ext_grid > ext_want) ext_grid = ext_want ? ext_want : 1u;
     const unsigned per_tile = (pool.n_slots + kShadeTile - 1) / kShadeTile;
     const unsigned tiles = per_tile ? per_tile : 1u;
-    if (per_class) {  // RTB200_WF_SHADE=perclass: wf_shade_class_kernel
-        wf_shade_class_kernel<WF_CLS_MISS><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        if (media) wf_shade_class_kernel<WF_CLS_MEDIUM><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        wf_shade_class_kernel<WF_CLS_MATERIAL + 0u><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        wf_shade_class_kernel<WF_CLS_MATERIAL + 1u><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        wf_shade_class_kernel<WF_CLS_MATERIAL + 2u><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        wf_shade_class_kernel<WF_CLS_MATERIAL + 3u><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        wf_shade_class_kernel<WF_CLS_MATERIAL + 4u><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-        if (feat(F_TEX)) wf_shade_class_kernel<WF_CLS_COSTLY><<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-    } else {
-        wf_shade_kernel<<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
-    }
+    wf_shade_kernel<<<tiles, kWfBlock, 0, stream>>>(sc, P, pool, counters);
     if (feat(F_TEX)) {  // pass 2 of shade; a grid-stride loop over a queue whose length only the device knows
         unsigned g = per_slot / 16u;
         wf_shade_deferred_kernel<<<g ? g : 1u, kWfBlock, 0, stream>>>(sc, P, pool, counters);

@@ -63,7 +63,6 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 }
 namespace rtb200dev {
 inline namespace RT_VARIANT_NS {
-#include "../../raytracinginrust_b200/csrc/device/sorted_phases.cuh"
 }
 }  // namespace rtb200dev
 
@@ -427,11 +426,11 @@ int toh_path_radiance(void *h, const RtCamera *cam, uint32_t width, uint32_t hei
     return 0;
 }
 
-// wavefront.inl, wf_shade_class_kernel (experiment): a path whose every segment is shaded by the path_shade build of
-// its hit class (path_shade_k<kind>: the other materials folded away) - must be the generic path, bit for bit.
-int toh_path_radiance_by_class(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t max_depth,
-                               const RtRenderOpts *opts, const uint32_t *px, const uint32_t *py, const uint32_t *sample,
-                               uint64_t n, double *rgb, uint32_t *segments) {
+// wavefront.inl: the search / resolve split of the wavefront stages (extend: world_search; shade: resolve_hit or
+// resolve_medium + path_shade) - must be the megakernel's fused world_hit path, bit for bit.
+int toh_path_radiance_split(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t max_depth,
+                            const RtRenderOpts *opts, const uint32_t *px, const uint32_t *py, const uint32_t *sample,
+                            uint64_t n, double *rgb, uint32_t *segments) {
     const HostTables &t = *(HostTables *)h;
     const RenderParams P = params(t, width, height, max_depth, opts);
     if (P.integrator == RT_INTEGRATOR_HEAD && t.cs.lights.empty()) return fail("HEAD integrator needs a non-empty light list");
@@ -452,13 +451,7 @@ int toh_path_radiance_by_class(void *h, const RtCamera *cam, uint32_t width, uin
                 if (cls == WF_CLS_MEDIUM) resolve_medium(t.ds, ps.ray, win, closest, rec);
                 else resolve_hit<false>(t.ds, ps.ray, win, closest, rec);
             }
-            switch (cls) {
-                case WF_CLS_MATERIAL + 0u: alive = path_shade_k<0>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
-                case WF_CLS_MATERIAL + 1u: alive = path_shade_k<1>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
-                case WF_CLS_MATERIAL + 2u: alive = path_shade_k<2>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
-                case WF_CLS_MATERIAL + 3u: alive = path_shade_k<3>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
-                default: alive = path_shade_k<-1>(t.ds, ps, hit, rec, P.integrator, P.flags); break;
-            }
+            alive = path_shade(t.ds, ps, hit, rec, P.integrator, P.flags);
         }
         rgb[3 * k] = ps.radiance.x;
         rgb[3 * k + 1] = ps.radiance.y;
@@ -511,148 +504,6 @@ int toh_render(void *h, const RtCamera *cam, uint32_t width, uint32_t height, ui
         stats[2] = n_bad;
     }
     return 0;
-}
-
-}  // extern "C"
-#pragma GCC visibility pop
-
-// sorted.inl: render_sorted_kernel over simulated blocks.  The per-lane phases are the device's own
-// (sorted_phases.cuh); the block-level part - the counting sort by hit class and the barriers - is restated: blocks
-// take turns, one segment at a time, and inside a block the phases run lane after lane.  Work items, planes and the
-// plane reduction are those of api.cu (make_params / reduce_planes_kernel) with `n_chunks` chunks of samples.
-// out: H x W x 3 f64 (plane sums added in chunk order), rows top-down.
-// stats[0..2]: paths, rays, non-finite paths; stats[3..6]: warp-segments with a live lane, live lanes in them, and the
-// number of (warp, class) pairs with the lanes in the order they arrive (what an unsorted warp shades: one pass per
-// class it holds) and in sorted order - live lanes / pairs is the average width of a shade pass
-template <int B>
-static int render_sorted_sim(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-                             const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks, double *out, uint64_t *stats) {
-    const HostTables &t = *(HostTables *)h;
-    RenderParams P = params(t, width, height, max_depth, opts);
-    if (P.integrator == RT_INTEGRATOR_HEAD && t.cs.lights.empty()) return fail("HEAD integrator needs a non-empty light list");
-    if (max_depth == 0 || n_chunks == 0 || n_blocks == 0) return fail("bad argument");
-    const uint32_t begin = opts ? opts->sample_begin : 0u;
-    const uint32_t count = (opts && opts->sample_count) ? opts->sample_count : (spp > begin ? spp - begin : 0u);
-    if (count == 0) return fail("empty sample range");
-    P.sample_begin = begin;
-    P.sample_end = begin + count;
-    P.tiles_x = (width + 7) / 8;
-    P.tiles_y = (height + 3) / 4;
-    P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
-    if (n_chunks > count) n_chunks = count;
-    P.chunk_size = (count + n_chunks - 1) / n_chunks;
-    P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
-    P.n_items = P.items_per_chunk * P.n_chunks;
-    struct Block {
-        SortedLane lane[B];
-        SortedShared<B> sh;
-        bool running = true;
-    };
-    std::vector<std::unique_ptr<Block>> blocks;
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        blocks.emplace_back(new Block());
-        for (int k = 0; k < B; ++k) sorted_lane_init(blocks.back()->lane[k], P.seed);
-    }
-    const size_t n_values = (size_t)width * height * 3;
-    std::vector<double> planes((size_t)P.n_chunks * n_values, 0.0);
-    unsigned long long counters[kNumCounters] = {0, 0, 0, 0};
-    uint64_t purity[4] = {0, 0, 0, 0};
-    const bool media = !t.cs.media.empty();
-    for (bool any = true; any;) {
-        any = false;
-        for (auto &bp : blocks) {
-            Block &blk = *bp;
-            if (!blk.running) continue;
-            any = true;
-            uint32_t cls[B];
-            unsigned bin[kSortedClasses] = {0}, pos[B];
-            for (int k = 0; k < B; ++k)  // phase A
-                cls[k] = media ? sorted_generate_search<true>(t.ds, *cam, P, planes.data(), counters, blk.lane[k])
-                               : sorted_generate_search<false>(t.ds, *cam, P, planes.data(), counters, blk.lane[k]);
-            // the count, as the kernel does it: per warp, __match_any_sync -> the first lane of every class adds the
-            // class's lane count to the bin once, every lane takes base + its rank among its peers.  The warps arrive
-            // in some order at the shared atomics: last warp first here.
-            for (int w = B / 32 - 1; w >= 0; --w) {
-                unsigned base_of_class[kSortedClasses];
-                for (int l = 0; l < 32; ++l) {
-                    const uint32_t c = cls[w * 32 + l];
-                    unsigned peers = 0u;
-                    for (int m = 0; m < 32; ++m)
-                        if (cls[w * 32 + m] == c) peers |= 1u << m;
-                    const unsigned leader = (unsigned)__builtin_ffs((int)peers) - 1u;
-                    if ((unsigned)l == leader) {
-                        base_of_class[c] = bin[c];
-                        bin[c] += (unsigned)__builtin_popcount(peers);
-                    }
-                    pos[w * 32 + l] = base_of_class[c] + (unsigned)__builtin_popcount(peers & ((1u << l) - 1u));
-                }
-            }
-            uint32_t sorted_cls[B];
-            bool taken[B] = {false};
-            for (int k = 0; k < B; ++k) {  // phase B
-                unsigned dst = pos[k];
-                for (uint32_t c = 0; c < cls[k]; ++c) dst += bin[c];
-                if (dst >= (unsigned)B || taken[dst]) return fail("the sort is not a permutation");
-                taken[dst] = true;
-                sorted_file(blk.sh, dst, blk.lane[k]);
-                sorted_cls[dst] = cls[k];
-            }
-            for (int w = 0; w < B / 32; ++w) {  // purity of the warps before and after the sort
-                unsigned seen_in = 0u, seen_out = 0u, live = 0u;
-                for (int l = 0; l < 32; ++l) {
-                    const uint32_t a = cls[w * 32 + l], b = sorted_cls[w * 32 + l];
-                    if (a != kSortedIdle) seen_in |= 1u << a;
-                    if (b != kSortedIdle) {
-                        seen_out |= 1u << b;
-                        live += 1u;
-                    }
-                }
-                if (seen_out) {
-                    purity[0] += 1;
-                    purity[1] += live;
-                    purity[3] += (uint64_t)__builtin_popcount(seen_out);
-                }
-                purity[2] += (uint64_t)__builtin_popcount(seen_in);
-            }
-            if (bin[kSortedIdle] == (unsigned)B) {
-                blk.running = false;
-                continue;
-            }
-            for (int k = 0; k < B; ++k) {  // phase C
-                sorted_pickup(blk.sh, (unsigned)k, P, blk.lane[k]);
-                sorted_shade(t.ds, P, blk.lane[k]);
-            }
-        }
-    }
-    unsigned long long n_paths = 0, n_rays = 0, n_bad = 0;
-    for (auto &bp : blocks)
-        for (int k = 0; k < B; ++k) {
-            n_paths += bp->lane[k].n_paths;
-            n_rays += bp->lane[k].n_rays;
-            n_bad += bp->lane[k].n_bad;
-        }
-    for (size_t k = 0; k < n_values; ++k) {  // reduce_planes_kernel: chunks in ascending order
-        double acc = 0.0;
-        for (uint32_t c = 0; c < P.n_chunks; ++c) acc += planes[(size_t)c * n_values + k];
-        out[k] = acc;
-    }
-    if (stats) {
-        stats[0] = n_paths;
-        stats[1] = n_rays;
-        stats[2] = n_bad;
-        for (int k = 0; k < 4; ++k) stats[3 + k] = purity[k];
-    }
-    return 0;
-}
-
-#pragma GCC visibility push(default)
-extern "C" {
-int toh_render_sorted(void *h, const RtCamera *cam, uint32_t width, uint32_t height, uint32_t spp,
-                                                             uint32_t max_depth, const RtRenderOpts *opts, uint32_t n_chunks, uint32_t n_blocks,
-                                                             uint32_t block, double *out, uint64_t *stats) {
-    if (block == 256) return render_sorted_sim<256>(h, cam, width, height, spp, max_depth, opts, n_chunks, n_blocks, out, stats);
-    if (block == 128) return render_sorted_sim<128>(h, cam, width, height, spp, max_depth, opts, n_chunks, n_blocks, out, stats);
-    return fail("block must be 128 or 256");
 }
 
 }  // extern "C"

@@ -39,12 +39,9 @@ def _lib():
     lib.toh_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32,
                                       C.POINTER(RtRenderOpts), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                       C.c_void_p, C.c_void_p]
-    lib.toh_path_radiance_by_class.argtypes = lib.toh_path_radiance.argtypes
+    lib.toh_path_radiance_split.argtypes = lib.toh_path_radiance.argtypes
     lib.toh_render.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                C.POINTER(RtRenderOpts), C.c_void_p, C.POINTER(C.c_uint64)]
-    lib.toh_render_sorted.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
-                                      C.POINTER(RtRenderOpts), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p,
-                                      C.POINTER(C.c_uint64)]
     return lib
 
 
@@ -113,16 +110,16 @@ class CompiledOnHost:
                                      seg.ctypes.data_as(C.c_void_p)))
         return rgb, seg
 
-    def path_radiance_by_class(self, camera, width, height, max_depth, opts, px, py, sample):
-        """path_radiance with every segment shaded by the path_shade build of its hit class (wf_shade_class_kernel)."""
+    def path_radiance_split(self, camera, width, height, max_depth, opts, px, py, sample):
+        """path_radiance in the wavefront stages' form: world_search, then resolve + path_shade."""
         px, py, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (px, py, sample))
         n = px.shape[0]
         rgb = np.zeros((n, 3), dtype=np.float64)
         seg = np.zeros(n, dtype=np.uint32)
-        _check(lib.toh_path_radiance_by_class(self._h, C.byref(camera), width, height, max_depth, C.byref(opts),
-                                              px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
-                                              sample.ctypes.data_as(C.c_void_p), n, rgb.ctypes.data_as(C.c_void_p),
-                                              seg.ctypes.data_as(C.c_void_p)))
+        _check(lib.toh_path_radiance_split(self._h, C.byref(camera), width, height, max_depth, C.byref(opts),
+                                           px.ctypes.data_as(C.c_void_p), py.ctypes.data_as(C.c_void_p),
+                                           sample.ctypes.data_as(C.c_void_p), n, rgb.ctypes.data_as(C.c_void_p),
+                                           seg.ctypes.data_as(C.c_void_p)))
         return rgb, seg
 
     def render(self, camera, width, height, spp, max_depth, opts):
@@ -132,23 +129,6 @@ class CompiledOnHost:
         _check(lib.toh_render(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts),
                               out.ctypes.data_as(C.c_void_p), stats))
         return out, {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
-
-
-def _render_sorted(self, camera, width, height, spp, max_depth, opts, n_chunks=1, n_blocks=2, block=128, purity=False):
-    """render_sorted_kernel (csrc/device/sorted.inl) over simulated blocks of 128 or 256 lanes: the device's per-lane
-    phases, the block-level sort restated.  Returns (f64 plane sums HxWx3 rows top-down, {paths, rays, non_finite});
-    purity=True adds the width of a shade pass (live lanes per (warp, class) pair) before and after the sort."""
-    out = np.zeros((height, width, 3), dtype=np.float64)
-    stats = (C.c_uint64 * 7)()
-    _check(lib.toh_render_sorted(self._h, C.byref(camera), width, height, spp, max_depth, C.byref(opts), n_chunks, n_blocks,
-                                 block, out.ctypes.data_as(C.c_void_p), stats))
-    res = {"paths": int(stats[0]), "rays": int(stats[1]), "non_finite": int(stats[2])}
-    if purity:
-        res.update(warp_segments=int(stats[3]), live_lanes=int(stats[4]), passes_unsorted=int(stats[5]), passes_sorted=int(stats[6]))
-    return out, res
-
-
-CompiledOnHost.render_sorted = _render_sorted
 
 
 def camera_rays(camera, width, height, opts, px, py, sample):

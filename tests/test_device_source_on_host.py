@@ -204,33 +204,10 @@ def test_parallel_compile_reports_the_errors_of_the_serial_walk(rt, orc, toh):
         assert ei.value.status == A.RT_ERR_BAD_ARGUMENT and word in str(ei.value)
 
 
-@pytest.mark.parametrize("name,shape", [("cornell", (37, 29, 8)), ("cornell_smoke", (24, 20, 6)), ("random", (30, 22, 5)), ("final", (20, 16, 4))])
-def test_sorted_megakernel_phases_on_simulated_blocks(rt, orc, toh, name, shape):
-    """csrc/device/sorted.inl (experiment, RTB200_PIPELINE=sorted): the megakernel with its lanes re-sorted by hit class
-    once per segment, the path state travelling through shared memory.  The per-lane phases are the device's own code
-    (sorted_phases.cuh); blocks of 128 lanes are simulated lane after lane.  A path, its work item and the item's sum
-    must survive every trip: the image equals the plain sample loop's bit for bit, the counters too."""
-    hs, comp, _ = scenes(rt, orc, toh, name)
-    W, H, spp = shape
-    opts = rt.render_opts(seed=8, integrator=hs.integrator)
-    ref, st = comp.render(hs.camera, W, H, spp, 100, opts)
-    img, s1 = comp.render_sorted(hs.camera, W, H, spp, 100, opts, n_chunks=1, n_blocks=3)
-    assert np.array_equal(img, ref, equal_nan=True) and s1 == st
-    # several sample chunks per pixel (the planes are added in chunk order: another grouping of the same additions)
-    img3, s3 = comp.render_sorted(hs.camera, W, H, spp, 100, opts, n_chunks=3, n_blocks=2)
-    assert s3 == st and rel_err(img3, ref, floor=1e-12).max() < 1e-14
-    # a sample sub-range (the multi-GPU partition)
-    part, _ = comp.render_sorted(hs.camera, W, H, spp, 100, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=2, sample_count=3), n_chunks=1, n_blocks=1)
-    want, _ = comp.render(hs.camera, W, H, spp, 100, rt.render_opts(seed=8, integrator=hs.integrator, sample_begin=2, sample_count=3))
-    assert np.array_equal(part, want, equal_nan=True)
-
-
 @pytest.mark.parametrize("name", SCENES + EXTRA_SCENES)
-def test_class_specialised_shading_is_the_generic_shading(rt, orc, toh, name):
-    """wavefront.inl, wf_shade_class_kernel (experiment, RTB200_WF_SHADE=perclass): every segment shaded by the
-    path_shade build of its hit class (the other materials folded away at compile time) gives the generic path's
-    radiance and segment count, bit for bit; and the search / resolve split of the wavefront stages (world_search +
-    resolve_hit) equals the megakernel's fused world_hit."""
+def test_search_resolve_split_is_the_fused_world_hit(rt, orc, toh, name):
+    """wavefront.inl: the search / resolve split of the wavefront stages (extend: world_search; shade: resolve_hit /
+    resolve_medium + path_shade) gives the radiance and segment count of the megakernel's fused world_hit, bit for bit."""
     hs, comp, _ = scenes(rt, orc, toh, name)
     W, H, depth = 96, 96, 100
     no_lights = name in ("random", "two_spheres", "two_perlin_spheres", "earth")  # HEAD needs a light list (§Q7)
@@ -238,5 +215,5 @@ def test_class_specialised_shading_is_the_generic_shading(rt, orc, toh, name):
         opts = rt.render_opts(seed=17, integrator=integrator)
         px, py, s = random_path_ids(4000, W, H, 128, seed=33)
         a, sa = comp.path_radiance(hs.camera, W, H, depth, opts, px, py, s)
-        b, sb = comp.path_radiance_by_class(hs.camera, W, H, depth, opts, px, py, s)
+        b, sb = comp.path_radiance_split(hs.camera, W, H, depth, opts, px, py, s)
         assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb), (name, integrator)

@@ -349,46 +349,6 @@ def test_random_scene_graphs_on_device(rt, orc, seed):
     osc.close()
 
 
-EXPERIMENTS = pytest.mark.skipif(os.environ.get("RTB200_TEST_EXPERIMENTS") != "1",
-                                 reason="experimental kernels that never ran on a GPU: set RTB200_TEST_EXPERIMENTS=1 and run under a timeout")
-
-
-@EXPERIMENTS
-@pytest.mark.parametrize("name", SCENES)
-def test_sorted_megakernel_equals_megakernel(rt, orc, name, monkeypatch):
-    """csrc/device/sorted.inl (RTB200_PIPELINE=sorted, not a default): bit-identical images and counters."""
-    hs, dev, _ = scenes(rt, orc, name)
-    W, H, spp, depth = 97, 61, 20, 100
-    opts = rt.render_opts(seed=6, integrator=hs.integrator, flags=rt._abi.FLAG_MEGAKERNEL)
-    monkeypatch.delenv("RTB200_PIPELINE", raising=False)
-    a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
-    for pipeline in ("sorted", "sorted256"):
-        monkeypatch.setenv("RTB200_PIPELINE", pipeline)
-        b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
-        assert dev.render_info["pipeline"] == pipeline
-        monkeypatch.delenv("RTB200_PIPELINE", raising=False)
-        assert np.array_equal(a, b, equal_nan=True)
-        assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
-
-
-@EXPERIMENTS
-@pytest.mark.parametrize("name", SCENES + ["earth", "cornell_pbr"])
-def test_per_class_shade_kernels_equal_the_sorted_pass(rt, orc, name, monkeypatch):
-    """csrc/device/wavefront.inl, wf_shade_class_kernel (RTB200_WF_SHADE=perclass, not a default): one shade launch per
-    hit class instead of the one class-sorted pass - bit-identical images and counters."""
-    hs, dev, _ = scenes(rt, orc, name)
-    W, H, spp, depth = 97, 61, 20, 100
-    opts = rt.render_opts(seed=6, integrator=hs.integrator, flags=rt._abi.FLAG_WAVEFRONT)
-    monkeypatch.delenv("RTB200_WF_SHADE", raising=False)
-    a, sa = dev.render(hs.camera, W, H, spp, depth, opts)
-    monkeypatch.setenv("RTB200_WF_SHADE", "perclass")
-    b, sb = dev.render(hs.camera, W, H, spp, depth, opts)
-    monkeypatch.delenv("RTB200_WF_SHADE", raising=False)
-    assert np.array_equal(a, b, equal_nan=True)
-    assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
-    assert sb.kernel_launches > sa.kernel_launches
-
-
 def test_shutter_outside_unit_range_is_refused_for_extrapolating_spheres(rt, orc):
     """A MovingSphere with (time0, time1) != (0, 1) extrapolates (sphere.rs:144-146); the compiled bounds cover shutter
     times in [0, 1], so another shutter is refused (RT_ERR_UNSUPPORTED) instead of culling the sphere wrongly."""
