@@ -270,7 +270,11 @@ RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width,
  * work is enqueued on `cuda_stream` (a cudaStream_t passed as void*; NULL = the
  * default stream).  Returns after enqueueing; stats (if non-NULL) are complete
  * after rt_render_wait().  This is the entry the multi-GPU host uses so that
- * the fp32 sums can go straight into ncclReduce. */
+ * the fp32 sums can go straight into ncclReduce.
+ * ONE render in flight per scene: the scene owns the scratch the kernels write (sample
+ * planes, counters, the wavefront pool and its CUDA graph), so a second rt_render_device
+ * or rt_render before rt_render_wait returns RT_ERR_BAD_ARGUMENT ("render pending").
+ * The image is OVERWRITTEN with the sums of the requested sample range, not added to. */
 RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t width,
                           uint32_t height, uint32_t spp, uint32_t max_depth,
                           const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream);

@@ -21,15 +21,30 @@ def build():
     subprocess.check_call(["make", "-C", _HERE, "-s"])
 
 
+def build_native():
+    """The timed build of bench.py's CPU legs: -O3 -march=native (still -ffp-contract=off: rustc never fuses), compiled
+    ON the machine that runs it - the default build travels to the GPU box from another CPU, so it stays generic.
+    Returns the library's path (cached per CPU flag set)."""
+    import hashlib
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags"))
+    except (OSError, StopIteration):
+        flags = "unknown"
+    out = os.path.join("build", "liboracle_native_%s.so" % hashlib.md5(flags.encode()).hexdigest()[:10])
+    subprocess.check_call(["make", "-C", _HERE, "-s", "OUT=" + out,
+                           "CXXFLAGS=-O3 -march=native -std=c++17 -fPIC -fopenmp -ffp-contract=off -fno-fast-math"])
+    return os.path.join(_HERE, out)
+
+
 class OracleCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("segments", "box_tests", "sphere_tests", "msphere_tests", "rect_tests",
                                           "tri_tests", "medium_tests", "xform")]
 
 
-def _lib():
-    if not os.path.exists(LIB_PATH):
+def _lib(path=LIB_PATH):
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         build()
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.oracle_last_error.restype = C.c_char_p
     lib.oracle_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(C.c_void_p)]
     lib.oracle_scene_destroy.argtypes = [C.c_void_p]
@@ -75,6 +90,13 @@ def _lib():
 
 
 lib = _lib()
+
+
+def use_native_build():
+    """Switch this module to the -O3 -march=native build (bench.py's timed CPU legs).  Call before creating scenes."""
+    global lib
+    lib = _lib(build_native())
+    return lib
 
 
 class OracleError(RuntimeError):

@@ -385,6 +385,7 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
+    s.render_info += " chunks=" + std::to_string(P.n_chunks) + " chunk_size=" + std::to_string(P.chunk_size);
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaMemcpyAsync(s.counters_host, s.counters, sizeof(unsigned long long) * kNumCounters, cudaMemcpyDeviceToHost, st));
@@ -555,6 +556,9 @@ RtStatus rt_render_device(const RtScene *scene, const RtCamera *camera, uint32_t
                           uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum_device, void *cuda_stream) {
     if (!scene || !camera || !out_rgb_sum_device) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     RtScene &s = *const_cast<RtScene *>(scene);
+    // One render in flight per scene: the planes, counters, events and the wavefront pool (and its graph) are the
+    // scene's own scratch; a second enqueue would resize or overwrite them under the kernels still running.
+    if (s.pending) return fail(RT_ERR_BAD_ARGUMENT, "render pending: call rt_render_wait before the next rt_render_device on this scene");
     if (check_shutter(s, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     s.t_call0 = now_ms();
     CU(cudaSetDevice(s.device));
@@ -585,6 +589,7 @@ RtStatus rt_render(const RtScene *scene, const RtCamera *camera, uint32_t width,
                    uint32_t max_depth, const RtRenderOpts *opts, float *out_rgb_sum, RtStats *stats) {
     if (!scene || !camera) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     RtScene &s = *const_cast<RtScene *>(scene);
+    if (s.pending) return fail(RT_ERR_BAD_ARGUMENT, "render pending: call rt_render_wait before rt_render on this scene");
     if (check_shutter(s, *camera) != RT_OK) return RT_ERR_UNSUPPORTED;
     RtStatus st = start_render_own(s, *camera, width, height, spp, max_depth, opts);
     if (st != RT_OK) return st;

@@ -7,7 +7,7 @@
 
 namespace rtb200dev {
 
-// out[p] (+)= sum over chunks of planes[c][p], c ascending: a fixed summation order
+// out[p] = (float)(sum over chunks of planes[c][p], c ascending): overwrites; a fixed summation order
 __global__ void reduce_planes_kernel(const double *__restrict__ planes, float *__restrict__ out, uint64_t n_values,
                                      uint32_t n_chunks) {
     uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,25 +1,22 @@
-// host_c_api.cpp — C entry points over the C++ host layer, for the Python test and
-// bench harness (ctypes).  The Rust host would call the classes' equivalents directly.
+// host_c_api.cpp — C entry points over the scene-graph half of the C++ host layer (librtb200_scenes.so), for the
+// Python test and bench harness (ctypes).  The Rust host would call the classes' equivalents directly.
+// Nothing here calls the device library; the render entry points are in host_render_c_api.cpp.
 #include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
 
+#include "host_c_api.h"
 #include "scene_api.hpp"
 
 using namespace rtb200;
-
-struct RthScene {
-    SceneSpec spec;
-    std::unique_ptr<FlatScene> flat;
-    explicit RthScene(SceneSpec s) : spec(std::move(s)) {}
-};
 
 static thread_local std::string g_host_err;
 
 extern "C" {
 
 const char *rth_last_error(void) { return g_host_err.c_str(); }
+void rth_set_error(const char *message) { g_host_err = message ? message : ""; }  // for host_render_c_api.cpp
 
 // Build one of the catalogue scenes (scenes.cpp) and flatten it.
 int rth_scene_build(const char *name, uint32_t construction_seed, const char *assets_dir, uint32_t mesh_detail,
@@ -77,45 +74,6 @@ int rth_write_ppm(const char *path, const float *rgb_sum, uint32_t width, uint32
     write_ppm(f, rgb_sum, width, height, samples_per_pixel);
     std::fclose(f);
     return RT_OK;
-}
-
-// The whole render(world, camera, width, height, spp, max_depth) -> pixels call on a
-// catalogue scene: flatten, compile + upload, render, read back.  This is the end-to-end
-// path bench.py times with host buffers.
-int rth_render(const RthScene *s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-               const RtRenderOpts *opts, int device, float *out_rgb_sum, RtStats *stats) {
-    try {
-        RenderResult r = render(s->spec.world, s->spec.lights, s->spec.background, s->spec.camera, width, height, spp,
-                                max_depth, *opts, device);
-        std::memcpy(out_rgb_sum, r.rgb_sum.data(), r.rgb_sum.size() * sizeof(float));
-        if (stats) *stats = r.stats;
-        return RT_OK;
-    } catch (const std::exception &e) {
-        g_host_err = e.what();
-        return RT_ERR_INTERNAL;
-    }
-}
-
-// render() over n_gpus GPUs (0 = all) with the P3 file produced on the GPU: what the CLI writes to stdout.
-// out_ppm: host buffer of `capacity` bytes (32 + 12*W*H suffices); *length = file size.
-int rth_render_ppm(const RthScene *s, uint32_t width, uint32_t height, uint32_t spp, uint32_t max_depth,
-                   const RtRenderOpts *opts, uint32_t n_gpus, char *out_ppm, uint64_t capacity, uint64_t *length,
-                   RtStats *stats) {
-    try {
-        RenderResult r = render_ppm(s->spec.world, s->spec.lights, s->spec.background, s->spec.camera, width, height, spp,
-                                    max_depth, *opts, n_gpus);
-        if (r.ppm.size() > capacity) {
-            g_host_err = "output buffer too small";
-            return RT_ERR_BAD_ARGUMENT;
-        }
-        std::memcpy(out_ppm, r.ppm.data(), r.ppm.size());
-        *length = r.ppm.size();
-        if (stats) *stats = r.stats;
-        return RT_OK;
-    } catch (const std::exception &e) {
-        g_host_err = e.what();
-        return RT_ERR_INTERNAL;
-    }
 }
 
 // OBJ reader check (mesh.rs:40-52): number of triangles of the first model

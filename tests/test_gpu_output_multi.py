@@ -166,3 +166,26 @@ def test_host_render_ppm_and_cli(rt, orc, tmp_path):
     assert a.stdout == ppm and b.stdout == ppm
     if rt.device_count() == 1:
         assert c.stdout == ppm
+
+
+def test_one_render_in_flight_per_scene(rt):
+    """A second rt_render_device (or rt_render) before rt_render_wait is refused: the scene's planes, counters and
+    wavefront pool are still being written by the first (include/rtb200.h)."""
+    import torch
+    hs = host_scene(rt, "cornell")
+    dev = rt.DeviceScene(hs.scene_desc, device=0)
+    opts = rt.render_opts(seed=2, integrator=hs.integrator)
+    out = torch.zeros((32, 32, 3), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    dev.render_device(hs.camera, 32, 32, 64, 20, opts, out.data_ptr(), stream)
+    with pytest.raises(rt.RtError, match="render pending"):
+        dev.render_device(hs.camera, 32, 32, 64, 20, opts, out.data_ptr(), stream)
+    with pytest.raises(rt.RtError, match="render pending"):
+        dev.render(hs.camera, 32, 32, 64, 20, opts)
+    st = dev.render_wait()
+    assert st.paths == 32 * 32 * 64
+    first = out.clone()
+    dev.render_device(hs.camera, 32, 32, 64, 20, opts, out.data_ptr(), stream)  # accepted again; the image is overwritten
+    dev.render_wait()
+    torch.cuda.synchronize()
+    assert torch.equal(first, out)
