@@ -52,7 +52,7 @@ struct RtScene {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t features = 0;     // Feat bits of the scene (the integrator bit is added per render)
-    int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media
+    int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media, bit 3: deferred BVH traversal
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
     size_t planes_bytes = 0;
@@ -193,6 +193,11 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.chunk_size = (uint32_t)((count + chunks - 1) / chunks);
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;
+    P.defer_threshold = 16;  // measured: profiles/r2_c_deferred_traversal.md
+    if (const char *v = std::getenv("RTB200_DEFER_THRESHOLD")) {
+        const int n = std::atoi(v);
+        if (n >= 1 && n <= 32) P.defer_threshold = (uint32_t)n;
+    }
     return RT_OK;
 }
 
@@ -381,7 +386,8 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         int blocks = 0;
         CU(pv.render_grid_size(s.device, variant, &blocks));
         s.render_info = std::string("pipeline=megakernel variant=") + pv.name +
-                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
+                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1)) +
+                        " traversal=" + ((variant & 8) && (pv.mask & F_BVH) ? "deferred" : "inline");
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
@@ -498,6 +504,14 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
         int budget = (!bvh && !media) ? 0 : ((bvh && !media && !tris) ? 2 : 1);
         if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) budget = std::atoi(v) & 3;
         s->render_variant = budget | (media ? 4 : 0);
+        // Deferred BVH traversal (megakernel.inl: render_deferred_kernel): worth it where only some of a warp's rays
+        // reach a BVH at all, i.e. where the world holds flat groups next to BVH groups (the mesh scene: 5 walls and
+        // a light next to two triangle meshes) - not where every ray starts in the one BVH (RTiOW, a lone mesh).
+        bool flat = false, tree = false;
+        for (uint32_t g = 0; g < cs.n_world_groups && g < cs.groups.size(); ++g) (cs.groups[g].bvh_root >= 0 ? tree : flat) = true;
+        bool defer = flat && tree && !media;
+        if (const char *v = std::getenv("RTB200_DEFER")) defer = std::atoi(v) != 0 && tree && !media;
+        if (defer) s->render_variant |= 8;
     }
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();
