@@ -421,6 +421,7 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
 // ---------------------------------------------------------------------------
 struct GroupBuild {
     std::vector<DOp> xform;  // chain without flips
+    bool tree = false;       // its primitives sit below a BVH node of the scene graph (see Walker::in_bvh)
     uint32_t chain = 0;
     std::vector<DPrim> prims;
 };
@@ -633,6 +634,12 @@ struct Walker {
     std::vector<DOp> stack;
     std::vector<std::vector<DOp>> chain_ops;  // interned chains
     uint32_t rank = 0;
+    // > 0 below a BVH node.  The reference scans the members of a HittableList linearly and only walks a tree where
+    // the scene says BVH::new, and the groups keep that distinction: what hangs directly in a list (the walls of a
+    // room) is a group of its own, scanned linearly when it is small, instead of being mixed into the tree of the
+    // mesh next to it - every ray would then walk that tree, where now only the rays that reach the mesh's bounds do
+    // (megakernel.inl: render_deferred_kernel lets them wait for each other).
+    int in_bvh = 0;
     std::vector<GroupBuild> *groups = nullptr;
     std::vector<PendingMedium> *media = nullptr;  // null while walking a medium boundary
 
@@ -654,9 +661,10 @@ struct Walker {
         for (const DOp &op : stack)
             if (op.kind != OP_FLIP) xf.push_back(op);
         for (GroupBuild &g : *groups)
-            if (same_ops(g.xform, xf)) return g;
+            if (g.tree == (in_bvh > 0) && same_ops(g.xform, xf)) return g;
         groups->emplace_back();
         groups->back().xform = xf;
+        groups->back().tree = in_bvh > 0;
         groups->back().chain = intern_chain(xf);
         return groups->back();
     }
@@ -838,12 +846,21 @@ struct Walker {
                     std::string e;
                     if (!ref_bvh_order(d, kids, n.v[0], n.v[1], order, e))
                         return fail(n.count == 0 ? RT_ERR_EMPTY_SCENE : RT_ERR_BAD_ARGUMENT, e);
+                    ++in_bvh;
+                    cache_valid = false;
                     auto TE = std::chrono::steady_clock::now();
                     bool many = emit_many(order);
                     if (getenv("RTB200_COMPILE_TIMING") && order.size() > 10000) fprintf(stderr, "[walk] emit_many(%zu) = %d: %.3f s\n", order.size(), (int)many, std::chrono::duration<double>(std::chrono::steady_clock::now() - TE).count());
-                    if (many) break;
-                    for (uint32_t id2 : order)
-                        if (!walk(id2, depth + 1)) return false;
+                    bool ok = true;
+                    if (!many)
+                        for (uint32_t id2 : order)
+                            if (!walk(id2, depth + 1)) {
+                                ok = false;
+                                break;
+                            }
+                    --in_bvh;
+                    cache_valid = false;
+                    if (!ok) return false;
                 } else {
                     for (uint32_t i = 0; i < n.count; ++i)
                         if (!walk(d.child_index[n.child + i], depth + 1)) return false;
@@ -947,7 +964,8 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
         }
         // one or two primitives are cheaper to test than to cull; a BVH culls with its own root boxes
         if (dg.n_prims > 2 && !has_bvh) dg.flags |= GROUP_CULL;
-        if (has_bvh && !g.xform.empty()) dg.flags |= GROUP_CULL;
+        // (except next to other groups or under a transform: there the group's bounds save the transform and the root visit)
+        if (has_bvh && (!g.xform.empty() || gb.size() > 1)) dg.flags |= GROUP_CULL;
         double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0};
         for (const DOp &op : g.xform) {
             dg.flags |= GROUP_XFORM;

@@ -1,0 +1,401 @@
+"""A second, independent restatement of the Cornell-box path in plain Python floats (IEEE f64, nothing fused) - TEST
+INFRASTRUCTURE, written from the reference's sources alone, not from oracle/oracle.cpp:
+
+  ray_color                         src/main.rs:41-120   (HEAD integrator, all arms a Cornell scene reaches)
+  HittableList / FlipNormal         src/hit.rs:58-133
+  AARect (hit, pdf_value, random)   src/rect.rs:26-111
+  Cube                              src/cube.rs:14-37
+  Translate / Rotate                src/translate.rs:21-30, src/rotate.rs:31-106 (incl. the face re-orientation with
+                                    the ROTATED ray)
+  ConstantMedium                    src/medium.rs:26-61 (both boundary queries and the clamping of hit1 / hit2)
+  Lambertian / Metal / DiffuseLight / Isotropic   src/mat.rs:212-422
+  PDF::{Cosine, Hittable, Mixture}, random_cosine_direction   src/pdf.rs:8-18, 62-176
+  ONB                               src/onb.rs:8-37
+  Camera::new / get_ray             src/camera.rs:19-59
+  the sample closure                src/main.rs:811-820
+  cornell_box / cornell_box_with_smoke and their cameras      src/main.rs:278-346, 700-705, 714-719
+
+The one thing it shares with the oracle is the convention that replaces thread_rng: Philox4x32-10,
+restated here as well, addressed by (pixel, sample | bounce, slot, sub, seed).  The oracle's per-path radiance must
+equal this file's to rounding (tests/test_oracle_second_hand.py) - an anchor for the mixture weighting, the Rotate
+quirk and the medium clamping that does not come from the first restatement's author reading his own code.
+"""
+import math
+
+INF = float("inf")
+F64_MAX = 1.7976931348623157e308
+
+SLOT_PIXEL, SLOT_LENS, SLOT_TIME, SLOT_MEDIUM, SLOT_SCATTER, SLOT_BALL = range(6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Philox4x32-10 (Salmon et al. 2011; the constants are those of Random123 / cuRAND) and the draw convention
+# ---------------------------------------------------------------------------------------------------------------
+def philox4x32_10(ctr, key):
+    c0, c1, c2, c3 = ctr
+    k0, k1 = key
+    for _ in range(10):
+        p0 = 0xD2511F53 * c0
+        p1 = 0xCD9E8D57 * c2
+        c0, c1, c2, c3 = ((p1 >> 32) ^ c1 ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c3 ^ k1) & 0xFFFFFFFF, p0 & 0xFFFFFFFF
+        k0 = (k0 + 0x9E3779B9) & 0xFFFFFFFF
+        k1 = (k1 + 0xBB67AE85) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def u53(hi, lo):
+    return float(((hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0)
+
+
+class Draws:
+    """The random numbers of one path: key (pixel, sample), counter (bounce, slot, sub, seed)."""
+
+    def __init__(self, seed, pixel, sample):
+        self.seed, self.pixel, self.sample = seed, pixel, sample
+
+    def draw(self, bounce, slot, sub):
+        w = philox4x32_10((bounce, slot, sub, self.seed), (self.pixel, self.sample))
+        return u53(w[0], w[1]), u53(w[2], w[3]), w[1] & 0x7FF, w[3] & 0x7FF
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Vec3 (src/vec.rs) on tuples
+# ---------------------------------------------------------------------------------------------------------------
+def add(a, b): return (a[0] + b[0], a[1] + b[1], a[2] + b[2])
+def sub(a, b): return (a[0] - b[0], a[1] - b[1], a[2] - b[2])
+def mul(a, s): return (a[0] * s, a[1] * s, a[2] * s)          # Vec3 * f64
+def smul(s, a): return (s * a[0], s * a[1], s * a[2])         # f64 * Vec3
+def vmul(a, b): return (a[0] * b[0], a[1] * b[1], a[2] * b[2])
+def div(a, s): return (a[0] / s, a[1] / s, a[2] / s)
+def dot(a, b): return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
+def length(a): return math.sqrt(dot(a, a))
+def cross(a, b): return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
+def normalized(a): return div(a, length(a))
+def reflect(v, n): return add(v, smul(-dot(v, n) * 2.0, n))   # vec.rs:112-114: self + (-self.dot(n) * 2.0 * n)
+
+
+class Ray:
+    def __init__(self, o, d, time):
+        self.o, self.d, self.time = o, d, time
+
+    def at(self, t):
+        return add(self.o, smul(t, self.d))
+
+
+class Hit:
+    __slots__ = ("p", "normal", "t", "u", "v", "front_face", "material")
+
+    def set_face_normal(self, r, outward):  # hit.rs:34-41
+        self.front_face = dot(r.d, outward) < 0.0
+        self.normal = outward if self.front_face else smul(-1.0, outward)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Hittables
+# ---------------------------------------------------------------------------------------------------------------
+PLANE_AXES = {"YZ": (0, 1, 2), "XZ": (1, 0, 2), "XY": (2, 0, 1)}  # rect.rs:26-32: (k, a, b)
+
+
+class AARect:
+    def __init__(self, plane, a0, a1, b0, b1, k, material):
+        self.axes, self.a0, self.a1, self.b0, self.b1, self.k, self.material = PLANE_AXES[plane], a0, a1, b0, b1, k, material
+
+    def hit(self, r, t_min, t_max, ctx):  # rect.rs:49-78
+        ki, ai, bi = self.axes
+        t = (self.k - r.o[ki]) / r.d[ki]
+        if t < t_min or t > t_max:
+            return None
+        a = r.o[ai] + t * r.d[ai]
+        b = r.o[bi] + t * r.d[bi]
+        if a < self.a0 or a > self.a1 or b < self.b0 or b > self.b1:
+            return None
+        h = Hit()
+        h.u = (a - self.a0) / (self.a1 - self.a0)
+        h.v = (b - self.b0) / (self.b1 - self.b0)
+        h.p = r.at(t)
+        h.t = t
+        n = [0.0, 0.0, 0.0]
+        n[ki] = 1.0
+        h.material = self.material
+        h.set_face_normal(r, tuple(n))
+        return h
+
+    def pdf_value(self, o, v):  # rect.rs:91-101
+        rec = self.hit(Ray(o, v, 0.0), 0.001, INF, None)
+        if rec is None:
+            return 0.0
+        area = (self.a1 - self.a0) * (self.b1 - self.b0)
+        distance_squared = rec.t ** 2 * length(v) ** 2
+        cosine = abs(dot(v, rec.normal)) / length(v)
+        return distance_squared / (cosine * area) if cosine != 0.0 else 0.0
+
+    def random(self, o, r1, r2):  # rect.rs:103-111; gen_range(lo..hi) = lo + (hi - lo) * u
+        ki, ai, bi = self.axes
+        p = [0.0, 0.0, 0.0]
+        p[ai] = self.a0 + (self.a1 - self.a0) * r1
+        p[bi] = self.b0 + (self.b1 - self.b0) * r2
+        p[ki] = self.k
+        return sub(tuple(p), o)
+
+
+class HittableList:
+    def __init__(self, items=None):
+        self.list = list(items or [])
+
+    def push(self, h):
+        self.list.append(h)
+
+    def hit(self, r, t_min, t_max, ctx):  # hit.rs:58-72
+        best, closest = None, t_max
+        for obj in self.list:
+            rec = obj.hit(r, t_min, closest, ctx)
+            if rec is not None:
+                closest, best = rec.t, rec
+        return best
+
+    def pdf_value(self, o, v):  # hit.rs:90-92
+        return sum(h.pdf_value(o, v) for h in self.list) / float(len(self.list))
+
+
+def cube(pmin, pmax, material):  # cube.rs:14-30: six rects in this order
+    return HittableList([
+        AARect("XY", pmin[0], pmax[0], pmin[1], pmax[1], pmax[2], material),
+        AARect("XY", pmin[0], pmax[0], pmin[1], pmax[1], pmin[2], material),
+        AARect("XZ", pmin[0], pmax[0], pmin[2], pmax[2], pmax[1], material),
+        AARect("XZ", pmin[0], pmax[0], pmin[2], pmax[2], pmin[1], material),
+        AARect("YZ", pmin[1], pmax[1], pmin[2], pmax[2], pmax[0], material),
+        AARect("YZ", pmin[1], pmax[1], pmin[2], pmax[2], pmin[0], material)])
+
+
+class FlipNormal:  # hit.rs:112-133
+    def __init__(self, inner):
+        self.inner = inner
+
+    def hit(self, r, t_min, t_max, ctx):
+        rec = self.inner.hit(r, t_min, t_max, ctx)
+        if rec is not None:
+            rec.front_face = not rec.front_face
+        return rec
+
+    def pdf_value(self, o, v):
+        return self.inner.pdf_value(o, v)
+
+    def random(self, o, r1, r2):
+        return self.inner.random(o, r1, r2)
+
+
+class Translate:  # translate.rs:21-30
+    def __init__(self, inner, offset):
+        self.inner, self.offset = inner, offset
+
+    def hit(self, r, t_min, t_max, ctx):
+        rec = self.inner.hit(Ray(sub(r.o, self.offset), r.d, r.time), t_min, t_max, ctx)
+        if rec is not None:
+            rec.p = add(rec.p, self.offset)
+        return rec
+
+
+ROT_AXES = {"X": (0, 1, 2), "Y": (1, 0, 2), "Z": (2, 0, 1)}  # rotate.rs:15-21: (r, a, b)
+
+
+class Rotate:
+    def __init__(self, axis, inner, angle):  # rotate.rs:33-37
+        self.axes, self.inner = ROT_AXES[axis], inner
+        radians = (math.pi / 180.0) * angle
+        self.sin_theta, self.cos_theta = math.sin(radians), math.cos(radians)
+
+    def hit(self, r, t_min, t_max, ctx):  # rotate.rs:77-106
+        _, a, b = self.axes
+        c, s = self.cos_theta, self.sin_theta
+        o, d = list(r.o), list(r.d)
+        o[a] = c * r.o[a] - s * r.o[b]
+        o[b] = s * r.o[a] + c * r.o[b]
+        d[a] = c * r.d[a] - s * r.d[b]
+        d[b] = s * r.d[a] + c * r.d[b]
+        rotated = Ray(tuple(o), tuple(d), r.time)
+        rec = self.inner.hit(rotated, t_min, t_max, ctx)
+        if rec is None:
+            return None
+        p, n = list(rec.p), list(rec.normal)
+        p[a] = c * rec.p[a] + s * rec.p[b]
+        p[b] = -s * rec.p[a] + c * rec.p[b]
+        n[a] = c * rec.normal[a] + s * rec.normal[b]
+        n[b] = -s * rec.normal[a] + c * rec.normal[b]
+        rec.p = tuple(p)
+        rec.set_face_normal(rotated, tuple(n))  # with the ROTATED ray, as written (§Q3)
+        return rec
+
+
+class ConstantMedium:  # medium.rs:26-61
+    def __init__(self, boundary, density, phase_material, draw_sub):
+        self.boundary, self.density, self.phase, self.draw_sub = boundary, density, phase_material, draw_sub
+
+    def hit(self, r, t_min, t_max, ctx):
+        hit1 = self.boundary.hit(r, -F64_MAX, F64_MAX, ctx)
+        if hit1 is None:
+            return None
+        hit2 = self.boundary.hit(r, hit1.t + 0.0001, F64_MAX, ctx)
+        if hit2 is None:
+            return None
+        t1, t2 = hit1.t, hit2.t
+        if t1 < t_min:
+            t1 = t_min
+        if t2 > t_max:
+            t2 = t_max
+        if not t1 < t2:
+            return None
+        dist_inside = (t2 - t1) * length(r.d)
+        draws, bounce = ctx
+        xi = draws.draw(bounce, SLOT_MEDIUM, self.draw_sub)[0]
+        hit_distance = -(1.0 / self.density) * math.log(xi)
+        if not hit_distance < dist_inside:
+            return None
+        h = Hit()
+        h.t = t1 + hit_distance / length(r.d)
+        h.p = r.at(h.t)
+        h.u = h.v = 0.0
+        h.front_face = False
+        h.normal = (1.0, 0.0, 0.0)
+        h.material = self.phase
+        return h
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Materials: ("lambertian", albedo) | ("metal", albedo, fuzz) | ("light", emit) | ("isotropic", albedo)
+# ---------------------------------------------------------------------------------------------------------------
+def onb_from_w(n):  # onb.rs:8-21
+    w = normalized(n)
+    a = (0.0, 1.0, 0.0) if abs(w[0]) > 0.9 else (1.0, 0.0, 0.0)
+    v = normalized(cross(w, a))
+    u = cross(w, v)
+    return u, v, w
+
+
+def onb_local(uvw, a):  # onb.rs:35-37
+    u, v, w = uvw
+    return add(add(smul(a[0], u), smul(a[1], v)), smul(a[2], w))
+
+
+def random_cosine_direction(r1, r2):  # pdf.rs:8-18
+    z = math.sqrt(1.0 - r2)
+    phi = 2.0 * math.pi * r1
+    return (math.cos(phi) * math.sqrt(r2), math.sin(phi) * math.sqrt(r2), z)
+
+
+def ray_color(ray, background, world, lights, depth, draws, max_depth):  # main.rs:41-120
+    if depth <= 0:
+        return (0.0, 0.0, 0.0)
+    bounce = max_depth - depth
+    rec = world.hit(ray, 0.00001, INF, (draws, bounce))
+    if rec is None:
+        return background
+    m = rec.material
+    kind = m[0]
+    emitted = (m[1] if rec.front_face else (0.0, 0.0, 0.0)) if kind == "light" else (0.0, 0.0, 0.0)  # mat.rs:395-401
+    if kind == "metal":  # mat.rs:280-293: ScatterRecord::Specular, or None when the ray ends up below the surface
+        reflected = normalized(reflect(ray.d, rec.normal))
+        assert m[2] == 0.0, "fuzz > 0 draws random_in_unit_sphere: not needed for the Cornell scenes"
+        scattered = Ray(rec.p, reflected, ray.time)
+        if dot(scattered.d, rec.normal) > 0.0:
+            return vmul(m[1], ray_color(scattered, background, world, lights, depth - 1, draws, max_depth))
+        return emitted
+    if kind == "lambertian":  # mat.rs:232-249 + main.rs:92-98
+        uvw = onb_from_w(rec.normal)                       # PDF::cosine_pdf(rec.normal)
+        a, b, bits_a, bits_b = draws.draw(bounce, SLOT_SCATTER, 0)
+        if bits_a & 1:                                     # pdf.rs:169: gen::<bool>() -> p0 = the hittable pdf
+            light = lights.list[(bits_b * len(lights.list)) >> 11]   # hit.rs:94-96: choose
+            direction = light.random(rec.p, a, b)
+        else:
+            direction = onb_local(uvw, random_cosine_direction(a, b))
+        scattered = Ray(rec.p, direction, ray.time)
+        cosine = dot(normalized(direction), uvw[2])        # pdf.rs:131-139
+        cosine_pdf = cosine / math.pi if cosine > 0.0 else 0.0
+        pdf_value = 0.5 * lights.pdf_value(rec.p, direction) + 0.5 * cosine_pdf   # pdf.rs:143-145
+        scattering_pdf = max(dot(rec.normal, normalized(scattered.d)), 0.0) / math.pi   # mat.rs:246-249
+        nxt = ray_color(scattered, background, world, lights, depth - 1, draws, max_depth)
+        # emitted + attenuation * scattering_pdf * ray_color(..) / pdf_value, left to right (main.rs:97)
+        return add(emitted, div(vmul(mul(m[1], scattering_pdf), nxt), pdf_value))
+    # DiffuseLight and Isotropic have no scatter_mc_method (trait default None, mat.rs:60-62): emitted
+    return emitted
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Camera (camera.rs:19-59) and the sample closure (main.rs:811-820)
+# ---------------------------------------------------------------------------------------------------------------
+class Camera:
+    def __init__(self, lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dist, time0, time1):
+        theta = math.pi / 180.0 * vfov
+        viewport_height = 2.0 * math.tan(theta / 2.0)
+        viewport_width = viewport_height * aspect_ratio
+        cw = normalized(sub(lookfrom, lookat))
+        cu = normalized(cross(vup, cw))
+        cv = cross(cw, cu)
+        h = smul(focus_dist * viewport_width, cu)
+        v = smul(focus_dist * viewport_height, cv)
+        self.origin, self.horizontal, self.vertical = lookfrom, h, v
+        self.llc = sub(sub(sub(lookfrom, div(h, 2.0)), div(v, 2.0)), smul(focus_dist, cw))
+        self.cu, self.cv, self.lens_radius, self.time0, self.time1 = cu, cv, aperture / 2.0, time0, time1
+
+    def get_ray(self, s, t, draws):
+        it = 0
+        while True:  # vec.rs:96-105
+            a, b, _, _ = draws.draw(0, SLOT_LENS, it)
+            p = (-1.0 + (1.0 - -1.0) * a, -1.0 + (1.0 - -1.0) * b, 0.0)
+            if length(p) < 1.0:
+                break
+            it += 1
+        rd = smul(self.lens_radius, p)
+        offset = add(mul(self.cu, rd[0]), mul(self.cv, rd[1]))
+        time = self.time0 + draws.draw(0, SLOT_TIME, 0)[0] * (self.time1 - self.time0)
+        o = add(self.origin, offset)
+        return Ray(o, sub(add(add(self.llc, smul(s, self.horizontal)), smul(t, self.vertical)), o), time)
+
+
+def path_radiance(scene, width, height, max_depth, seed, i, j, sample):
+    """ray_color of sample `sample` of pixel (i, j), j counted bottom-up as in main.rs:772-777."""
+    world, lights, background, camera = scene
+    draws = Draws(seed, j * width + i, sample)
+    ru, rv, _, _ = draws.draw(0, SLOT_PIXEL, 0)
+    u = (float(i) + ru) / float(width - 1)
+    v = (float(j) + rv) / float(height - 1)
+    return ray_color(camera.get_ray(u, v, draws), background, world, lights, max_depth, draws, max_depth)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Scenes: main.rs:278-311 and :313-346, cameras :700-705 and :714-719
+# ---------------------------------------------------------------------------------------------------------------
+def _room():
+    red, white, green = ("lambertian", (0.65, 0.05, 0.05)), ("lambertian", (0.73, 0.73, 0.73)), ("lambertian", (0.12, 0.45, 0.15))
+    light = ("light", (15.0, 15.0, 15.0))
+    rect_light = FlipNormal(AARect("XZ", 213.0, 343.0, 227.0, 332.0, 554.0, light))
+    world = HittableList()
+    world.push(AARect("YZ", 0.0, 555.0, 0.0, 555.0, 555.0, green))
+    world.push(AARect("YZ", 0.0, 555.0, 0.0, 555.0, 0.0, red))
+    world.push(rect_light)
+    world.push(AARect("XZ", 0.0, 555.0, 0.0, 555.0, 0.0, white))
+    world.push(AARect("XZ", 0.0, 555.0, 0.0, 555.0, 555.0, white))
+    world.push(AARect("XY", 0.0, 555.0, 0.0, 555.0, 555.0, white))
+    return world, HittableList([rect_light]), white
+
+
+def _camera():
+    return Camera((278.0, 278.0, -800.0), (278.0, 278.0, 0.0), (0.0, 1.0, 0.0), 40.0, 1.0, 0.05, 10.0, 0.0, 1.0)
+
+
+def cornell_box():
+    world, lights, white = _room()
+    metal = ("metal", (0.8, 0.85, 0.88), 0.0)
+    world.push(Translate(Rotate("Y", cube((0.0, 0.0, 0.0), (165.0, 165.0, 165.0), white), -18.0), (130.0, 0.0, 65.0)))
+    world.push(Translate(Rotate("Y", cube((0.0, 0.0, 0.0), (165.0, 330.0, 165.0), metal), 15.0), (265.0, 0.0, 295.0)))
+    return world, lights, (0.0, 0.0, 0.0), _camera()
+
+
+def cornell_box_with_smoke(medium_draw_subs):
+    """medium_draw_subs: the two sub-slot numbers of the media's free-path draws (the medium's node
+    index in the scene description; a property of the convention, not of the reference)."""
+    world, lights, white = _room()
+    box1 = Translate(Rotate("Y", cube((0.0, 0.0, 0.0), (165.0, 165.0, 165.0), white), -18.0), (130.0, 0.0, 65.0))
+    box2 = Translate(Rotate("Y", cube((0.0, 0.0, 0.0), (165.0, 330.0, 165.0), white), 15.0), (265.0, 0.0, 295.0))
+    world.push(ConstantMedium(box1, 0.01, ("isotropic", (1.0, 1.0, 1.0)), medium_draw_subs[0]))
+    world.push(ConstantMedium(box2, 0.01, ("isotropic", (0.0, 0.0, 0.0)), medium_draw_subs[1]))
+    return world, lights, (0.0, 0.0, 0.0), _camera()

@@ -1,0 +1,70 @@
+"""The oracle against tests/second_hand.py, a restatement of the Cornell path written a second time, in Python, from
+the reference's sources (and building the two Cornell scenes and their camera itself from src/main.rs): per-path
+radiance of identical (pixel, sample) paths must agree to rounding.  Anchors what the closed-form tests do not reach:
+the 50/50 mixture weighting of main.rs:92-98, Rotate's re-orientation with the rotated ray (§Q3) and the clamping
+of ConstantMedium's two boundary hits (medium.rs:32-58)."""
+import numpy as np
+import pytest
+
+import second_hand as sh
+from util import host_scene
+
+W = H = 64
+DEPTH = 50
+SEED = 7
+
+
+def _oracle_paths(rt, orc, name, px, py, s):
+    hs = host_scene(rt, name)
+    osc = orc.OracleScene(hs.scene_desc)
+    opts = rt.render_opts(seed=SEED, integrator=rt.INTEGRATOR_HEAD)
+    rgb, seg = osc.path_radiance(hs.camera, W, H, DEPTH, opts, px, py, s)
+    return hs, rgb, seg
+
+
+def _ids(n, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.integers(0, W, n, dtype=np.uint32), rng.integers(0, H, n, dtype=np.uint32), rng.integers(0, 1000, n, dtype=np.uint32))
+
+
+def _compare(scene, rgb, px, py, s):
+    mine = np.array([sh.path_radiance(scene, W, H, DEPTH, SEED, int(i), int(j), int(k)) for i, j, k in zip(px, py, s)])
+    assert np.isfinite(mine).all() and np.isfinite(rgb).all()
+    err = np.abs(mine - rgb) / np.maximum(np.abs(rgb), 1e-12)
+    lit = (rgb > 0).any(axis=1)
+    print("paths %d, lit %d, max rel err %.3e, identical %.4f" % (len(px), lit.sum(), err.max(), (mine == rgb).all(axis=1).mean()))
+    assert lit.sum() > len(px) // 10  # the comparison is not one of zeros
+    assert err.max() <= 1e-12
+    assert (mine == 0.0).all(axis=1).tolist() == (rgb == 0.0).all(axis=1).tolist()
+
+
+def test_philox_restated_twice(orc):
+    for ctr, key in (((0, 0, 0, 0), (0, 0)), ((1, 4, 0, 7), (4095, 999)), ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2)):
+        assert list(sh.philox4x32_10(ctr, key)) == orc.philox4x32_10(list(ctr), list(key))
+    a, b, ba, bb = sh.Draws(3, 77, 5).draw(2, sh.SLOT_SCATTER, 0)
+    assert (a, b, ba, bb) == orc.draw(3, 77, 5, 2, sh.SLOT_SCATTER, 0)
+
+
+def test_camera_restated_twice(rt):
+    hs = host_scene(rt, "cornell")
+    cam = sh.cornell_box()[3]
+    c = hs.camera
+    for mine, theirs in ((cam.origin, c.origin), (cam.llc, c.lower_left_corner), (cam.horizontal, c.horizontal),
+                         (cam.vertical, c.vertical), (cam.cu, c.cu), (cam.cv, c.cv)):
+        assert tuple(mine) == tuple(theirs)
+    assert (cam.lens_radius, cam.time0, cam.time1) == (c.lens_radius, c.time0, c.time1)
+
+
+def test_cornell_box_paths(rt, orc):
+    px, py, s = _ids(1500, 1)
+    _, rgb, _ = _oracle_paths(rt, orc, "cornell", px, py, s)
+    _compare(sh.cornell_box(), rgb, px, py, s)
+
+
+def test_cornell_smoke_paths(rt, orc):
+    px, py, s = _ids(1500, 2)
+    hs, rgb, _ = _oracle_paths(rt, orc, "cornell_smoke", px, py, s)
+    d = hs.scene_desc.struct
+    media = [k for k in range(d.n_nodes) if d.nodes[k].kind == rt._abi.NODE_MEDIUM]
+    assert len(media) == 2
+    _compare(sh.cornell_box_with_smoke(media), rgb, px, py, s)
