@@ -307,12 +307,16 @@ class Job:
         """RtSceneDesc in host memory -> rt_scene_create (compile, BVH build, upload) -> render (-> reduce) -> fp32 sums
         in pinned host memory, wall clock, max over ranks per iteration; one untimed iteration, then the median."""
         torch, dist, rt = self.torch, self.dist, self.rt
+        from raytracinginrust_b200.multi_gpu import create_scene_distributed
         host_out = torch.empty((self.H, self.W, 3), dtype=torch.float32).pin_memory() if self.rank == 0 else None
         ms, h2d, d2h = [], 0, 0
         for it in range(iters + 1):
             self.barrier()
             t0 = time.perf_counter()
-            sc = rt.DeviceScene(self.hs.scene_desc, device=self.local_rank)
+            if dist is not None:  # one compile on rank 0, the blob over ncclBroadcast, one upload per rank
+                sc, tables_hash = create_scene_distributed(self.hs.scene_desc, self.rank, self.local_rank, device="cuda")
+            else:
+                sc, tables_hash = rt.DeviceScene(self.hs.scene_desc, device=self.local_rank), None
             self.step(sc)
             if self.rank == 0:
                 host_out.copy_(self.out, non_blocking=True)
@@ -331,9 +335,12 @@ class Job:
         med = ms[len(ms) // 2]
         return {"value": (self.W * self.H * self.spp) / (med * 1e-3) / 1e6, "unit": "Mpaths/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": med,
-                "iterations": len(ms), "ms_min": ms[0], "ms_max": ms[-1],
-                "what": "RtSceneDesc in host memory -> rt_scene_create (compile, BVH build, upload) -> render -> "
-                        "fp32 sums copied to pinned host memory; median of %d iterations after one untimed" % len(ms)}
+                "iterations": len(ms), "ms_min": ms[0], "ms_max": ms[-1], "tables_hash": tables_hash,
+                "what": ("RtSceneDesc in host memory -> rt_scene_create (compile, BVH build, upload) -> render -> "
+                         "fp32 sums copied to pinned host memory" if dist is None else
+                         "RtSceneDesc in host memory -> rt_compile on rank 0 -> ncclBroadcast of the table blob -> "
+                         "rt_scene_create_compiled on every rank -> render -> ncclReduce -> fp32 sums in pinned host memory")
+                        + "; median of %d iterations after one untimed" % len(ms)}
 
 
 def fp64_roofline(flops_seg, rays_per_launch, kern_s, fp64_peak, kernel_name):

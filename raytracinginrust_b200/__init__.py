@@ -65,6 +65,17 @@ _dev.rt_encode_rgb8.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, 
 _dev.rt_encode_ppm.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64,
                                C.POINTER(C.c_uint64)]
 
+_dev.rt_compile.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(C.c_void_p)]
+_dev.rt_compiled_data.argtypes = [C.c_void_p]
+_dev.rt_compiled_data.restype = C.c_void_p
+_dev.rt_compiled_size.argtypes = [C.c_void_p]
+_dev.rt_compiled_size.restype = C.c_uint64
+_dev.rt_compiled_hash.argtypes = [C.c_void_p, C.c_uint64]
+_dev.rt_compiled_hash.restype = C.c_uint64
+_dev.rt_compiled_destroy.argtypes = [C.c_void_p]
+_dev.rt_compiled_destroy.restype = None
+_dev.rt_scene_create_compiled.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]
+
 _host.rth_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
                              C.c_int, C.c_void_p, C.POINTER(RtStats)]
 _host.rth_render_ppm.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
@@ -264,18 +275,47 @@ class HostScene(_scenes.HostScene):
         return buf[:int(n.value)].tobytes(), stats
 
 
+def compile_scene(scene_desc):
+    """rt_compile: the host half of rt_scene_create (graph walk, reference order, SAH BVH build) -> the relocatable
+    blob as a numpy uint8 array.  Needs no GPU.  One rank compiles, the bytes travel, every rank calls
+    DeviceScene.from_compiled (multi_gpu.render_distributed does that over torch.distributed)."""
+    h = C.c_void_p()
+    _check(_dev.rt_compile(scene_desc.ptr, C.byref(h)))
+    try:
+        n = int(_dev.rt_compiled_size(h))
+        blob = np.empty(n, dtype=np.uint8)
+        C.memmove(blob.ctypes.data, _dev.rt_compiled_data(h), n)
+    finally:
+        _dev.rt_compiled_destroy(h)
+    return blob
+
+
+def compiled_hash(blob):
+    """FNV-1a over the tables of a compiled scene (0: not a blob of this library)."""
+    blob = np.ascontiguousarray(blob, dtype=np.uint8)
+    return int(_dev.rt_compiled_hash(blob.ctypes.data_as(C.c_void_p), blob.size))
+
+
 class DeviceScene:
     """A scene compiled and resident on one GPU (rt_scene_create)."""
 
-    def __init__(self, scene_desc, device=0, _borrowed=None):
+    def __init__(self, scene_desc, device=0, _borrowed=None, _compiled=None):
         self._h = C.c_void_p()
         self._desc = scene_desc
         self._owned = _borrowed is None
-        if _borrowed is None:
+        if _compiled is not None:
+            blob = np.ascontiguousarray(_compiled, dtype=np.uint8)
+            _check(_dev.rt_scene_create_compiled(blob.ctypes.data_as(C.c_void_p), blob.size, device, C.byref(self._h)))
+        elif _borrowed is None:
             _check(_dev.rt_scene_create(scene_desc.ptr, device, C.byref(self._h)))
         else:  # a member of a SceneGroup: the group owns the handle
             self._h = C.c_void_p(_borrowed)
         self.device = device
+
+    @classmethod
+    def from_compiled(cls, blob, device=0):
+        """rt_scene_create_compiled: upload the tables of a blob made by compile_scene (here or on another rank)."""
+        return cls(None, device=device, _compiled=blob)
 
     def close(self):
         if getattr(self, "_h", None):

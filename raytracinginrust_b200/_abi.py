@@ -100,4 +100,6 @@ EXPORTS = ["rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_d
            "rt_render_device", "rt_render_wait", "rt_trace_first_hit", "rt_path_radiance", "rt_camera_rays",
            "rt_measure_fp64_peak", "rt_render_info", "rt_last_error", "rt_version",
            "rt_scene_group_create", "rt_scene_group_destroy", "rt_scene_group_size", "rt_scene_group_scene",
-           "rt_render_multi", "rt_encode_rgb8", "rt_encode_ppm"]
+           "rt_render_multi", "rt_encode_rgb8", "rt_encode_ppm",
+           "rt_compile", "rt_compiled_data", "rt_compiled_size", "rt_compiled_hash", "rt_compiled_destroy",
+           "rt_scene_create_compiled"]

@@ -52,7 +52,7 @@ struct RtScene {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t features = 0;     // Feat bits of the scene (the integrator bit is added per render)
-    int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media, bit 3: deferred BVH traversal
+    int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
     size_t planes_bytes = 0;
@@ -193,11 +193,6 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.chunk_size = (uint32_t)((count + chunks - 1) / chunks);
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;
-    P.defer_threshold = 16;  // measured: profiles/r2_c_deferred_traversal.md
-    if (const char *v = std::getenv("RTB200_DEFER_THRESHOLD")) {
-        const int n = std::atoi(v);
-        if (n >= 1 && n <= 32) P.defer_threshold = (uint32_t)n;
-    }
     return RT_OK;
 }
 
@@ -386,8 +381,7 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         int blocks = 0;
         CU(pv.render_grid_size(s.device, variant, &blocks));
         s.render_info = std::string("pipeline=megakernel variant=") + pv.name +
-                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1)) +
-                        " traversal=" + ((variant & 8) && (pv.mask & F_BVH) ? "deferred" : "inline");
+                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
@@ -504,14 +498,6 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
         int budget = (!bvh && !media) ? 0 : ((bvh && !media && !tris) ? 2 : 1);
         if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) budget = std::atoi(v) & 3;
         s->render_variant = budget | (media ? 4 : 0);
-        // Deferred BVH traversal (megakernel.inl: render_deferred_kernel): worth it where only some of a warp's rays
-        // reach a BVH at all, i.e. where the world holds flat groups next to BVH groups (the mesh scene: 5 walls and
-        // a light next to two triangle meshes) - not where every ray starts in the one BVH (RTiOW, a lone mesh).
-        bool flat = false, tree = false;
-        for (uint32_t g = 0; g < cs.n_world_groups && g < cs.groups.size(); ++g) (cs.groups[g].bvh_root >= 0 ? tree : flat) = true;
-        bool defer = flat && tree && !media;
-        if (const char *v = std::getenv("RTB200_DEFER")) defer = std::atoi(v) != 0 && tree && !media;
-        if (defer) s->render_variant |= 8;
     }
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();
@@ -561,6 +547,146 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
 }
 
 void rt_scene_destroy(RtScene *scene) { delete scene; }
+
+// ---------------------------------------------------------------------------
+// Compile once, create many: CompiledScene <-> a relocatable blob
+// ---------------------------------------------------------------------------
+}  // extern "C"
+
+struct RtCompiled {
+    std::vector<unsigned char> blob;
+};
+
+namespace {
+constexpr uint64_t kBlobMagic = 0x3130424c42425452ull;  // "RTBBLB01"
+constexpr uint32_t kBlobTables = 12;
+struct BlobHeader {
+    uint64_t magic;
+    uint32_t abi_version, header_bytes;
+    uint64_t total_bytes, hash;             // hash: FNV-1a over everything after the header
+    uint64_t count[kBlobTables];            // elements per table, in the order of CompiledScene
+    uint32_t elem_bytes[kBlobTables];       // sizeof of each table's element in the library that wrote the blob
+    uint32_t n_world_groups, max_bvh_depth, shutter_limited, pad;
+    double background[3];
+};
+uint64_t fnv1a(const unsigned char *p, uint64_t n) {
+    uint64_t h = 1469598103934665603ull;
+    // eight bytes per step keeps 75 MB at a few tens of ms; the tail byte by byte
+    uint64_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);
+        h = (h ^ w) * 1099511628211ull;
+    }
+    for (; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h;
+}
+uint64_t pad16(uint64_t n) { return (n + 15u) & ~15ull; }
+
+template <class F>
+void for_each_table(CompiledScene &cs, F f) {
+    int k = 0;
+    f(k++, cs.prims); f(k++, cs.ops); f(k++, cs.chains); f(k++, cs.groups); f(k++, cs.nodes); f(k++, cs.media);
+    f(k++, cs.lights); f(k++, cs.materials); f(k++, cs.textures); f(k++, cs.images); f(k++, cs.perlin); f(k++, cs.texels);
+}
+
+void serialize(CompiledScene &cs, std::vector<unsigned char> &blob) {
+    BlobHeader h;
+    std::memset(&h, 0, sizeof(h));
+    h.magic = kBlobMagic;
+    h.abi_version = RTB200_ABI_VERSION;
+    h.header_bytes = (uint32_t)pad16(sizeof(BlobHeader));
+    uint64_t total = h.header_bytes;
+    for_each_table(cs, [&](int k, auto &v) {
+        h.count[k] = v.size();
+        h.elem_bytes[k] = (uint32_t)sizeof(v[0]);
+        total += pad16(v.size() * sizeof(v[0]));
+    });
+    h.total_bytes = total;
+    h.n_world_groups = cs.n_world_groups;
+    h.max_bvh_depth = cs.max_bvh_depth;
+    h.shutter_limited = cs.shutter_limited ? 1u : 0u;
+    for (int a = 0; a < 3; ++a) h.background[a] = cs.background[a];
+    blob.assign(total, 0);
+    uint64_t off = h.header_bytes;
+    for_each_table(cs, [&](int, auto &v) {
+        const uint64_t bytes = v.size() * sizeof(v[0]);
+        if (bytes) std::memcpy(blob.data() + off, v.data(), bytes);
+        off += pad16(bytes);
+    });
+    h.hash = fnv1a(blob.data() + h.header_bytes, total - h.header_bytes);
+    std::memcpy(blob.data(), &h, sizeof(h));
+}
+
+// false: not a blob of this library (message in err)
+bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string &err) {
+    BlobHeader h;
+    if (!data || size < sizeof(BlobHeader)) return err = "compiled scene: truncated header", false;
+    std::memcpy(&h, data, sizeof(h));
+    if (h.magic != kBlobMagic || h.abi_version != RTB200_ABI_VERSION || h.header_bytes != pad16(sizeof(BlobHeader)))
+        return err = "compiled scene: not a blob of this library version", false;
+    if (h.total_bytes != size) return err = "compiled scene: size does not match the header (truncated?)", false;
+    uint64_t need = h.header_bytes;
+    bool sizes_ok = true;
+    for_each_table(cs, [&](int k, auto &v) {
+        if (h.elem_bytes[k] != sizeof(v[0]) || h.count[k] > (1ull << 34)) sizes_ok = false;
+        else need += pad16(h.count[k] * sizeof(v[0]));
+    });
+    if (!sizes_ok || need != size) return err = "compiled scene: table sizes do not match this library", false;
+    const unsigned char *p = (const unsigned char *)data;
+    if (fnv1a(p + h.header_bytes, size - h.header_bytes) != h.hash) return err = "compiled scene: checksum mismatch (corrupted)", false;
+    uint64_t off = h.header_bytes;
+    for_each_table(cs, [&](int k, auto &v) {
+        v.resize(h.count[k]);
+        const uint64_t bytes = h.count[k] * sizeof(v[0]);
+        if (bytes) std::memcpy(v.data(), p + off, bytes);
+        off += pad16(bytes);
+    });
+    cs.n_world_groups = h.n_world_groups;
+    cs.max_bvh_depth = h.max_bvh_depth;
+    cs.shutter_limited = h.shutter_limited != 0u;
+    for (int a = 0; a < 3; ++a) cs.background[a] = h.background[a];
+    // what the kernels index without checking must stay inside the tables even for a blob that was made by hand
+    if (cs.n_world_groups > cs.groups.size()) return err = "compiled scene: group count out of range", false;
+    for (const DGroup &g : cs.groups)
+        if ((uint64_t)g.first_prim + g.n_prims > cs.prims.size() || (g.bvh_root >= 0 && (uint64_t)g.bvh_root >= cs.nodes.size()))
+            return err = "compiled scene: group out of range", false;
+    return true;
+}
+}  // namespace
+
+extern "C" {
+
+RtStatus rt_compile(const RtSceneDesc *desc, RtCompiled **out_compiled) {
+    if (!desc || !out_compiled) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *out_compiled = nullptr;
+    CompiledScene cs;
+    std::string err;
+    RtStatus st = compile_scene(*desc, cs, err);
+    if (st != RT_OK) return fail(st, err);
+    std::unique_ptr<RtCompiled> c(new RtCompiled());
+    serialize(cs, c->blob);
+    *out_compiled = c.release();
+    return RT_OK;
+}
+const void *rt_compiled_data(const RtCompiled *c) { return c ? c->blob.data() : nullptr; }
+uint64_t rt_compiled_size(const RtCompiled *c) { return c ? c->blob.size() : 0; }
+uint64_t rt_compiled_hash(const void *data, uint64_t size) {
+    BlobHeader h;
+    if (!data || size < sizeof(h)) return 0;
+    std::memcpy(&h, data, sizeof(h));
+    return h.magic == kBlobMagic ? h.hash : 0;
+}
+void rt_compiled_destroy(RtCompiled *c) { delete c; }
+
+RtStatus rt_scene_create_compiled(const void *data, uint64_t size, int device, RtScene **out_scene) {
+    if (!data || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
+    *out_scene = nullptr;
+    CompiledScene cs;
+    std::string err;
+    if (!deserialize(data, size, cs, err)) return fail(RT_ERR_BAD_ARGUMENT, err);
+    return create_on_device(cs, device, out_scene);
+}
 
 uint64_t rt_scene_device_bytes(const RtScene *scene) { return scene ? scene->device_bytes : 0; }
 

@@ -923,6 +923,21 @@ struct Walker {
 };
 
 bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::string &err) {
+    // List members stay apart from the tree of the same transform only while they are few enough to be scanned
+    // linearly; a larger flat part would need a second tree that every ray walks next to the first, so it joins
+    // the tree (measured on the Next Week final scene, 7 list members next to the 400 ground boxes: one tree 36.1 ms,
+    // two trees 36.8 ms; on the mesh scene, 6 walls next to 394k triangles: 190.6 ms in one tree, 126.6 ms apart).
+    for (GroupBuild &flat : gb) {
+        if (flat.tree || flat.prims.size() <= LINEAR_MAX) continue;
+        for (GroupBuild &tree : gb)
+            if (tree.tree && !tree.prims.empty() && same_ops(tree.xform, flat.xform)) {
+                tree.prims.insert(tree.prims.end(), flat.prims.begin(), flat.prims.end());
+                flat.prims.clear();
+                break;
+            }
+    }
+    size_t n_live = 0;
+    for (const GroupBuild &g : gb) n_live += g.prims.empty() ? 0 : 1;
     for (GroupBuild &g : gb) {
         if (g.prims.empty()) continue;
         DGroup dg;
@@ -965,7 +980,7 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
         // one or two primitives are cheaper to test than to cull; a BVH culls with its own root boxes
         if (dg.n_prims > 2 && !has_bvh) dg.flags |= GROUP_CULL;
         // (except next to other groups or under a transform: there the group's bounds save the transform and the root visit)
-        if (has_bvh && (!g.xform.empty() || gb.size() > 1)) dg.flags |= GROUP_CULL;
+        if (has_bvh && (!g.xform.empty() || n_live > 1)) dg.flags |= GROUP_CULL;
         double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, T[3] = {0, 0, 0};
         for (const DOp &op : g.xform) {
             dg.flags |= GROUP_XFORM;

@@ -27,8 +27,6 @@ struct RenderParams {
     uint32_t tiles_x, tiles_y;          // 8x4 pixel tiles
     uint64_t items_per_chunk;           // tiles_x * tiles_y * 32 (includes padding of partial tiles)
     uint64_t n_items;                   // n_chunks * items_per_chunk
-    uint32_t defer_threshold;           // render_deferred_kernel: lanes of a warp that wait before the BVHs are walked
-    uint32_t pad0;
 };
 
 cudaError_t measure_fp64_peak(int device, double *tflops);

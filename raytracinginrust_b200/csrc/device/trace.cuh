@@ -466,126 +466,15 @@ RT_DEV void trace_one_group(const DScene &sc, const DGroup &g, const Ray &ray, V
 }
 
 // Closest hit over a sub-scene (a range of groups) for the ray given in the outermost space.
-// WHICH = GROUPS_ALL: every group.  The winner does not depend on the order the groups are visited in (accept
-// keeps the smallest t, and of equal t the highest rank), so a search can be cut in two:
-// WHICH = GROUPS_FLAT: only the groups that are a single leaf (scanned linearly); returns whether some group with a
-//   BVH passes its cull test against the interval that is left, i.e. whether GROUPS_BVH has anything to do;
-// WHICH = GROUPS_BVH: only the groups with a BVH (render_deferred_kernel runs it for many lanes at once).
-enum : int { GROUPS_ALL = 0, GROUPS_FLAT = 1, GROUPS_BVH = 2 };
-template <int WHICH>
-RT_DEV bool trace_groups_sel(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
-                             Best &best) {
-    bool bvh_left = false;
+RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
+                         Best &best) {
 #pragma unroll 1
     for (uint32_t gi = 0; gi < n_groups; ++gi) {
         const DGroup &g = sc.groups[first_group + gi];
-        const bool has_bvh = feat(F_BVH) && g.bvh_root >= 0;
-        if (WHICH == GROUPS_BVH && !has_bvh) continue;
-        if (WHICH == GROUPS_FLAT && has_bvh) continue;
         double e;
         // a one- or two-primitive group is cheaper to test than to cull
         if ((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, t_min, best.t, e)) continue;
         trace_one_group(sc, g, ray, inv, t_min, best);
-    }
-    if (WHICH == GROUPS_FLAT && feat(F_BVH)) {  // second sweep: the interval has shrunk to the flat groups' winner
-#pragma unroll 1
-        for (uint32_t gi = 0; gi < n_groups && !bvh_left; ++gi) {
-            const DGroup &g = sc.groups[first_group + gi];
-            double e;
-            if (g.bvh_root >= 0 && (!(g.flags & GROUP_CULL) || slab(ray.o, inv, g.bmin, g.bmax, t_min, best.t, e))) bvh_left = true;
-        }
-    }
-    return bvh_left;
-}
-RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
-                         Best &best) {
-    trace_groups_sel<GROUPS_ALL>(sc, first_group, n_groups, ray, inv, t_min, best);
-}
-
-#ifndef RT_SMEM_TOP
-#define RT_SMEM_TOP 0  // megakernel.inl: render_deferred_kernel stages the top N nodes of the largest BVH in shared memory
-#endif
-// The BVH half of a deferred search: trace_groups_sel<GROUPS_BVH> with the node loop written out, so that the
-// leaves' reciprocal direction (rects, boxes and spheres use it, triangles do not) is made on demand and does not
-// live through the node loop.
-RT_DEV void deferred_bvh_search(const DScene &sc, const Ray &ray, Best &best, const float4 *s_top, int top_first) {
-    const int kDone = (int)0x80000000;
-    const V3 inv = mk(rcp_fast(ray.d.x), rcp_fast(ray.d.y), rcp_fast(ray.d.z));
-    int stack[kStackSize];
-#pragma unroll 1
-    for (uint32_t gi = 0; gi < sc.n_world_groups; ++gi) {
-        const DGroup &g = sc.groups[gi];
-        int node = g.bvh_root;
-        if (node < 0) continue;
-        double e;
-        if ((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, kTMin, best.t, e)) continue;
-        SRay r;
-        r.o = ray.o;
-        r.d = ray.d;
-        r.time = ray.time;
-        if (g.flags & GROUP_XFORM) {  // search-grade: one composed affine map instead of the op chain (trace_one_group)
-            const double *m = g.m;
-            const V3 o = ray.o, d = ray.d;
-            r.o = mk(fma(m[0], o.x, fma(m[1], o.y, fma(m[2], o.z, g.t[0]))), fma(m[3], o.x, fma(m[4], o.y, fma(m[5], o.z, g.t[1]))),
-                     fma(m[6], o.x, fma(m[7], o.y, fma(m[8], o.z, g.t[2]))));
-            if (g.flags & GROUP_ROTATED)
-                r.d = mk(fma(m[0], d.x, fma(m[1], d.y, m[2] * d.z)), fma(m[3], d.x, fma(m[4], d.y, m[5] * d.z)),
-                         fma(m[6], d.x, fma(m[7], d.y, m[8] * d.z)));
-        }
-        const FRay f = make_fray(r);
-        const float t_min_f = __double2float_rd(kTMin);
-        float t_max_f = __double2float_ru(best.t);
-        int sp = 0;
-        while (node != kDone) {
-            while (node >= 0) {
-                float4 q0, q1, q2;
-                int4 ch;
-                if (RT_SMEM_TOP > 0 && (unsigned)(node - top_first) < (unsigned)RT_SMEM_TOP) {
-                    const float4 *np = s_top + 4 * (node - top_first);
-                    q0 = np[0];
-                    q1 = np[1];
-                    q2 = np[2];
-                    ch = *reinterpret_cast<const int4 *>(np + 3);
-                } else {
-                    const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
-                    q0 = __ldg(np);
-                    q1 = __ldg(np + 1);
-                    q2 = __ldg(np + 2);
-                    ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
-                }
-                float e0, e1;
-                const bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
-                const bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
-                if (h0 && h1) {
-                    const bool swap = e1 < e0;
-                    const int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
-                    if (sp < kStackSize) stack[sp++] = far_c;
-                    node = near_c;
-                } else if (h0) {
-                    node = ch.x;
-                } else if (h1) {
-                    node = ch.y;
-                } else {
-                    node = sp ? stack[--sp] : kDone;
-                }
-            }
-            if (node != kDone) {
-                const uint32_t code = ~(uint32_t)node;
-                const uint32_t first = code >> 3, count = (code & 7u) + 1u;
-                const double before = best.t;
-                for (uint32_t k = 0; k < count; ++k) {
-                    const DPrim &p = sc.prims[first + k];
-                    if (feat(F_TRI) && p.kind == PRIM_TRI) {
-                        s_tri(r, p.d, kTMin, first + k, p.rank, best);
-                    } else {
-                        r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
-                        s_prim(sc, first + k, r, kTMin, best);
-                    }
-                }
-                if (best.t != before) t_max_f = __double2float_ru(best.t);
-                node = sp ? stack[--sp] : kDone;
-            }
-        }
     }
 }
 

@@ -394,32 +394,6 @@ int toh_trace_first_hit(void *h, const RtRay *rays, uint64_t n, RtHit *hits) {
     return 0;
 }
 
-// megakernel.inl: render_deferred_kernel cuts a search in two - the flat groups first (trace_groups_sel<GROUPS_FLAT>),
-// the groups with a BVH later (deferred_bvh_search).  Returns the number of rays whose winner (primitive, face,
-// search-grade t) differs from the one-pass search of world_hit, or whose "a BVH is left" answer is wrong.
-int64_t toh_split_search_mismatches(void *h, const RtRay *rays, uint64_t n) {
-    const HostTables &t = *(HostTables *)h;
-    int64_t bad = 0;
-#pragma omp parallel for schedule(dynamic, 256) reduction(+ : bad)
-    for (int64_t k = 0; k < (int64_t)n; ++k) {
-        Ray r;
-        r.o = ld3(rays[k].origin);
-        r.d = ld3(rays[k].direction);
-        r.time = rays[k].time;
-        const V3 inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
-        Best all{RT_INF, kNoPrim, 0, 0}, split{RT_INF, kNoPrim, 0, 0};
-        trace_groups(t.ds, 0, t.ds.n_world_groups, r, inv, kTMin, all);
-        const bool left = trace_groups_sel<GROUPS_FLAT>(t.ds, 0, t.ds.n_world_groups, r, inv, kTMin, split);
-        const Best flat_only = split;
-        deferred_bvh_search(t.ds, r, split, nullptr, 0);
-        bool same = all.prim == split.prim && all.face == split.face && std::memcmp(&all.t, &split.t, sizeof(double)) == 0;
-        // "nothing left" must mean that the BVH pass changes nothing
-        if (!left && (flat_only.prim != split.prim || std::memcmp(&flat_only.t, &split.t, sizeof(double)) != 0)) same = false;
-        if (!same) ++bad;
-    }
-    return bad;
-}
-
 // kernels.cu: camera_rays_kernel
 int toh_camera_rays(const RtCamera *cam, uint32_t width, uint32_t height, const RtRenderOpts *opts, const uint32_t *px,
                     const uint32_t *py, const uint32_t *sample, uint64_t n, RtRay *rays) {

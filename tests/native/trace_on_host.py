@@ -34,8 +34,6 @@ def _lib():
     lib.toh_tables_hash.argtypes = [C.c_void_p]
     lib.toh_tables_hash.restype = C.c_uint64
     lib.toh_trace_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
-    lib.toh_split_search_mismatches.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
-    lib.toh_split_search_mismatches.restype = C.c_int64
     lib.toh_camera_rays.argtypes = [C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts), C.c_void_p,
                                     C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.toh_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.c_uint32,
@@ -100,11 +98,6 @@ class CompiledOnHost:
         _check(lib.toh_trace_first_hit(self._h, rays.ctypes.data_as(C.c_void_p), rays.shape[0],
                                        hits.ctypes.data_as(C.c_void_p)))
         return hits
-
-    def split_search_mismatches(self, rays):
-        """Rays whose two-pass search (flat groups, then the BVHs: render_deferred_kernel) differs from the one-pass search."""
-        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
-        return int(lib.toh_split_search_mismatches(self._h, rays.ctypes.data_as(C.c_void_p), rays.shape[0]))
 
     def path_radiance(self, camera, width, height, max_depth, opts, px, py, sample):
         px, py, sample = (np.ascontiguousarray(a, dtype=np.uint32) for a in (px, py, sample))

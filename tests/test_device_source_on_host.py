@@ -218,18 +218,3 @@ def test_search_resolve_split_is_the_fused_world_hit(rt, orc, toh, name):
         b, sb = comp.path_radiance_split(hs.camera, W, H, depth, opts, px, py, s)
         assert np.array_equal(a, b, equal_nan=True) and np.array_equal(sa, sb), (name, integrator)
 
-
-@pytest.mark.parametrize("name", SCENES + EXTRA_SCENES)
-def test_two_pass_search_is_the_one_pass_search(rt, orc, toh, name):
-    """render_deferred_kernel scans the flat groups of the world first and walks the groups with a BVH later
-    (trace_groups_sel<GROUPS_FLAT>, deferred_bvh_search).  The winner - primitive, face and search-grade t, to the
-    bit - must be the one trace_groups finds in one pass, on primary and on secondary rays; and when the first pass
-    says that no BVH is left, the second must not change anything."""
-    hs, comp, osc = scenes(rt, orc, toh, name)
-    W, H = 200, 200
-    opts = rt.render_opts(seed=6, integrator=hs.integrator)
-    px, py, s = random_path_ids(30000, W, H, 64, seed=21)
-    rays = orc.camera_rays(hs.camera, W, H, opts, px, py, s)
-    assert comp.split_search_mismatches(rays) == 0
-    rays2 = secondary_rays(osc.trace_first_hit(rays), rays, seed=8)
-    assert comp.split_search_mismatches(rays2) == 0

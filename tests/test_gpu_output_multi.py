@@ -189,3 +189,22 @@ def test_one_render_in_flight_per_scene(rt):
     dev.render_wait()
     torch.cuda.synchronize()
     assert torch.equal(first, out)
+
+
+@pytest.mark.parametrize("name", ["cornell", "final", "mesh"])
+def test_scene_from_compiled_blob_renders_the_same_image(rt, name):
+    """rt_compile + rt_scene_create_compiled (what a rank does with the blob another rank compiled) against
+    rt_scene_create: same tables, so the same image bit for bit and the same counters."""
+    hs = host_scene(rt, name)
+    blob = rt.compile_scene(hs.scene_desc)
+    a = rt.DeviceScene(hs.scene_desc, device=0)
+    b = rt.DeviceScene.from_compiled(blob, device=0)
+    assert a.device_bytes == b.device_bytes
+    opts = rt.render_opts(seed=3, integrator=hs.integrator)
+    ia, sa = a.render(hs.camera, 64, 48, 8, 30, opts)
+    ib, sb = b.render(hs.camera, 64, 48, 8, 30, opts)
+    assert np.array_equal(ia, ib, equal_nan=True)
+    assert (sa.paths, sa.rays) == (sb.paths, sb.rays)
+    assert a.render_info == b.render_info
+    a.close()
+    b.close()

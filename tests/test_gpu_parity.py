@@ -367,28 +367,3 @@ def test_shutter_outside_unit_range_is_refused_for_extrapolating_spheres(rt, orc
     assert ei.value.status == A.RT_ERR_UNSUPPORTED and "shutter" in str(ei.value)
     dev.close()
 
-
-@pytest.mark.parametrize("name", ["mesh", "random"])
-def test_deferred_traversal_equals_plain_megakernel(rt, orc, name, monkeypatch):
-    """render_deferred_kernel (flat groups first, the BVHs when enough lanes of a warp wait) must give render_kernel's
-    image bit for bit, whatever the threshold and the register budget: the winner of a search does not depend on the
-    order its groups are visited in."""
-    hs = host_scene(rt, name)
-    W, H, spp, depth = 96, 54, 6, 50
-    opts = rt.render_opts(seed=5, integrator=hs.integrator, flags=rt._abi.FLAG_MEGAKERNEL)
-    monkeypatch.setenv("RTB200_DEFER", "0")
-    plain = rt.DeviceScene(hs.scene_desc, device=0)
-    a, sa = plain.render(hs.camera, W, H, spp, depth, opts)
-    assert "traversal=inline" in " ".join("%s=%s" % kv for kv in plain.render_info.items())
-    monkeypatch.setenv("RTB200_DEFER", "1")
-    for budget in ("0", "1", "2", "3"):
-        monkeypatch.setenv("RTB200_RENDER_VARIANT", budget)
-        deferred = rt.DeviceScene(hs.scene_desc, device=0)
-        for thr in ("1", "7", "16", "32"):
-            monkeypatch.setenv("RTB200_DEFER_THRESHOLD", thr)
-            b, sb = deferred.render(hs.camera, W, H, spp, depth, opts)
-            assert deferred.render_info.get("traversal") == "deferred"
-            assert np.array_equal(a, b, equal_nan=True), (budget, thr)
-            assert (sa.paths, sa.rays, sa.nonfinite_samples) == (sb.paths, sb.rays, sb.nonfinite_samples)
-        deferred.close()
-    plain.close()
