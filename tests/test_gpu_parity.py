@@ -367,3 +367,43 @@ def test_shutter_outside_unit_range_is_refused_for_extrapolating_spheres(rt, orc
     assert ei.value.status == A.RT_ERR_UNSUPPORTED and "shutter" in str(ei.value)
     dev.close()
 
+
+
+@pytest.mark.parametrize("name,oracle_spp", [("final", 8), ("mesh", 1)])
+def test_full_size_properties_of_the_two_largest_configs(rt, orc, name, oracle_spp):
+    """Configs 4 and 5 at BASELINE's FULL size (800x800x10000 and 3840x2160x1024) are out of the oracle's reach
+    (minutes to hours of CPU), so the full-size renders are checked through size-independent properties:
+    (1) additivity - four disjoint sample blocks, the multi-GPU partition, add up to the one-call render;
+    (2) the oracle's first `oracle_spp` samples ARE the first samples of the full render (same Philox keys), so a
+        render restricted to that sample range must equal the oracle's image pixel by pixel at full resolution;
+    (3) unbiasedness at full size - the mean radiance of the full render equals the mean radiance of that short
+        oracle render within its Monte-Carlo error (a wrong weight anywhere in the path shows as a shifted mean)."""
+    hs = rt.HostScene(name, construction_seed=1)  # the bench's scene: the mesh at full detail (393k + 1k triangles)
+    dev, osc = rt.DeviceScene(hs.scene_desc, device=0), orc.OracleScene(hs.scene_desc)
+    W, H, spp, depth = hs.width, hs.height, hs.spp, hs.max_depth
+    full, st = dev.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=1, integrator=hs.integrator))
+    assert st.paths == W * H * spp
+    # (1)
+    acc = np.zeros((H, W, 3), dtype=np.float64)
+    q = spp // 4
+    for k in range(4):
+        n = q if k < 3 else spp - 3 * q
+        part, _ = dev.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=1, integrator=hs.integrator, sample_begin=k * q, sample_count=n))
+        acc += part
+    finite = np.isfinite(full) & np.isfinite(acc)
+    assert finite.mean() > 0.9999
+    assert rel_err(acc[finite], full[finite], floor=1e-3).max() < 1e-5
+    # (2)
+    head, _ = dev.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=1, integrator=hs.integrator, sample_begin=0, sample_count=oracle_spp))
+    ref, _ = osc.render(hs.camera, W, H, spp, depth, rt.render_opts(seed=1, integrator=hs.integrator, sample_begin=0, sample_count=oracle_spp))
+    err = rel_err(head, ref, floor=1e-6).max(axis=2)
+    assert (err <= 1e-4).mean() >= 0.999
+    # (3) per-pixel means, clipped at 20x the light's radiance so that single fireflies do not set the variance
+    a = np.clip(np.nan_to_num(full.astype(np.float64) / spp), 0, 300).mean(axis=2)
+    b = np.clip(np.nan_to_num(ref / oracle_spp), 0, 300).mean(axis=2)
+    diff = a - b
+    sigma = diff.std() / np.sqrt(diff.size)
+    print("%s full size: mean radiance gpu %.6f oracle(%d spp) %.6f, difference %.2e = %.2f sigma" % (name, a.mean(), oracle_spp, b.mean(), diff.mean(), diff.mean() / sigma))
+    assert abs(diff.mean()) <= 5.0 * sigma + 1e-4 * b.mean()
+    dev.close()
+    osc.close()
