@@ -566,7 +566,7 @@ struct BlobHeader {
     uint64_t total_bytes, hash;             // hash: FNV-1a over everything after the header
     uint64_t count[kBlobTables];            // elements per table, in the order of CompiledScene
     uint32_t elem_bytes[kBlobTables];       // sizeof of each table's element in the library that wrote the blob
-    uint32_t n_world_groups, max_bvh_depth, shutter_limited, max_bvh_stack;
+    uint32_t n_world_groups, max_bvh_depth, shutter_limited, pad;
     double background[3];
 };
 uint64_t fnv1a(const unsigned char *p, uint64_t n) {
@@ -605,7 +605,6 @@ void serialize(CompiledScene &cs, std::vector<unsigned char> &blob) {
     h.total_bytes = total;
     h.n_world_groups = cs.n_world_groups;
     h.max_bvh_depth = cs.max_bvh_depth;
-    h.max_bvh_stack = cs.max_bvh_stack;
     h.shutter_limited = cs.shutter_limited ? 1u : 0u;
     for (int a = 0; a < 3; ++a) h.background[a] = cs.background[a];
     blob.assign(total, 0);
@@ -645,8 +644,6 @@ bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string
     });
     cs.n_world_groups = h.n_world_groups;
     cs.max_bvh_depth = h.max_bvh_depth;
-    cs.max_bvh_stack = h.max_bvh_stack;
-    if (cs.max_bvh_stack + 1 > (uint32_t)kStackSize) return err = "compiled scene: tree deeper than the traversal stack", false;
     cs.shutter_limited = h.shutter_limited != 0u;
     for (int a = 0; a < 3; ++a) cs.background[a] = h.background[a];
     // what the kernels index without checking must stay inside the tables even for a blob that was made by hand
@@ -654,13 +651,6 @@ bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string
     for (const DGroup &g : cs.groups)
         if ((uint64_t)g.first_prim + g.n_prims > cs.prims.size() || (g.bvh_root >= 0 && (uint64_t)g.bvh_root >= cs.nodes.size()))
             return err = "compiled scene: group out of range", false;
-    for (const DBvhNode &n : cs.nodes)
-        for (int k = 0; k < 4; ++k) {
-            const int32_t c = n.child[k];
-            if (c == kNodeEmpty) continue;
-            if (c >= 0 ? (uint64_t)c >= cs.nodes.size() : (uint64_t)((~(uint32_t)c) >> 3) + ((~(uint32_t)c) & 7u) + 1u > cs.prims.size())
-                return err = "compiled scene: node child out of range", false;
-        }
     return true;
 }
 }  // namespace

@@ -364,6 +364,7 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     int root = b.build(0, count, 1);
     lap("build");
     b.nodes.resize((size_t)b.next.load());
+    out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth.load());
     // permute the primitives into leaf order
     {
         std::unique_ptr<DPrim[]> tmp(new DPrim[count]);  // not value-initialised: every record is overwritten below
@@ -373,86 +374,42 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
         parallel_for(count, [&](size_t i0, size_t i1) { std::copy(tmp.get() + i0, tmp.get() + i1, out.prims.begin() + first + i0); });
     }
     lap("permute");
-    // Collapse the binary tree into 4-wide nodes, breadth-first: a wide node starts from the two children of a
-    // binary node and, while it has a free slot, replaces its inner child of largest surface area by that child's two
-    // children (the child a ray is most likely to enter is the one whose test is brought forward).
-    auto area = [&](int c) {
-        const Box &x = b.nodes[c].box;
-        const double dx = x.hi[0] - x.lo[0], dy = x.hi[1] - x.lo[1], dz = x.hi[2] - x.lo[2];
-        return dx * dy + dy * dz + dz * dx;
-    };
-    struct Wide {
-        int kid[4];
-        int n;
-        uint32_t depth;
-    };
+    // breadth-first emission of the inner nodes
     uint32_t base = (uint32_t)out.nodes.size();
-    std::vector<Wide> wide;               // in BFS order
-    std::vector<int> wide_of(b.nodes.size(), -1);  // binary inner node -> the wide node that starts at it
-    std::vector<int> queue{root};
-    wide_of[root] = 0;
-    std::vector<uint32_t> depth_of{1u};
-    for (size_t h = 0; h < queue.size(); ++h) {
-        const TNode &n = b.nodes[queue[h]];
-        Wide w;
-        w.kid[0] = n.left;
-        w.kid[1] = n.right;
-        w.n = 2;
-        w.depth = depth_of[h];
-        while (w.n < 4) {
-            int pick = -1;
-            double best = -1.0;
-            for (int k = 0; k < w.n; ++k)
-                if (b.nodes[w.kid[k]].left >= 0 && area(w.kid[k]) > best) {
-                    best = area(w.kid[k]);
-                    pick = k;
-                }
-            if (pick < 0) break;
-            const TNode &c = b.nodes[w.kid[pick]];
-            w.kid[pick] = c.left;
-            w.kid[w.n++] = c.right;
-        }
-        for (int k = 0; k < w.n; ++k)
-            if (b.nodes[w.kid[k]].left >= 0) {
-                wide_of[w.kid[k]] = (int)queue.size();
-                queue.push_back(w.kid[k]);
-                depth_of.push_back(w.depth + 1);
+    std::vector<int> bfs;  // temp-node ids of inner nodes in BFS order
+    std::vector<int32_t> slot(b.nodes.size(), -1);
+    bfs.push_back(root);
+    slot[root] = 0;
+    for (size_t h = 0; h < bfs.size(); ++h) {
+        const TNode &n = b.nodes[bfs[h]];
+        for (int c : {n.left, n.right}) {
+            if (b.nodes[c].left >= 0) {
+                slot[c] = (int32_t)bfs.size();
+                bfs.push_back(c);
             }
-        wide.push_back(w);
+        }
     }
-    out.nodes.resize(base + wide.size());
-    // the most entries a traversal can hold: a visit pushes every hit child but the one it enters (trace.cuh)
-    std::vector<uint32_t> need(wide.size(), 0);
-    for (size_t h = wide.size(); h-- > 0;) {
-        uint32_t below = 0;
-        for (int k = 0; k < wide[h].n; ++k)
-            if (b.nodes[wide[h].kid[k]].left >= 0) below = std::max(below, need[(size_t)wide_of[wide[h].kid[k]]]);
-        need[h] = (uint32_t)(wide[h].n - 1) + below;
-        out.max_bvh_depth = std::max(out.max_bvh_depth, wide[h].depth);
-    }
-    out.max_bvh_stack = std::max(out.max_bvh_stack, need[0]);
+    out.nodes.resize(base + bfs.size());
     auto encode = [&](int c) -> int32_t {
         const TNode &n = b.nodes[c];
-        if (n.left >= 0) return (int32_t)(base + (uint32_t)wide_of[c]);
+        if (n.left >= 0) return (int32_t)(base + slot[c]);
         uint32_t code = ((first + n.first) << 3) | (n.count - 1);
         return (int32_t)~code;
     };
-    parallel_for(wide.size(), [&](size_t h0, size_t h1) {
+    parallel_for(bfs.size(), [&](size_t h0, size_t h1) {
         for (size_t h = h0; h < h1; ++h) {
-            const Wide &w = wide[h];
+            const TNode &n = b.nodes[bfs[h]];
             DBvhNode &dn = out.nodes[base + h];
-            for (int k = 0; k < 4; ++k) {
-                if (k < w.n) {
-                    const Box &x = b.nodes[w.kid[k]].box;
-                    dn.lox[k] = f32_down(x.lo[0]); dn.loy[k] = f32_down(x.lo[1]); dn.loz[k] = f32_down(x.lo[2]);
-                    dn.hix[k] = f32_up(x.hi[0]); dn.hiy[k] = f32_up(x.hi[1]); dn.hiz[k] = f32_up(x.hi[2]);
-                    dn.child[k] = encode(w.kid[k]);
-                } else {  // an empty slot: a point no ray reaches (and the traversal checks the child code as well)
-                    dn.lox[k] = dn.loy[k] = dn.loz[k] = dn.hix[k] = dn.hiy[k] = dn.hiz[k] = FLT_MAX;
-                    dn.child[k] = kNodeEmpty;
-                }
-                dn.pad[k] = 0;
+            const Box &b0 = b.nodes[n.left].box, &b1 = b.nodes[n.right].box;
+            for (int a = 0; a < 3; ++a) {
+                dn.lo0[a] = f32_down(b0.lo[a]);
+                dn.hi0[a] = f32_up(b0.hi[a]);
+                dn.lo1[a] = f32_down(b1.lo[a]);
+                dn.hi1[a] = f32_up(b1.hi[a]);
             }
+            dn.child0 = encode(n.left);
+            dn.child1 = encode(n.right);
+            dn.pad0 = dn.pad1 = 0;
         }
     });
     lap("emit");
@@ -1250,14 +1207,6 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
             l.kind = LIGHT_DEFAULT;
         }
         out.lights.push_back(l);
-    }
-    // The traversal keeps its pending nodes on a fixed stack (trace.cuh: kStackSize entries) and would drop a subtree
-    // - geometry - rather than overflow; a tree that could need more is refused here.  (Median splits below depth 32
-    // keep every tree of up to 2^28 primitives far from that: the 394k-triangle mesh needs 23 entries.)
-    if (out.max_bvh_stack + 1 > (uint32_t)kStackSize) {
-        err = "a BVH of this scene needs " + std::to_string(out.max_bvh_stack + 1) + " traversal stack entries, the kernels have " +
-              std::to_string(kStackSize);
-        return RT_ERR_UNSUPPORTED;
     }
     return RT_OK;
 }

@@ -24,8 +24,7 @@ struct CompiledScene {
     std::vector<uint8_t> texels;
     uint32_t n_world_groups = 0;
     double background[3] = {0, 0, 0};
-    uint32_t max_bvh_depth = 0;  // of the 4-wide trees
-    uint32_t max_bvh_stack = 0;  // most entries a traversal can have on its stack (must stay below kStackSize)
+    uint32_t max_bvh_depth = 0;
     // Some MovingSphere has (time0, time1) != (0, 1): its centre extrapolates (sphere.rs:144-146) and the bounds
     // were built for shutter times in [0, 1] (compile.cpp: prim_box) - a camera whose shutter leaves that range is
     // refused at render time instead of being culled wrongly.

@@ -7,7 +7,7 @@
 //   ops     translate / rotate / flip steps      (translate.rs, rotate.rs, hit.rs:99-133)
 //   chains  op sequences, outermost first: the wrappers above a primitive
 //   groups  primitives that share a ray transform; linear or with a BVH
-//   nodes   flattened SAH BVH collapsed to four child boxes per node, breadth-first order
+//   nodes   flattened SAH BVH2, two child boxes per node, breadth-first order
 //   media   ConstantMedium records (medium.rs) with their boundary sub-scene
 //   lights  the light list (pdf.rs PDF::Hittable -> hit.rs:90-96)
 #pragma once
@@ -67,22 +67,16 @@ struct alignas(16) DGroup {
     double m[9], t[3];
 };
 
-// A 4-wide node: up to four child boxes, 128 bytes = seven 128-bit loads used of eight (one box coordinate of all
-// four children per load).  The binary SAH tree is collapsed into it (compile.cpp): a ray that walks the tree is a
-// chain of dependent node fetches, and a 4-wide node halves the length of that chain - what the long rays of a warp,
-// the ones the others wait for, are bound by (profiles/r2_d_render_kernel_mesh4spp.txt: 4 active lanes in the node
-// loop, long_scoreboard the largest stall).
-// child >= 0: inner node; child < 0: leaf, ~child = (first_prim << 3) | (count-1); kNodeEmpty: no child in this slot
-// (its box is a point at +FLT_MAX, which no ray reaches).  The boxes only cull, so they are fp32: each bound is the
-// f64 bound rounded OUTWARD, which together with the traversal's directed per-ray constants and its relative slack
-// on the slab distances (trace.cuh slab2f) can only make a box larger than the f64 box, never smaller.
-constexpr int32_t kNodeEmpty = (int32_t)0x80000000;
-constexpr int kStackSize = 64;  // traversal stack entries per ray; compile_scene refuses a tree that could need more
+// Two child boxes per node, 64 bytes = four 128-bit loads.  child >= 0: inner node; child < 0:
+// leaf, ~child = (first_prim << 3) | (count-1).  The boxes only cull, so they are fp32: each
+// bound is the f64 bound rounded OUTWARD, which together with the traversal's rounded-up /
+// rounded-down ray origin and its relative slack on the slab distances (trace.cuh slab2f) can
+// only make a box larger than the f64 box, never smaller.
 struct alignas(16) DBvhNode {
-    float lox[4], loy[4], loz[4];
-    float hix[4], hiy[4], hiz[4];
-    int32_t child[4];
-    int32_t pad[4];
+    float lo0[3], hi0[3];
+    float lo1[3], hi1[3];
+    int32_t child0, child1;
+    int32_t pad0, pad1;
 };
 
 struct alignas(16) DMedium {

@@ -43,6 +43,7 @@ constexpr double kPi = 3.14159265358979323846264338327950288;
 constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
 constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
 constexpr uint32_t kMediumFlag = 0x80000000u;
+constexpr int kStackSize = 64;
 #define RT_INF (__longlong_as_double(0x7FF0000000000000ll))
 
 // ---------------------------------------------------------------------------
@@ -395,48 +396,11 @@ RT_DEV bool slab2f(const FRay &f, float lx, float ly, float lz, float hx, float 
     return tin <= tout;
 }
 
-// One visit of a 4-wide node: the four child boxes are tested, the nearest hit child is returned (or the next
-// pending node when none is hit), the other hit children are pushed so that the nearer one is popped first.
-// kTraversalDone when nothing is left.  Shared by the megakernel's trace_group and the wavefront extend stage.
-constexpr int kTraversalDone = kNodeEmpty;
-RT_DEV void order2(float &ka, int &ca, float &kb, int &cb) {  // compare-exchange: (ka, ca) becomes the nearer
-    const bool swap = kb < ka;
-    const float k0 = swap ? kb : ka, k1 = swap ? ka : kb;
-    const int c0 = swap ? cb : ca, c1 = swap ? ca : cb;
-    ka = k0; kb = k1; ca = c0; cb = c1;
-}
-RT_DEV int visit_node4(const DBvhNode *nodes, int node, const FRay &f, float t_min_f, float t_max_f, int *stack, int &sp) {
-    const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-    const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2);
-    const float4 hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
-    const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 6));
-    const float kMiss = __int_as_float(0x7f800000);
-    float e0, e1, e2, e3;
-    const bool h0 = slab2f(f, lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, t_min_f, t_max_f, e0) && ch.x != kNodeEmpty;
-    const bool h1 = slab2f(f, lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, t_min_f, t_max_f, e1) && ch.y != kNodeEmpty;
-    const bool h2 = slab2f(f, lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, t_min_f, t_max_f, e2) && ch.z != kNodeEmpty;
-    const bool h3 = slab2f(f, lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, t_min_f, t_max_f, e3) && ch.w != kNodeEmpty;
-    // (entry distance, child) pairs; a child that is not hit becomes kNodeEmpty with distance +inf.  Whether a child
-    // is visited depends on the code alone, the distance only orders the visits.
-    float k0 = h0 ? e0 : kMiss, k1 = h1 ? e1 : kMiss, k2 = h2 ? e2 : kMiss, k3 = h3 ? e3 : kMiss;
-    int c0 = h0 ? ch.x : kNodeEmpty, c1 = h1 ? ch.y : kNodeEmpty, c2 = h2 ? ch.z : kNodeEmpty, c3 = h3 ? ch.w : kNodeEmpty;
-    order2(k0, c0, k1, c1);  // sorting network for four keys
-    order2(k2, c2, k3, c3);
-    order2(k0, c0, k2, c2);
-    order2(k1, c1, k3, c3);
-    order2(k1, c1, k2, c2);
-    if (c3 != kNodeEmpty && sp < kStackSize) stack[sp++] = c3;
-    if (c2 != kNodeEmpty && sp < kStackSize) stack[sp++] = c2;
-    if (c1 != kNodeEmpty && sp < kStackSize) stack[sp++] = c1;
-    if (c0 != kNodeEmpty) return c0;
-    return sp ? stack[--sp] : kTraversalDone;
-}
-
 // g.bvh_root >= 0: a BVH node; < 0: a leaf code (a small group is a single leaf).  "while-while"
 // traversal: every lane first descends inner nodes until it holds a leaf (or is done), then the
 // leaves are tested together, which keeps the warp together in both phases.
 RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double t_min, Best &best) {
-    const int kDone = kTraversalDone;
+    const int kDone = (int)0x80000000;
     int stack[kStackSize];
     int sp = 0;
     int node = g.bvh_root;
@@ -449,7 +413,26 @@ RT_DEV void trace_group(const DScene &sc, const DGroup &g, const SRay &r, double
         t_max_f = __double2float_ru(best.t);
     }
     while (node != kDone) {
-        while (feat(F_BVH) && node >= 0) node = visit_node4(sc.nodes, node, f, t_min_f, t_max_f, stack, sp);
+        while (feat(F_BVH) && node >= 0) {
+            const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
+            float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+            float e0, e1;
+            bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
+            bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
+            if (h0 && h1) {
+                bool swap = e1 < e0;
+                int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
+                if (sp < kStackSize) stack[sp++] = far_c;
+                node = near_c;
+            } else if (h0) {
+                node = ch.x;
+            } else if (h1) {
+                node = ch.y;
+            } else {
+                node = sp ? stack[--sp] : kDone;
+            }
+        }
         if (node < 0 && node != kDone) {
             uint32_t code = ~(uint32_t)node;
             uint32_t first = code >> 3, count = (code & 7u) + 1u;

@@ -396,7 +396,7 @@ template <bool MEDIA>
 __global__ void __launch_bounds__(kWfBlock, RT_WF_EXTEND_MIN_BLOCKS)
 wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPool pool, uint32_t seed, uint32_t max_depth,
                  uint32_t leave_threshold) {
-    const int kDone = kTraversalDone;
+    const int kDone = (int)0x80000000;
     const unsigned n = pool.n_slots;
     unsigned *cursor = &pool.ctl->ext_cursor;
     const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -573,7 +573,24 @@ wf_extend_kernel(const __grid_constant__ DScene sc, const __grid_constant__ WfPo
         // ---- C: traverse --------------------------------------------------------------------
         while (node != kDone) {
             while (node >= 0) {
-                node = visit_node4(sc.nodes, node, f, t_min_f, t_max_f, stack, sp);
+                const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
+                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+                const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
+                float e0, e1;
+                const bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
+                const bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
+                if (h0 && h1) {
+                    const bool swap = e1 < e0;
+                    const int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
+                    if (sp < kStackSize) stack[sp++] = far_c;
+                    node = near_c;
+                } else if (h0) {
+                    node = ch.x;
+                } else if (h1) {
+                    node = ch.y;
+                } else {
+                    node = sp ? stack[--sp] : kDone;
+                }
                 // lanes that hold a leaf wait here for the others: stop descending once few are left
                 if ((unsigned)__popc(__ballot_sync(__activemask(), node >= 0)) < inner_below) break;
             }

@@ -197,23 +197,15 @@ struct TableCheck {
         if (node_seen[node]) return bad("node " + std::to_string(node) + " has two parents");
         node_seen[node] = 1;
         const DBvhNode &n = cs.nodes[node];
-        int n_kids = 0;
-        for (int k = 0; k < 4; ++k) {
-            if (n.child[k] == kNodeEmpty) continue;
-            ++n_kids;
-            Bounds bk;
-            bk.lo[0] = n.lox[k]; bk.lo[1] = n.loy[k]; bk.lo[2] = n.loz[k];
-            bk.hi[0] = n.hix[k]; bk.hi[1] = n.hiy[k]; bk.hi[2] = n.hiz[k];
-            for (int a = 0; a < 3; ++a) {
-                if (!(bk.lo[a] <= bk.hi[a])) return bad("node " + std::to_string(node) + ": empty or NaN child box");
-                if (within && !(within->lo[a] <= bk.lo[a] && within->hi[a] >= bk.hi[a]))
-                    return bad("node " + std::to_string(node) + ": a child box sticks out of its parent's");
-            }
-            // pending nodes: this visit leaves the other children on the stack while child k is walked
-            if (!subtree(gi, n.child[k], &bk, depth + 1)) return false;
+        Bounds b0, b1;
+        for (int a = 0; a < 3; ++a) {
+            b0.lo[a] = n.lo0[a]; b0.hi[a] = n.hi0[a];
+            b1.lo[a] = n.lo1[a]; b1.hi[a] = n.hi1[a];
+            if (!(n.lo0[a] <= n.hi0[a]) || !(n.lo1[a] <= n.hi1[a])) return bad("node " + std::to_string(node) + ": empty or NaN child box");
+            if (within && !(within->lo[a] <= b0.lo[a] && within->hi[a] >= b0.hi[a] && within->lo[a] <= b1.lo[a] && within->hi[a] >= b1.hi[a]))
+                return bad("node " + std::to_string(node) + ": a child box sticks out of its parent's");
         }
-        if (n_kids < 2) return bad("node " + std::to_string(node) + ": fewer than two children");
-        return true;
+        return subtree(gi, n.child0, &b0, depth + 1) && subtree(gi, n.child1, &b1, depth + 1);
     }
 
     bool run() {
@@ -269,8 +261,7 @@ struct TableCheck {
         }
         for (size_t i = 0; i < cs.nodes.size(); ++i)
             if (!node_seen[i]) return bad("node " + std::to_string(i) + " is unreachable");
-        if (cs.max_bvh_stack + 1 > (uint32_t)kStackSize) return bad("a BVH needs more traversal stack than the kernels have");
-        if (max_depth > cs.max_bvh_depth + 1) return bad("max_bvh_depth is not the depth of the deepest tree");
+        if (max_depth >= (uint32_t)kStackSize) return bad("BVH deeper than the traversal stack");
         // ranks: the reference's traversal order is a total order inside each sub-scene
         auto ranks_unique = [&](uint32_t g0, uint32_t g1, const char *what) {
             std::vector<uint32_t> r;
