@@ -644,6 +644,7 @@ bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string
     });
     cs.n_world_groups = h.n_world_groups;
     cs.max_bvh_depth = h.max_bvh_depth;
+    if (cs.max_bvh_depth >= (uint32_t)kStackSize) return err = "compiled scene: tree deeper than the traversal stack", false;
     cs.shutter_limited = h.shutter_limited != 0u;
     for (int a = 0; a < 3; ++a) cs.background[a] = h.background[a];
     // what the kernels index without checking must stay inside the tables even for a blob that was made by hand
@@ -651,6 +652,10 @@ bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string
     for (const DGroup &g : cs.groups)
         if ((uint64_t)g.first_prim + g.n_prims > cs.prims.size() || (g.bvh_root >= 0 && (uint64_t)g.bvh_root >= cs.nodes.size()))
             return err = "compiled scene: group out of range", false;
+    for (const DBvhNode &n : cs.nodes)
+        for (const int32_t c : {n.child0, n.child1})
+            if (c >= 0 ? (uint64_t)c >= cs.nodes.size() : (uint64_t)((~(uint32_t)c) >> 3) + ((~(uint32_t)c) & 7u) + 1u > cs.prims.size())
+                return err = "compiled scene: node child out of range", false;
     return true;
 }
 }  // namespace

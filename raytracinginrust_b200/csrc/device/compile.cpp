@@ -1208,6 +1208,15 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         }
         out.lights.push_back(l);
     }
+    // The traversal keeps its pending nodes on a fixed stack (tables.h: kStackSize entries; a visit pushes at most
+    // one child, so a tree of depth d needs fewer than d) and would drop a subtree - geometry - rather than
+    // overflow; a tree that could need more is refused here.  (Median splits below depth 32 keep every tree of up to
+    // 2^28 primitives far from that: the 394k-triangle mesh is 22 levels deep.)
+    if (out.max_bvh_depth >= (uint32_t)kStackSize) {
+        err = "a BVH of this scene is " + std::to_string(out.max_bvh_depth) + " levels deep, the traversal stack of the kernels holds " +
+              std::to_string(kStackSize) + " entries";
+        return RT_ERR_UNSUPPORTED;
+    }
     return RT_OK;
 }
 

@@ -72,6 +72,7 @@ struct alignas(16) DGroup {
 // bound is the f64 bound rounded OUTWARD, which together with the traversal's rounded-up /
 // rounded-down ray origin and its relative slack on the slab distances (trace.cuh slab2f) can
 // only make a box larger than the f64 box, never smaller.
+constexpr int kStackSize = 64;  // traversal stack entries per ray; compile_scene refuses a tree that could need more
 struct alignas(16) DBvhNode {
     float lo0[3], hi0[3];
     float lo1[3], hi1[3];

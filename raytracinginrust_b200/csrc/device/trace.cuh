@@ -43,7 +43,6 @@ constexpr double kPi = 3.14159265358979323846264338327950288;
 constexpr double kTMin = 0.00001;  // src/main.rs:48 (§Q1)
 constexpr uint32_t kNoPrim = 0xFFFFFFFFu;
 constexpr uint32_t kMediumFlag = 0x80000000u;
-constexpr int kStackSize = 64;
 #define RT_INF (__longlong_as_double(0x7FF0000000000000ll))
 
 // ---------------------------------------------------------------------------
