@@ -389,7 +389,8 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line (no "NCCL version" banner)
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version banner and warnings: not on stdout, which holds the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
