@@ -66,9 +66,10 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
 }
 
 // variant bits 0-1: the register budget, as resident blocks per SM - 0: 6 blocks (80 registers), 1: 8 (64),
-// 2: 12 (40), 3: 7 (72: the smallest budget at which the BVH node loop keeps its ray
-// constants in registers).  Measured per scene class (profiles/r1_e_launch_bounds.md): flat scenes peak at 6, media
-// and triangle-BVH scenes at 8, sphere-BVH scenes (cheap leaves, latency-bound) at 12.
+// 2: 12 (40).  Measured per scene class (profiles/r1_e_launch_bounds.md): flat scenes peak at 6, media
+// and triangle-BVH scenes at 8, sphere-BVH scenes (cheap leaves, latency-bound) at 12.  A 72-register build (7 blocks: the smallest budget at
+// which the BVH node loop keeps its ray constants in registers) was measured in r2-g and changed nothing
+// (profiles/r2_g_register_budgets.md).
 // variant bit 2: the scene has media (the kernel carries the boundary-query loop of medium.rs)
 // f(kernel, threads per block)
 template <class F>
@@ -76,12 +77,10 @@ static cudaError_t with_render_kernel(int variant, F f) {
     switch (variant & 7) {
         case 0: return f(render_kernel<6, false>, kRenderBlock);
         case 1: return f(render_kernel<8, false>, kRenderBlock);
-        case 2: return f(render_kernel<12, false>, kRenderBlock);
-        case 3: return f(render_kernel<7, false>, kRenderBlock);
+        case 2: case 3: return f(render_kernel<12, false>, kRenderBlock);
         case 4: return f(render_kernel<6, true>, kRenderBlock);
         case 5: return f(render_kernel<8, true>, kRenderBlock);
-        case 6: return f(render_kernel<12, true>, kRenderBlock);
-        default: return f(render_kernel<7, true>, kRenderBlock);
+        default: return f(render_kernel<12, true>, kRenderBlock);
     }
 }
 static cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
