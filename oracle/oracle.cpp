@@ -1469,6 +1469,18 @@ int oracle_scene_create(const RtSceneDesc *d, OScene **out) {
         g_err = "lights must be a LIST node";
         return RT_ERR_BAD_ARGUMENT;
     }
+    // a list nested in the light list would need a second `choose` (hit.rs:94-96) with random numbers of its own;
+    // the draw convention has one light index per scatter, so both sides of the parity tests refuse it
+    for (uint32_t i = 0; i < sd.nodes[d->lights].count; ++i) {
+        const uint64_t at = (uint64_t)sd.nodes[d->lights].child + i;
+        if (at >= sd.child_index.size()) break;  // build_node reports the range error
+        uint32_t id = sd.child_index[at];
+        for (uint32_t guard = 0; id < sd.nodes.size() && sd.nodes[id].kind == RT_NODE_FLIP && guard < sd.nodes.size(); ++guard) id = sd.nodes[id].child;
+        if (id < sd.nodes.size() && sd.nodes[id].kind == RT_NODE_LIST) {
+            g_err = "a HittableList nested in the light list is not supported";
+            return RT_ERR_UNSUPPORTED;
+        }
+    }
     HPtr l = build_node(*sc, d->lights, state, ok);
     if (!ok) return RT_ERR_BAD_ARGUMENT;
     sc->lights = std::static_pointer_cast<HittableList>(l);

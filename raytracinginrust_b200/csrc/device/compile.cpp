@@ -18,6 +18,7 @@
 #include <memory>
 #include <queue>
 #include <thread>
+#include <unordered_map>
 
 namespace rtb200dev {
 namespace {
@@ -650,18 +651,46 @@ struct Walker {
         }
         return false;
     }
+    // chains and groups are looked up by a hash of their ops (a scene of n individually transformed instances has n
+    // of each; the linear scans that were here made the walk quadratic in n)
+    static uint64_t ops_hash(const std::vector<DOp> &ops) {
+        uint64_t h = 1469598103934665603ull;
+        for (const DOp &op : ops) {
+            uint64_t w[7] = {op.kind, op.axis, 0, 0, 0, 0, 0};
+            std::memcpy(&w[2], &op.sin_theta, sizeof(double) * 5);
+            for (uint64_t x : w) h = (h ^ x) * 1099511628211ull;
+        }
+        return h;
+    }
+    std::unordered_multimap<uint64_t, uint32_t> chain_index;
+    std::unordered_multimap<uint64_t, size_t> group_index;  // of the vector `groups` points at (use_groups resets it)
+    void use_groups(std::vector<GroupBuild> *g) {
+        groups = g;
+        group_index.clear();
+        for (size_t i = 0; i < g->size(); ++i) group_index.emplace(ops_hash((*g)[i].xform) * 2u + ((*g)[i].tree ? 1u : 0u), i);
+        cache_valid = false;
+    }
     uint32_t intern_chain(const std::vector<DOp> &ops) {
-        for (size_t i = 0; i < chain_ops.size(); ++i)
-            if (same_ops(chain_ops[i], ops)) return (uint32_t)i;
+        const uint64_t h = ops_hash(ops);
+        auto range = chain_index.equal_range(h);
+        for (auto it = range.first; it != range.second; ++it)
+            if (same_ops(chain_ops[it->second], ops)) return it->second;
         chain_ops.push_back(ops);
+        chain_index.emplace(h, (uint32_t)(chain_ops.size() - 1));
         return (uint32_t)(chain_ops.size() - 1);
     }
     GroupBuild &group_for_stack() {
         std::vector<DOp> xf;
         for (const DOp &op : stack)
             if (op.kind != OP_FLIP) xf.push_back(op);
-        for (GroupBuild &g : *groups)
+        const uint64_t key = ops_hash(xf) * 2u + (in_bvh > 0 ? 1u : 0u);
+        auto &index = group_index;
+        auto range = index.equal_range(key);
+        for (auto it = range.first; it != range.second; ++it) {
+            GroupBuild &g = (*groups)[it->second];
             if (g.tree == (in_bvh > 0) && same_ops(g.xform, xf)) return g;
+        }
+        index.emplace(key, groups->size());
         groups->emplace_back();
         groups->back().xform = xf;
         groups->back().tree = in_bvh > 0;
@@ -1127,7 +1156,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     Walker w(d, out, err);
     std::vector<GroupBuild> world_groups;
     std::vector<PendingMedium> pending;
-    w.groups = &world_groups;
+    w.use_groups(&world_groups);
     w.media = &pending;
     w.cache_valid = false;
     if (!w.walk(d.world, 0)) return w.status;
@@ -1143,7 +1172,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     for (const PendingMedium &pm : pending) {
         const RtNode &n = d.nodes[pm.node];
         std::vector<GroupBuild> bgroups;
-        w.groups = &bgroups;
+        w.use_groups(&bgroups);
         w.media = nullptr;
         w.stack = pm.stack;
         w.cache_valid = false;
@@ -1196,7 +1225,18 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         const RtNode &n = d.nodes[id];
         DLight l;
         std::memset(&l, 0, sizeof(l));
+        // A HittableList forwards pdf_value / random to its members (hit.rs:90-96), so a list nested in the light
+        // list is sampled through a second `choose` with random numbers of its own; the slot-addressed draw of
+        // DESIGN.md §3 has one light index per scatter.  Refused rather than sampled differently from the reference.
+        if (n.kind == RT_NODE_LIST) {
+            err = "a HittableList nested in the light list is not supported (flatten it into the light list)";
+            return RT_ERR_UNSUPPORTED;
+        }
         if (n.kind == RT_NODE_RECT) {
+            if (n.axis > 2) {
+                err = "bad rect plane in the light list";
+                return RT_ERR_BAD_ARGUMENT;
+            }
             l.kind = LIGHT_RECT;
             l.axis = n.axis;
             for (int k = 0; k < 5; ++k) l.d[k] = n.v[k];
