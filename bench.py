@@ -21,8 +21,9 @@ The JSON line (rank 0):
   roofline_hbm  the same kernel against measured HBM copy bandwidth (SURVEY §8(d)'s byte model) with the
              MEASURED dram bytes of an ncu capture of this build (profiles/ncu_traffic.json): this path
              is not HBM-bound, the entry is there to show it
-  workloads  the Next Week final scene and the triangle-mesh scene (the configs the scaling targets
-             name) at reduced spp: device and e2e numbers measured the same way
+  workloads  the other four configs (RTiOW and Cornell smoke at full spp, the Next Week final scene and the
+             triangle-mesh scene - the ones the scaling targets name - at reduced spp): device and e2e
+             numbers measured the same way
   cpu_baseline   the f64 oracle (a restatement of the reference: no Rust toolchain here) on the
              box's host cores, on a bounded sample of the same workload (N = 1 only)
 `--impl reference` times that CPU oracle as the reference arm (rank 0 only) in a process that never
@@ -47,9 +48,10 @@ WORKLOADS = {
     "final": "Next Week final scene (configs[3]): 800x800, 10000 spp",
     "mesh": "Triangle-mesh scene (configs[4]): 3840x2160, 1024 spp (Venus stand-in + teapot)",
 }
-# The two configs the scaling targets of BASELINE.json name, measured next to the headline at a bounded spp
-# (throughput is linear in spp; the image size, depth and scene are the config's own).
-EXTRA_WORKLOADS = {"final": 2000, "mesh": 32}
+# The other four configs of BASELINE.json, measured next to the headline: configs[0] and [2] at their full spp, the
+# two the scaling targets name ([3], [4]) at a bounded spp (throughput is linear in spp; image size, depth and scene
+# are the config's own).
+EXTRA_WORKLOADS = {"final": 2000, "mesh": 32, "cornell_smoke": 1000, "random": 800}
 
 # f64 bytes a test has to read (the reference's own parameters), SURVEY §8(d) restated for f64:
 # AABB 6 doubles; sphere c+r; moving sphere c0,c1,t0,t1,r; rect a0,a1,b0,b1,k; triangle 3 vertices;
@@ -511,7 +513,7 @@ def main():
         xk, xr = x.pop("_kern_ms"), x.pop("_rank_rays")
         xw, xh, xdepth, xint = x.pop("_job")
         if world == 1 and not args.no_cpu_baseline and xk:
-            small = {"final": 2, "mesh": 1}.get(name, 1)
+            small = {"final": 2, "mesh": 1, "cornell_smoke": 8, "random": 8}.get(name, 1)
             r = cpu_oracle_run(name, xw, xh, small, xdepth, xint)
             _, _, xflops = algorithmic_work(r["counters"])
             x["roofline"] = fp64_roofline(xflops, xr / len(xk), sum(xk) / len(xk) * 1e-3, fp64_peak,

@@ -247,6 +247,14 @@ int rt_device_count(void);
  * device representation on CUDA device `device` and upload it once.
  * Replaces: the scene borrow held by the loop at src/main.rs:624,827. */
 RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene);
+/* The same with options.  RT_CREATE_GPU_BVH: BVH::new (src/bvh.rs:18-73) runs ON THE GPU for every
+ * tree of at least 4096 primitives - a linear BVH (Morton codes, radix sort, Karras hierarchy,
+ * bottom-up refit: about a millisecond for the 394k triangles of config 5) instead of the host's
+ * binned-SAH build (0.2-0.3 s).  Rays find the same hits on either tree, so images are
+ * bit-identical; the linear tree is slower to traverse, so this is for callers that want the
+ * first image sooner (previews, short renders), not the default.   */
+enum { RT_CREATE_GPU_BVH = 1 };
+RtStatus rt_scene_create_ex(const RtSceneDesc *desc, int device, uint32_t create_flags, RtScene **out_scene);
 void rt_scene_destroy(RtScene *scene);
 
 /* Bytes of device memory the compiled scene occupies (h2d traffic of create). */

@@ -25,6 +25,7 @@ INTEGRATOR_HEAD, INTEGRATOR_LEGACY = 0, 1
 FLAG_TRACE_ZERO_THROUGHPUT = 1
 FLAG_WAVEFRONT = 2   # generate / extend / shade stages over HBM-resident ray queues
 FLAG_MEGAKERNEL = 4  # one persistent kernel, path state in registers
+CREATE_GPU_BVH = 1   # rt_scene_create_ex: build large trees on the GPU
 
 
 class RtNode(C.Structure):
@@ -102,4 +103,4 @@ EXPORTS = ["rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_d
            "rt_scene_group_create", "rt_scene_group_destroy", "rt_scene_group_size", "rt_scene_group_scene",
            "rt_render_multi", "rt_encode_rgb8", "rt_encode_ppm",
            "rt_compile", "rt_compiled_data", "rt_compiled_size", "rt_compiled_hash", "rt_compiled_destroy",
-           "rt_scene_create_compiled"]
+           "rt_scene_create_compiled", "rt_scene_create_ex"]

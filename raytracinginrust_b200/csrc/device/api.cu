@@ -52,6 +52,7 @@ struct RtScene {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t features = 0;     // Feat bits of the scene (the integrator bit is added per render)
+    uint32_t gpu_built_trees = 0;  // trees built by gpu_bvh.cu (RT_CREATE_GPU_BVH)
     int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
@@ -386,6 +387,7 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         s.pending_launches += 1;
     }
     s.render_info += " chunks=" + std::to_string(P.n_chunks) + " chunk_size=" + std::to_string(P.chunk_size);
+    if (s.gpu_built_trees) s.render_info += " gpu_built_trees=" + std::to_string(s.gpu_built_trees);
     CU(launch_reduce_planes(s.planes, out_dev, (uint64_t)P.width * P.height * 3, P.n_chunks, st));
     CU(cudaEventRecord(s.ev1, st));
     CU(cudaMemcpyAsync(s.counters_host, s.counters, sizeof(unsigned long long) * kNumCounters, cudaMemcpyDeviceToHost, st));
@@ -481,6 +483,20 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
     UP(perlin);
     UP(texels);
 #undef UP
+    // trees the compiler left for the device (RT_CREATE_GPU_BVH): built in place in the uploaded tables
+    if (!cs.pending_bvh.empty()) {
+        float *boxes_dev = nullptr;
+        CU(cudaMalloc((void **)&boxes_dev, cs.pending_boxes.size() * sizeof(float)));
+        cudaError_t e = cudaMemcpy(boxes_dev, cs.pending_boxes.data(), cs.pending_boxes.size() * sizeof(float), cudaMemcpyHostToDevice);
+        for (size_t k = 0; e == cudaSuccess && k < cs.pending_bvh.size(); ++k) {
+            const CompiledScene::PendingBvh &pb = cs.pending_bvh[k];
+            e = build_bvh_on_device(const_cast<DPrim *>(d.prims) + pb.first_prim, pb.n_prims, boxes_dev + 6 * pb.first_box,
+                                    const_cast<DBvhNode *>(d.nodes) + pb.node_base, pb.node_base, pb.first_prim, pb.lo, pb.hi, nullptr);
+        }
+        cudaFree(boxes_dev);
+        if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e));
+        s->gpu_built_trees = (uint32_t)cs.pending_bvh.size();
+    }
     d.n_world_groups = cs.n_world_groups;
     d.n_media = (uint32_t)cs.media.size();
     d.n_lights = (uint32_t)cs.lights.size();
@@ -536,14 +552,24 @@ RtStatus rt_measure_fp64_peak(int device, double *tflops_out) {
     return RT_OK;
 }
 
-RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
+RtStatus rt_scene_create_ex(const RtSceneDesc *desc, int device, uint32_t create_flags, RtScene **out_scene) {
     if (!desc || !out_scene) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     *out_scene = nullptr;
+    if (create_flags & ~(uint32_t)RT_CREATE_GPU_BVH) return fail(RT_ERR_BAD_ARGUMENT, "unknown create flag");
     CompiledScene cs;
     std::string err;
-    RtStatus st = compile_scene(*desc, cs, err);
+    CompileOptions opts;
+    if (create_flags & RT_CREATE_GPU_BVH) opts.gpu_bvh_min_prims = 4096;  // smaller trees: the host build is microseconds
+    RtStatus st = compile_scene(*desc, cs, err, opts);
     if (st != RT_OK) return fail(st, err);
     return create_on_device(cs, device, out_scene);
+}
+
+RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scene) {
+    uint32_t flags = 0;
+    if (const char *v = std::getenv("RTB200_GPU_BVH"))  // A/B switch for the probes
+        if (std::atoi(v) != 0) flags |= RT_CREATE_GPU_BVH;
+    return rt_scene_create_ex(desc, device, flags, out_scene);
 }
 
 void rt_scene_destroy(RtScene *scene) { delete scene; }

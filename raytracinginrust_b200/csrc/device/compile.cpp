@@ -951,7 +951,7 @@ struct Walker {
     }
 };
 
-bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::string &err) {
+bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::string &err, const CompileOptions &opts) {
     // List members stay apart from the tree of the same transform only while they are few enough to be scanned
     // linearly; a larger flat part would need a second tree that every ray walks next to the first, so it joins
     // the tree (measured on the Next Week final scene, 7 list members next to the 400 ground boxes: one tree 36.1 ms,
@@ -1000,7 +1000,38 @@ bool finalize_groups(CompiledScene &out, std::vector<GroupBuild> &gb, std::strin
             dg.bmax[a] = wb.hi[a];
         }
         bool has_bvh = dg.n_prims > LINEAR_MAX;
-        if (has_bvh) {
+        if (has_bvh && opts.gpu_bvh_min_prims > 0 && dg.n_prims >= opts.gpu_bvh_min_prims) {
+            // the tree is left to gpu_bvh.cu: the primitives stay in walk order, their boxes go along as fp32
+            CompiledScene::PendingBvh pb;
+            pb.group = (uint32_t)out.groups.size();
+            pb.first_prim = dg.first_prim;
+            pb.n_prims = dg.n_prims;
+            pb.node_base = (uint32_t)out.nodes.size();
+            pb.first_box = out.pending_boxes.size() / 6;
+            for (int a = 0; a < 3; ++a) {
+                pb.lo[a] = ob.lo[a];
+                pb.hi[a] = ob.hi[a];
+            }
+            out.pending_boxes.resize(out.pending_boxes.size() + 6 * (size_t)dg.n_prims);
+            float *dst = out.pending_boxes.data() + 6 * pb.first_box;
+            const uint32_t first = dg.first_prim;
+            parallel_for(dg.n_prims, [&](size_t i0, size_t i1) {
+                for (size_t i = i0; i < i1; ++i) {
+                    Box b = prim_box(out.prims[first + i]);
+                    b.pad();
+                    for (int a = 0; a < 3; ++a) {
+                        dst[6 * i + a] = f32_down(b.lo[a]);
+                        dst[6 * i + 3 + a] = f32_up(b.hi[a]);
+                    }
+                }
+            });
+            DBvhNode zero;
+            std::memset(&zero, 0, sizeof(zero));
+            out.nodes.resize(out.nodes.size() + (size_t)dg.n_prims - 1, zero);
+            dg.bvh_root = (int32_t)pb.node_base;
+            out.max_bvh_depth = std::max(out.max_bvh_depth, 62u);  // a radix tree over 62-bit keys (gpu_bvh.cu)
+            out.pending_bvh.push_back(pb);
+        } else if (has_bvh) {
             dg.bvh_root = build_group_bvh(out, dg.first_prim, dg.n_prims);
         } else {
             // a small group is one leaf: same encoding as a BVH leaf (LINEAR_MAX <= 8)
@@ -1055,7 +1086,7 @@ bool texture_needs_uv(const RtSceneDesc &d, uint32_t id, int depth) {
 
 }  // namespace
 
-RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &err) {
+RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &err, const CompileOptions &opts) {
     if (d.abi_version != RTB200_ABI_VERSION) {
         err = "abi version mismatch";
         return RT_ERR_BAD_ARGUMENT;
@@ -1161,7 +1192,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
     w.cache_valid = false;
     if (!w.walk(d.world, 0)) return w.status;
     lap("walk");
-    if (!finalize_groups(out, world_groups, err)) return RT_ERR_BAD_ARGUMENT;
+    if (!finalize_groups(out, world_groups, err, opts)) return RT_ERR_BAD_ARGUMENT;
     lap("finalize (BVH build)");
     out.n_world_groups = (uint32_t)out.groups.size();
     if (out.n_world_groups == 0 && pending.empty()) {
@@ -1180,7 +1211,7 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         DMedium dm;
         std::memset(&dm, 0, sizeof(dm));
         dm.first_group = (uint32_t)out.groups.size();
-        if (!finalize_groups(out, bgroups, err)) return RT_ERR_BAD_ARGUMENT;
+        if (!finalize_groups(out, bgroups, err, opts)) return RT_ERR_BAD_ARGUMENT;
         dm.n_groups = (uint32_t)out.groups.size() - dm.first_group;
         dm.chain = w.intern_chain(pm.stack);
         dm.material = n.material;

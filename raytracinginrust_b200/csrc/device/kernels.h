@@ -40,6 +40,10 @@ cudaError_t launch_camera_rays(const RtCamera &cam, const RenderParams &P, const
                                const uint32_t *sample, uint64_t n, RtRay *rays, cudaStream_t stream);
 
 
+// ---- gpu_bvh.cu: a linear BVH built on the device ----
+cudaError_t build_bvh_on_device(DPrim *prims, uint32_t n, const float *boxes_dev, DBvhNode *nodes, uint32_t node_base,
+                                uint32_t first_prim, const double lo[3], const double hi[3], cudaStream_t st);
+
 // ---- image.cu: multi-GPU combine, format_color, P3 text ----
 constexpr uint32_t kMaxGroupDevices = 16;
 struct PeerImages {

@@ -202,3 +202,17 @@ def test_many_individually_transformed_instances_compile_in_linear_time(rt):
     dt = time.perf_counter() - t0
     assert rt.compiled_hash(blob) != 0
     assert dt < 2.0, dt
+
+
+def test_scene_create_ex_argument_checks(rt):
+    b, s, light = _simple(rt)
+    sd = b.finish(b.list([s, light]), b.list([light]))
+    h = C.c_void_p()
+    assert rt._dev.rt_scene_create_ex(sd.ptr, 0, 0x80, C.byref(h)) == rt._abi.RT_ERR_BAD_ARGUMENT
+    assert "create flag" in rt._dev.rt_last_error().decode()
+    st = rt._dev.rt_scene_create_ex(sd.ptr, 0, rt._abi.CREATE_GPU_BVH, C.byref(h))
+    if rt.device_count() == 0:
+        assert st == rt._abi.RT_ERR_CUDA  # the GPU build has no CPU stand-in either
+    else:
+        assert st == 0
+        rt._dev.rt_scene_destroy(h)
