@@ -72,8 +72,8 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
 // walk is not finished when the slice ends keeps its traversal state (node, stack, ray constants) and goes on in
 // the next iteration, while the lanes that are done shade, start their next segment and join the next slice with
 // fresh walks: short walks no longer wait for long ones, and a slice holds old and new walks together.
-// No warp-level synchronisation is involved - every lane runs its own state machine - and the per-path arithmetic
-// is render_kernel's, so the image is bit-identical (test_sliced_traversal_equals_plain_megakernel).
+// The per-path arithmetic is render_kernel's, so the image is bit-identical
+// (test_sliced_traversal_equals_plain_megakernel).
 #ifndef RT_SLICE_STEPS
 #define RT_SLICE_STEPS 32
 #endif
@@ -101,10 +101,15 @@ render_sliced_kernel(const __grid_constant__ DScene sc, const __grid_constant__ 
     r.o = r.d = r.inv = mk(0.0, 0.0, 0.0);
     r.time = 0.0;
     f = FRay{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const unsigned kAll = 0xFFFFFFFFu;
     for (;;) {
+        // The phases below are re-aligned with __syncwarp: left to itself the compiler keeps lanes that took
+        // different branches apart through the whole body (measured: the flat scan at 10 of 32 lanes, the slice at
+        // 3), and a slice only pays if the lanes that walk a tree walk it together.  So every lane stays in the loop
+        // until the whole warp is done.
         bool ended = false;
-        if (!searching) {
-            if (done) break;
+        __syncwarp(kAll);
+        if (!searching && !done) {
             if (!alive) {
                 if (!have_item || s == s_end) {
                     if (have_item) {
@@ -127,64 +132,66 @@ render_sliced_kernel(const __grid_constant__ DScene sc, const __grid_constant__ 
                         have_item = true;
                         break;
                     }
-                    if (!have_item) {
-                        done = true;
-                        continue;  // leaves at the top of the next iteration
-                    }
+                    if (!have_item) done = true;
                 }
-                path_begin(ps, cam, P.width, P.height, i, P.height - 1u - row, s, P.seed, P.max_depth);
-                ++s;
-                ++n_paths;
-                alive = true;
+                if (!done) {
+                    path_begin(ps, cam, P.width, P.height, i, P.height - 1u - row, s, P.seed, P.max_depth);
+                    ++s;
+                    ++n_paths;
+                    alive = true;
+                }
             }
-            // path_step, first half (main.rs:42-48): a new segment's search starts
-            ps.radiance = mk(0.0, 0.0, 0.0);
-            if (ps.depth_left == 0) {
-                alive = false;
-                ended = true;
-            } else {
-                ps.segments += 1;
-                win = Best{RT_INF, kNoPrim, 0, 0};
-                gi = 0;
-                node = kDone;
-                searching = true;
+            if (!done) {  // path_step, first half (main.rs:42-48): a new segment's search starts
+                ps.radiance = mk(0.0, 0.0, 0.0);
+                if (ps.depth_left == 0) {
+                    alive = false;
+                    ended = true;
+                } else {
+                    ps.segments += 1;
+                    win = Best{RT_INF, kNoPrim, 0, 0};
+                    gi = 0;
+                    node = kDone;
+                    searching = true;
+                }
             }
         }
-        if (searching) {
-            if (node == kDone) {  // open groups until one has a tree to walk (trace_groups / trace_one_group)
-                const V3 inv = mk(rcp_fast(ps.ray.d.x), rcp_fast(ps.ray.d.y), rcp_fast(ps.ray.d.z));
-                while (gi < sc.n_world_groups) {
-                    const DGroup &g = sc.groups[gi++];
-                    double e;
-                    if ((g.flags & GROUP_CULL) && !slab(ps.ray.o, inv, g.bmin, g.bmax, kTMin, win.t, e)) continue;
-                    r.o = ps.ray.o;
-                    r.d = ps.ray.d;
-                    r.time = ps.ray.time;
-                    r.inv = inv;
-                    if (g.flags & GROUP_XFORM) {
-                        const double *m = g.m;
-                        const V3 o = ps.ray.o, d = ps.ray.d;
-                        r.o = mk(fma(m[0], o.x, fma(m[1], o.y, fma(m[2], o.z, g.t[0]))), fma(m[3], o.x, fma(m[4], o.y, fma(m[5], o.z, g.t[1]))),
-                                 fma(m[6], o.x, fma(m[7], o.y, fma(m[8], o.z, g.t[2]))));
-                        if (g.flags & GROUP_ROTATED) {
-                            r.d = mk(fma(m[0], d.x, fma(m[1], d.y, m[2] * d.z)), fma(m[3], d.x, fma(m[4], d.y, m[5] * d.z)),
-                                     fma(m[6], d.x, fma(m[7], d.y, m[8] * d.z)));
-                            r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
-                        }
+        __syncwarp(kAll);
+        if (searching && node == kDone) {  // open groups until one has a tree to walk (trace_groups / trace_one_group)
+            const V3 inv = mk(rcp_fast(ps.ray.d.x), rcp_fast(ps.ray.d.y), rcp_fast(ps.ray.d.z));
+            while (gi < sc.n_world_groups) {
+                const DGroup &g = sc.groups[gi++];
+                double e;
+                if ((g.flags & GROUP_CULL) && !slab(ps.ray.o, inv, g.bmin, g.bmax, kTMin, win.t, e)) continue;
+                r.o = ps.ray.o;
+                r.d = ps.ray.d;
+                r.time = ps.ray.time;
+                r.inv = inv;
+                if (g.flags & GROUP_XFORM) {
+                    const double *m = g.m;
+                    const V3 o = ps.ray.o, d = ps.ray.d;
+                    r.o = mk(fma(m[0], o.x, fma(m[1], o.y, fma(m[2], o.z, g.t[0]))), fma(m[3], o.x, fma(m[4], o.y, fma(m[5], o.z, g.t[1]))),
+                             fma(m[6], o.x, fma(m[7], o.y, fma(m[8], o.z, g.t[2]))));
+                    if (g.flags & GROUP_ROTATED) {
+                        r.d = mk(fma(m[0], d.x, fma(m[1], d.y, m[2] * d.z)), fma(m[3], d.x, fma(m[4], d.y, m[5] * d.z)),
+                                 fma(m[6], d.x, fma(m[7], d.y, m[8] * d.z)));
+                        r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
                     }
-                    if (g.bvh_root < 0) {  // the whole group is one leaf
-                        const uint32_t code = ~(uint32_t)g.bvh_root;
-                        const uint32_t first = code >> 3, count = (code & 7u) + 1u;
-                        for (uint32_t k = 0; k < count; ++k) s_prim(sc, first + k, r, kTMin, win);
-                        continue;
-                    }
-                    node = g.bvh_root;
-                    sp = 0;
-                    f = make_fray(r);
-                    t_max_f = __double2float_ru(win.t);
-                    break;
                 }
+                if (g.bvh_root < 0) {  // the whole group is one leaf
+                    const uint32_t code = ~(uint32_t)g.bvh_root;
+                    const uint32_t first = code >> 3, count = (code & 7u) + 1u;
+                    for (uint32_t k = 0; k < count; ++k) s_prim(sc, first + k, r, kTMin, win);
+                    continue;
+                }
+                node = g.bvh_root;
+                sp = 0;
+                f = make_fray(r);
+                t_max_f = __double2float_ru(win.t);
+                break;
             }
+        }
+        __syncwarp(kAll);
+        if (searching) {
             int budget = RT_SLICE_STEPS;  // one slice of the walk (trace_group's while-while, resumable)
             while (node != kDone && budget > 0) {
                 while (node >= 0 && budget > 0) {
@@ -218,24 +225,26 @@ render_sliced_kernel(const __grid_constant__ DScene sc, const __grid_constant__ 
                     --budget;
                 }
             }
-            if (node == kDone && gi >= sc.n_world_groups) {  // the search is complete: the record and main.rs:62-119
-                searching = false;
-                HitRec rec;
-                const bool hit = win.prim != kNoPrim;
-                if (hit) {
-                    V3 o, d;
-                    object_ray(sc, sc.prims[win.prim].chain, ps.ray, o, d);
-                    resolve_hit_obj<false>(sc, ps.ray, win, exact_t_obj(sc, win, o, d, ps.ray.time, kTMin), o, d, rec);
-                }
-                alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
-                ended = !alive;
+        }
+        __syncwarp(kAll);
+        if (searching && node == kDone && gi >= sc.n_world_groups) {  // the search is complete: the record and main.rs:62-119
+            searching = false;
+            HitRec rec;
+            const bool hit = win.prim != kNoPrim;
+            if (hit) {
+                V3 o, d;
+                object_ray(sc, sc.prims[win.prim].chain, ps.ray, o, d);
+                resolve_hit_obj<false>(sc, ps.ray, win, exact_t_obj(sc, win, o, d, ps.ray.time, kTMin), o, d, rec);
             }
+            alive = path_shade(sc, ps, hit, rec, P.integrator, P.flags);
+            ended = !alive;
         }
         if (ended) {
             n_rays += ps.segments;
             if (!(isfinite(ps.radiance.x) && isfinite(ps.radiance.y) && isfinite(ps.radiance.z))) ++n_bad;
             sum = sum + ps.radiance;  // vec.rs:253-260 Sum, in sample order
         }
+        if (__all_sync(kAll, done && !searching)) break;
     }
     atomicAdd(&counters[kCounterPaths], n_paths);
     atomicAdd(&counters[kCounterRays], n_rays);

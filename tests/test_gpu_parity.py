@@ -454,7 +454,7 @@ def test_sliced_traversal_equals_plain_megakernel(rt, orc, name, monkeypatch):
         monkeypatch.setenv("RTB200_RENDER_VARIANT", budget)
         sliced = rt.DeviceScene(hs.scene_desc, device=0)
         b, sb = sliced.render(hs.camera, W, H, spp, depth, opts)
-        if plain.render_info.get("variant") != "vflat":
+        if name != "two_spheres":  # (two spheres are one linear group: no tree, the plain kernel runs)
             assert sliced.render_info.get("traversal") == "sliced"
         assert np.array_equal(a, b, equal_nan=True), budget
         assert (sa.paths, sa.rays, sa.nonfinite_samples) == (sb.paths, sb.rays, sb.nonfinite_samples)

@@ -7,7 +7,7 @@ mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "sliced" > $O/i_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 $O/i_pytest.log
 echo "== render_kernel (defaults)" | tee $O/i_ab.txt
 timeout 120 python tools/wf_probe2.py mesh:16 random:128 2>&1 | tee -a $O/i_ab.txt
-for V in lib slice8 slice16 slice64; do
+for V in lib slice16 slice64 slice128; do
   D=variants_build/$V; [ $V = lib ] && D=raytracinginrust_b200/lib
   for B in 0 1 2 3; do
     echo "== sliced, steps $V (lib = 32), budget $B (0: 80 regs x6, 1: 64 x8, 2: 96 x5, 3: 128 x4)" | tee -a $O/i_ab.txt
