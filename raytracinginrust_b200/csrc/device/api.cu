@@ -382,8 +382,7 @@ RtStatus enqueue_render(RtScene &s, const RtCamera &cam, const RenderParams &P, 
         int blocks = 0;
         CU(pv.render_grid_size(s.device, variant, &blocks));
         s.render_info = std::string("pipeline=megakernel variant=") + pv.name +
-                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1)) +
-                        ((variant & 8) && (pv.mask & F_BVH) ? " traversal=sliced" : "");
+                        " blocks_per_sm=" + std::to_string(blocks / (s.sms > 0 ? s.sms : 1));
         CU(pv.launch_render(s.ds, cam, P, variant, blocks, s.planes, s.counters, st));
         s.pending_launches += 1;
     }
@@ -515,9 +514,6 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
         int budget = (!bvh && !media) ? 0 : ((bvh && !media && !tris) ? 2 : 1);
         if (const char *v = std::getenv("RTB200_RENDER_VARIANT")) budget = std::atoi(v) & 3;
         s->render_variant = budget | (media ? 4 : 0);
-        // sliced tree walk (megakernel.inl: render_sliced_kernel): A/B switch, scenes with a BVH and without media
-        if (const char *v = std::getenv("RTB200_SLICED"))
-            if (std::atoi(v) != 0 && bvh && !media) s->render_variant |= 8;
     }
     CU(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device));
     s->has_media = !cs.media.empty();

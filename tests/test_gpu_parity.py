@@ -437,26 +437,3 @@ def test_gpu_built_bvh_renders_the_same_image(rt, orc, detail):
     host_tree.close()
     gpu_tree.close()
 
-
-@pytest.mark.parametrize("name", ["mesh", "random", "two_spheres"])
-def test_sliced_traversal_equals_plain_megakernel(rt, orc, name, monkeypatch):
-    """render_sliced_kernel (the tree walk in slices of a fixed number of node visits, lanes resume where they were)
-    must give render_kernel's image bit for bit at every register budget: the per-path arithmetic is the same."""
-    hs = host_scene(rt, name)
-    W, H, spp, depth = 96, 54, 6, 50
-    opts = rt.render_opts(seed=5, integrator=hs.integrator, flags=rt._abi.FLAG_MEGAKERNEL)
-    monkeypatch.delenv("RTB200_SLICED", raising=False)
-    plain = rt.DeviceScene(hs.scene_desc, device=0)
-    a, sa = plain.render(hs.camera, W, H, spp, depth, opts)
-    assert "traversal" not in plain.render_info
-    monkeypatch.setenv("RTB200_SLICED", "1")
-    for budget in ("0", "1", "2", "3"):
-        monkeypatch.setenv("RTB200_RENDER_VARIANT", budget)
-        sliced = rt.DeviceScene(hs.scene_desc, device=0)
-        b, sb = sliced.render(hs.camera, W, H, spp, depth, opts)
-        if name != "two_spheres":  # (two spheres are one linear group: no tree, the plain kernel runs)
-            assert sliced.render_info.get("traversal") == "sliced"
-        assert np.array_equal(a, b, equal_nan=True), budget
-        assert (sa.paths, sa.rays, sa.nonfinite_samples) == (sb.paths, sb.rays, sb.nonfinite_samples)
-        sliced.close()
-    plain.close()
