@@ -468,143 +468,6 @@ RT_DEV void trace_one_group(const DScene &sc, const DGroup &g, const Ray &ray, V
     trace_group(sc, g, group_ray(g, ray, inv), t_min, best);
 }
 
-// ---- a tree walked by the warp: idle lanes take pending subtrees of the long walks ------------------------
-// Walk lengths are heavy-tailed: most rays that enter a mesh's bounds leave its tree after a handful of nodes, a few
-// graze the surface for hundreds, and in trace_group the lanes that are done wait for the longest walk of their
-// warp - the node loop runs at 4-5 of 32 lanes (profiles/r2_d_render_kernel_mesh4spp.txt); starting walks together
-// or cutting them into slices does not change that (profiles/r2_c_*, r2_i_*).  What does: after every burst of
-// RT_COOP_BURST visits the idle lanes of the warp each take the BOTTOM entry of a busy lane's stack - the pending
-// subtree nearest the root, the largest piece of work it has - together with that lane's ray (41 shuffles), walk it
-// with the winner so far as their bound, and hand their winner back to the ray's owner at the next burst boundary.
-// The winner of a search does not depend on the order or the lane its candidates are found in (accept keeps the
-// smallest t, and of equal t the highest rank), so the result - and every image - is unchanged.
-#ifndef RT_COOP_WALK
-#define RT_COOP_WALK 1
-#endif
-#ifndef RT_COOP_BURST
-#define RT_COOP_BURST 8
-#endif
-#if defined(__CUDACC__) && RT_COOP_WALK
-RT_DEV void merge_best(Best &into, double t, uint32_t prim, uint32_t rank, int face) {
-    if (prim != kNoPrim && (t < into.t || (t == into.t && rank > into.rank))) into = Best{t, prim, rank, face};
-}
-// Called by every lane of the (converged part of the) warp; enter: this lane's ray passed the group's bounds.
-RT_DEV void trace_group_coop(const DScene &sc, const DGroup &g, SRay r, double t_min, Best &best, bool enter) {
-    const int kDone = (int)0x80000000;
-    const unsigned mask = __activemask();
-    const unsigned lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-    int stack[kStackSize];
-    int sp = 0, sb = 0;  // the stack is [sb, sp): the top is popped by its lane, the bottom given away
-    int node = enter ? g.bvh_root : kDone;
-    FRay f = FRay{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float t_min_f = __double2float_rd(t_min), t_max_f = 0.f;
-    if (enter) {
-        f = make_fray(r);
-        t_max_f = __double2float_ru(best.t);
-    }
-    unsigned owner = lane;      // whose ray this lane is walking
-    bool in_hand = enter;       // a task (own walk or a taken subtree) is in progress
-    bool deliver = false;       // `work` holds a winner for another lane's ray
-    Best work = best;           // winner so far of the task in hand
-    for (;;) {
-        int budget = RT_COOP_BURST;
-        while (node != kDone && budget > 0) {
-            while (node >= 0 && budget > 0) {
-                const float4 *np = reinterpret_cast<const float4 *>(sc.nodes + node);
-                const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-                const int4 ch = __ldg(reinterpret_cast<const int4 *>(np + 3));
-                float e0, e1;
-                const bool h0 = slab2f(f, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, t_min_f, t_max_f, e0);
-                const bool h1 = slab2f(f, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, t_min_f, t_max_f, e1);
-                if (h0 && h1) {
-                    const bool swap = e1 < e0;
-                    const int near_c = swap ? ch.y : ch.x, far_c = swap ? ch.x : ch.y;
-                    if (sp < kStackSize) stack[sp++] = far_c;
-                    node = near_c;
-                } else if (h0) {
-                    node = ch.x;
-                } else if (h1) {
-                    node = ch.y;
-                } else {
-                    node = sp > sb ? stack[--sp] : kDone;
-                }
-                --budget;
-            }
-            if (node < 0 && node != kDone) {
-                const uint32_t code = ~(uint32_t)node;
-                const uint32_t first = code >> 3, count = (code & 7u) + 1u;
-                const double before = work.t;
-                for (uint32_t i = 0; i < count; ++i) s_prim(sc, first + i, r, t_min, work);
-                if (work.t != before) t_max_f = __double2float_ru(work.t);
-                node = sp > sb ? stack[--sp] : kDone;
-                --budget;
-            }
-        }
-        __syncwarp(mask);
-        if (in_hand && node == kDone) {  // the task in hand is complete
-            in_hand = false;
-            sp = sb = 0;
-            if (owner == lane) merge_best(best, work.t, work.prim, work.rank, work.face);
-            else deliver = work.prim != kNoPrim;
-        }
-        const unsigned busy = __ballot_sync(mask, node != kDone);
-        unsigned dl = __ballot_sync(mask, deliver);
-        if (busy == 0u && dl == 0u) break;
-        while (dl) {  // winners go back to the lanes whose rays they belong to
-            const int h = __ffs((int)dl) - 1;
-            dl &= dl - 1u;
-            const unsigned o = __shfl_sync(mask, owner, h);
-            const double t = __shfl_sync(mask, work.t, h);
-            const uint32_t prim = __shfl_sync(mask, work.prim, h), rank = __shfl_sync(mask, work.rank, h);
-            const int face = __shfl_sync(mask, work.face, h);
-            if (lane == o) {
-                merge_best(best, t, prim, rank, face);
-                if (in_hand && owner == lane) {  // still walking that ray itself: the bound tightens
-                    merge_best(work, t, prim, rank, face);
-                    t_max_f = __double2float_ru(work.t);
-                }
-            }
-            if ((int)lane == h) deliver = false;
-        }
-        const unsigned idle = mask & ~busy;
-        const unsigned donors = __ballot_sync(mask, node != kDone && sp > sb);
-        if (idle != 0u && donors != 0u) {  // the k-th idle lane takes from the k-th lane that has something pending
-            const int n_pairs = min(__popc(idle), __popc(donors));
-            const bool taking = ((idle >> lane) & 1u) && __popc(idle & lt) < n_pairs;
-            const bool giving = ((donors >> lane) & 1u) && __popc(donors & lt) < n_pairs;
-            const int from = taking ? (int)__fns(donors, 0u, __popc(idle & lt) + 1) : (int)lane;
-            int give = kDone;
-            if (giving) give = stack[sb++];
-            const int got = __shfl_sync(mask, give, from);
-            FRay tf;
-            tf.ix = __shfl_sync(mask, f.ix, from); tf.iy = __shfl_sync(mask, f.iy, from); tf.iz = __shfl_sync(mask, f.iz, from);
-            tf.clx = __shfl_sync(mask, f.clx, from); tf.cly = __shfl_sync(mask, f.cly, from); tf.clz = __shfl_sync(mask, f.clz, from);
-            tf.chx = __shfl_sync(mask, f.chx, from); tf.chy = __shfl_sync(mask, f.chy, from); tf.chz = __shfl_sync(mask, f.chz, from);
-            SRay tr;
-            tr.o = mk(__shfl_sync(mask, r.o.x, from), __shfl_sync(mask, r.o.y, from), __shfl_sync(mask, r.o.z, from));
-            tr.d = mk(__shfl_sync(mask, r.d.x, from), __shfl_sync(mask, r.d.y, from), __shfl_sync(mask, r.d.z, from));
-            tr.time = feat(F_MSPHERE) ? __shfl_sync(mask, r.time, from) : 0.0;
-            const double t_bound = __shfl_sync(mask, work.t, from), tt_min = __shfl_sync(mask, t_min, from);
-            const uint32_t rank_bound = __shfl_sync(mask, work.rank, from);
-            const float tt_max_f = __shfl_sync(mask, t_max_f, from), tt_min_f = __shfl_sync(mask, t_min_f, from);
-            const unsigned t_owner = __shfl_sync(mask, owner, from);
-            if (taking) {
-                node = got;
-                f = tf;
-                r = tr;
-                r.inv = mk(rcp_fast(r.d.x), rcp_fast(r.d.y), rcp_fast(r.d.z));
-                t_min = tt_min;
-                t_min_f = tt_min_f;
-                t_max_f = tt_max_f;
-                work = Best{t_bound, kNoPrim, rank_bound, 0};  // only what beats the owner's winner so far counts
-                owner = t_owner;
-                in_hand = true;
-            }
-        }
-    }
-}
-#endif
-
 // Closest hit over a sub-scene (a range of groups) for the ray given in the outermost space.
 RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_groups, const Ray &ray, V3 inv, double t_min,
                          Best &best) {
@@ -613,18 +476,8 @@ RT_DEV void trace_groups(const DScene &sc, uint32_t first_group, uint32_t n_grou
         const DGroup &g = sc.groups[first_group + gi];
         double e;
         // a one- or two-primitive group is cheaper to test than to cull
-        const bool enter = !((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, t_min, best.t, e));
-#if defined(__CUDACC__) && RT_COOP_WALK
-        if (feat(F_BVH) && g.bvh_root >= 0) {  // a tree: every lane comes along, the ones without business as helpers
-            SRay r;
-            r.o = r.d = r.inv = mk(0.0, 0.0, 0.0);
-            r.time = 0.0;
-            if (enter) r = group_ray(g, ray, inv);
-            trace_group_coop(sc, g, r, t_min, best, enter);
-            continue;
-        }
-#endif
-        if (enter) trace_one_group(sc, g, ray, inv, t_min, best);
+        if ((g.flags & GROUP_CULL) && !slab(ray.o, inv, g.bmin, g.bmax, t_min, best.t, e)) continue;
+        trace_one_group(sc, g, ray, inv, t_min, best);
     }
 }
 
