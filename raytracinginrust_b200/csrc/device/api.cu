@@ -194,6 +194,8 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.chunk_size = (uint32_t)((count + chunks - 1) / chunks);
     P.n_chunks = (count + P.chunk_size - 1) / P.chunk_size;
     P.n_items = P.items_per_chunk * P.n_chunks;
+    P.inv_items_per_chunk = 1.0 / (double)P.items_per_chunk;
+    P.inv_tiles_x = 1.0 / (double)P.tiles_x;
     return RT_OK;
 }
 

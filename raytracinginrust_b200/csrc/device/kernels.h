@@ -27,6 +27,7 @@ struct RenderParams {
     uint32_t tiles_x, tiles_y;          // 8x4 pixel tiles
     uint64_t items_per_chunk;           // tiles_x * tiles_y * 32 (includes padding of partial tiles)
     uint64_t n_items;                   // n_chunks * items_per_chunk
+    double inv_items_per_chunk, inv_tiles_x;  // reciprocals for the item -> (chunk, tile, pixel) arithmetic (trace.cuh: item_split)
 };
 
 cudaError_t measure_fp64_peak(int device, double *tflops);

@@ -34,9 +34,9 @@ render_kernel(const __grid_constant__ DScene sc, const __grid_constant__ RtCamer
                 for (;;) {
                     unsigned long long item = atomicAdd(&counters[kCounterWork], 1ull);
                     if (item >= P.n_items) break;
-                    uint32_t chunk = (uint32_t)(item / P.items_per_chunk);
-                    uint64_t lin = item - (uint64_t)chunk * P.items_per_chunk;
-                    if (!item_pixel(P.tiles_x, P.width, P.height, lin, i, row)) continue;
+                    uint64_t lin;
+                    const uint32_t chunk = item_split(P, item, lin);
+                    if (!item_pixel(P, lin, i, row)) continue;
                     s = P.sample_begin + chunk * P.chunk_size;
                     s_end = min(s + P.chunk_size, P.sample_end);
                     slot = (uint64_t)chunk * P.width * P.height + (uint64_t)row * P.width + i;

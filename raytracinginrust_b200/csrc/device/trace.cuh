@@ -36,6 +36,9 @@ namespace rtb200dev {
 inline namespace RT_VARIANT_NS {
 
 #define RT_DEV __device__ __forceinline__
+#ifndef RT_MICRO_OPT
+#define RT_MICRO_OPT 1  // r2-k A/B: 0 restores the branchy accept, the mean over one light and the integer divisions
+#endif
 __host__ __device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
 #define RT_DEV_COLD static __device__ __noinline__
 
@@ -239,12 +242,17 @@ struct Best {
 // Every reference test accepts t == t_max, and lists / BVH nodes keep the object visited
 // last (hit.rs:64-66, bvh.rs:81-84; §Q17): an equal t only wins with a higher rank.
 RT_DEV void accept(bool h, double t, uint32_t pi, uint32_t rank, int face, Best &best) {
-    if (h && (t < best.t || rank > best.rank)) {
-        best.t = t;
-        best.prim = pi;
-        best.rank = rank;
-        best.face = face;
-    }
+    // selects, not a branch: a third of a warp's lanes take a candidate at a time, and the branch around four
+    // moves cost more issue slots than the moves
+    const bool take = h && (t < best.t || rank > best.rank);
+#if !RT_MICRO_OPT
+    if (take) best = Best{t, pi, rank, face};
+    return;
+#endif
+    best.t = take ? t : best.t;
+    best.prim = take ? pi : best.prim;
+    best.rank = take ? rank : best.rank;
+    best.face = take ? face : best.face;
 }
 
 RT_DEV V3 msphere_center(const double *pd, double time) {  // sphere.rs:144-146
@@ -878,6 +886,7 @@ RT_DEV double light_pdf_one(const DLight &l, V3 o, V3 v) {
     return 0.0;  // hit.rs:29
 }
 RT_DEV double lights_pdf_value(const DScene &sc, V3 o, V3 v) {  // hit.rs:90-92
+    if (RT_MICRO_OPT && sc.n_lights == 1u) return light_pdf_one(sc.lights[0], o, v);  // 0.0 + x == x and x / 1.0 == x exactly
     double sum = 0.0;
     for (uint32_t i = 0; i < sc.n_lights; ++i) sum += light_pdf_one(sc.lights[i], o, v);
     return sum / (double)sc.n_lights;
@@ -1208,14 +1217,39 @@ RT_DEV void path_begin(PathState &ps, const RtCamera &cam, uint32_t width, uint3
     ps.segments = 0;
 }
 
+// q = n / d and n - q * d for 0 <= n < 2^53, 1 <= d < 2^32, with inv = 1.0 / d: the product is within one of the
+// quotient (its relative error is below 2^-51 and the quotient below 2^33 here), one correction step makes it exact.
+// Replaces a 64-bit integer division (a ~70-instruction subroutine that the item fetch ran at two active lanes).
+RT_DEV uint64_t divmod_by(uint64_t n, uint64_t d, double inv, uint64_t &rem) {
+#if !RT_MICRO_OPT
+    rem = n % d;
+    return n / d;
+#endif
+    uint64_t q = (uint64_t)((double)n * inv);
+    int64_t r = (int64_t)(n - q * d);
+    if (r < 0) {
+        --q;
+        r += (int64_t)d;
+    } else if (r >= (int64_t)d) {
+        ++q;
+        r -= (int64_t)d;
+    }
+    rem = (uint64_t)r;
+    return q;
+}
+// A work item is (sample chunk, pixel): item = chunk * items_per_chunk + lin.
+RT_DEV uint32_t item_split(const RenderParams &P, uint64_t item, uint64_t &lin) {
+    return (uint32_t)divmod_by(item, P.items_per_chunk, P.inv_items_per_chunk, lin);
+}
 // pixel order inside the item space: 8x4 tiles so that the 32 lanes of a warp start
 // on neighbouring pixels (coherent primary rays and BVH paths)
-__device__ __forceinline__ bool item_pixel(uint32_t tiles_x, uint32_t width, uint32_t height, uint64_t lin, uint32_t &i, uint32_t &row) {
-    uint32_t tile = (uint32_t)(lin >> 5), within = (uint32_t)(lin & 31u);
-    uint32_t tx = tile % tiles_x, ty = tile / tiles_x;
-    i = tx * 8u + (within & 7u);
+RT_DEV bool item_pixel(const RenderParams &P, uint64_t lin, uint32_t &i, uint32_t &row) {
+    const uint32_t within = (uint32_t)(lin & 31u);
+    uint64_t tx;
+    const uint32_t ty = (uint32_t)divmod_by(lin >> 5, P.tiles_x, P.inv_tiles_x, tx);
+    i = (uint32_t)tx * 8u + (within & 7u);
     row = ty * 4u + (within >> 3);
-    return i < width && row < height;
+    return i < P.width && row < P.height;
 }
 
 // What a ray found, as the class the sorting stages group by (wavefront.inl: shade tiles; sorted.inl: the lanes of a

@@ -336,10 +336,10 @@ wf_generate_kernel(const __grid_constant__ RtCamera cam, const __grid_constant__
             if (item >= P.n_items) {
                 need_item = false;  // no work left: the slot retires
             } else {
-                const uint32_t c = (uint32_t)(item / P.items_per_chunk);
-                const uint64_t lin = item - (uint64_t)c * P.items_per_chunk;
+                uint64_t lin;
+                const uint32_t c = item_split(P, item, lin);
                 uint32_t i, row;
-                if (item_pixel(P.tiles_x, P.width, P.height, lin, i, row)) {
+                if (item_pixel(P, lin, i, row)) {
                     chunk = c;
                     sample = P.sample_begin + c * P.chunk_size;
                     s_end = min(sample + P.chunk_size, P.sample_end);
