@@ -392,11 +392,6 @@ const char *rt_render_info(const RtScene *scene);
  * the bound that actually applies to this path (DESIGN.md "Rooflines"). */
 RtStatus rt_measure_fp64_peak(int device, double *tflops_out);
 
-/* Diagnostic: the device code divides a Vec3 by an f64 (src/vec.rs:222-230, three IEEE divisions) with ONE refined
- * reciprocal, replicating the compiler's own f64 division instruction for instruction.  This runs n_triples random and
- * structured (a0, a1, a2) / b on the GPU and counts the quotients whose bits differ from `a / b`: must be 0. */
-RtStatus rt_selftest_division(int device, uint64_t n_triples, uint32_t seed, uint64_t *mismatches_out);
-
 /* Thread-local description of the last error returned on this thread. */
 const char *rt_last_error(void);
 

@@ -51,7 +51,6 @@ _dev.rt_path_radiance.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C
 _dev.rt_camera_rays.argtypes = [C.c_void_p, C.POINTER(RtCamera), C.c_uint32, C.c_uint32, C.POINTER(RtRenderOpts),
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
 _dev.rt_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
-_dev.rt_selftest_division.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64)]
 _dev.rt_last_error.restype = C.c_char_p
 _dev.rt_version.restype = C.c_char_p
 _dev.rt_scene_group_create.argtypes = [C.POINTER(RtSceneDesc), C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]
@@ -98,13 +97,6 @@ def measure_fp64_peak(device=0):
     v = C.c_double()
     _check(_dev.rt_measure_fp64_peak(device, C.byref(v)))
     return float(v.value)
-
-
-def selftest_division(n_triples, seed=1, device=0):
-    """Quotients of Vec3 / f64 (shared reciprocal) whose bits differ from the compiler's division: must be 0."""
-    bad = C.c_uint64()
-    _check(_dev.rt_selftest_division(device, n_triples, seed, C.byref(bad)))
-    return int(bad.value)
 
 
 def version():

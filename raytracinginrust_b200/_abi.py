@@ -103,4 +103,4 @@ EXPORTS = ["rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_d
            "rt_scene_group_create", "rt_scene_group_destroy", "rt_scene_group_size", "rt_scene_group_scene",
            "rt_render_multi", "rt_encode_rgb8", "rt_encode_ppm",
            "rt_compile", "rt_compiled_data", "rt_compiled_size", "rt_compiled_hash", "rt_compiled_destroy",
-           "rt_scene_create_compiled", "rt_scene_create_ex", "rt_selftest_division"]
+           "rt_scene_create_compiled", "rt_scene_create_ex"]

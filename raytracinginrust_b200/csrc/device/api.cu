@@ -544,16 +544,6 @@ int rt_device_count(void) {
     return n;
 }
 
-RtStatus rt_selftest_division(int device, uint64_t n_triples, uint32_t seed, uint64_t *mismatches_out) {
-    if (!mismatches_out) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
-    if (rt_device_count() == 0) return fail(RT_ERR_CUDA, "no CUDA device (this library has no CPU path)");
-    CU(cudaSetDevice(device));
-    unsigned long long bad = 0;
-    CU(selftest_division(device, n_triples, seed, &bad));
-    *mismatches_out = bad;
-    return RT_OK;
-}
-
 RtStatus rt_measure_fp64_peak(int device, double *tflops_out) {
     if (!tflops_out) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     int n = rt_device_count();

@@ -121,67 +121,6 @@ cudaError_t measure_fp64_peak(int device, double *tflops) {
 }
 
 // ---------------------------------------------------------------------------
-// self-test: Vec3 / f64 with the shared reciprocal (trace.cuh) against the compiler's own division
-// ---------------------------------------------------------------------------
-// Operand classes, chosen by the pair's index: random bit patterns (every exponent, NaN, inf, denormals), operands
-// of the magnitudes a render sees (exponents within +-40 of 1), exact zeros of both signs, significands of all ones or
-// one bit, and quotients at the edges of the normal range.  A mismatch is a quotient whose 64 bits differ from
-// `a / b` (two NaNs count as equal: their payloads are not defined by IEEE 754).
-__global__ void division_selftest_kernel(unsigned long long n, uint32_t seed, unsigned long long *mismatches) {
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long bad = 0;
-    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        uint32_t c0 = (uint32_t)k, c1 = (uint32_t)(k >> 32), c2 = 0x5eedu, c3 = seed;
-        philox4x32_10(c0, c1, c2, c3, 0x243F6A88u, 0x85A308D3u);
-        uint32_t d0 = c0 ^ 0x9E3779B9u, d1 = c1, d2 = c2, d3 = c3 + 1u;
-        philox4x32_10(d0, d1, d2, d3, 0x13198A2Eu, 0x03707344u);
-        unsigned long long w[4] = {((unsigned long long)c0 << 32) | c1, ((unsigned long long)c2 << 32) | c3,
-                                   ((unsigned long long)d0 << 32) | d1, ((unsigned long long)d2 << 32) | d3};
-        const uint32_t cls = (uint32_t)(k % 7ull);
-        double v[4];
-        for (int j = 0; j < 4; ++j) {
-            unsigned long long bits = w[j];
-            if (cls == 1 || cls == 2) {  // exponent within +-40 of 1.0
-                const unsigned long long ex = 1023ull - 40ull + (bits >> 52) % 81ull;
-                bits = (bits & 0x800FFFFFFFFFFFFFull) | (ex << 52);
-            } else if (cls == 3 && j < 3) {
-                bits = (bits & 0x8000000000000000ull);  // +-0 numerators
-            } else if (cls == 4) {
-                bits = (bits & 0xFFF0000000000000ull) | ((bits & 1ull) ? 0x000FFFFFFFFFFFFFull : 1ull << (bits % 52ull));
-                const unsigned long long ex = 1023ull - 30ull + ((bits >> 52) & 0x7FFull) % 61ull;
-                bits = (bits & 0x800FFFFFFFFFFFFFull) | (ex << 52);
-            } else if (cls == 5) {  // quotients near the ends of the normal range
-                const unsigned long long ex = j < 3 ? ((bits >> 52) & 1ull ? 40ull : 2000ull) : ((bits >> 52) & 2ull ? 1060ull : 980ull);
-                bits = (bits & 0x800FFFFFFFFFFFFFull) | (ex << 52);
-            }
-            v[j] = __longlong_as_double((long long)bits);
-        }
-        const V3 q = mk(v[0], v[1], v[2]) / v[3];
-        const double got[3] = {q.x, q.y, q.z};
-        for (int j = 0; j < 3; ++j) {
-            const double want = __ddiv_rn(v[j], v[3]);
-            const bool same = (want != want && got[j] != got[j]) || __double_as_longlong(want) == __double_as_longlong(got[j]);
-            if (!same) ++bad;
-        }
-    }
-    if (bad) atomicAdd(mismatches, bad);
-}
-cudaError_t selftest_division(int device, unsigned long long n, uint32_t seed, unsigned long long *mismatches_host) {
-    (void)device;
-    unsigned long long *dev = nullptr;
-    cudaError_t e = cudaMalloc((void **)&dev, sizeof(unsigned long long));
-    if (e != cudaSuccess) return e;
-    e = cudaMemset(dev, 0, sizeof(unsigned long long));
-    if (e == cudaSuccess) {
-        division_selftest_kernel<<<148 * 8, 256>>>(n, seed, dev);
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(mismatches_host, dev, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    cudaFree(dev);
-    return e;
-}
-
-// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,

@@ -31,7 +31,6 @@ struct RenderParams {
 };
 
 cudaError_t measure_fp64_peak(int device, double *tflops);
-cudaError_t selftest_division(int device, unsigned long long n, uint32_t seed, unsigned long long *mismatches_host);
 cudaError_t launch_reduce_planes(const double *planes, float *out, uint64_t n_values, uint32_t n_chunks,
                                  cudaStream_t stream);
 cudaError_t launch_first_hit(const DScene &sc, const RtRay *rays, uint64_t n, RtHit *hits, cudaStream_t stream);

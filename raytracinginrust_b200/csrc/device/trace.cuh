@@ -37,9 +37,10 @@ inline namespace RT_VARIANT_NS {
 
 #define RT_DEV __device__ __forceinline__
 #ifndef RT_MICRO_OPT
-#define RT_MICRO_OPT 3  // A/B levels: 0 none; 1 branch-free accept, no mean over one light, item arithmetic by reciprocal;
-                        // 2 also Vec3 / f64 with one reciprocal and one cosine / PI where the ONB's w is the normal; 3 also no square root
-                        // for vectors whose squared length is exactly 1
+#define RT_MICRO_OPT 2  // A/B levels: 0 none; 1 branch-free accept, no mean over one light, item arithmetic by reciprocal
+                        // (r2-k: Cornell +6.6 %); 2 also one cosine / PI where the ONB's w is the normal and no square root for
+                        // vectors whose squared length is exactly 1.  (Vec3 / f64 with one shared reciprocal - the compiler's
+                        // division sequence restated, bit-exact on 4 x 10^8 quotients - was measured in r2-l: +0.3 %, removed.)
 #endif
 __host__ __device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
 #define RT_DEV_COLD static __device__ __noinline__
@@ -71,41 +72,7 @@ RT_DEV double ddiv(double a, double b) {
     }
     return a / b;
 }
-#if defined(__CUDACC__) && RT_MICRO_OPT >= 2
-// Vec3 / f64 (vec.rs:222-230: three IEEE divisions by the same divisor) with the reciprocal refined ONCE.
-// This is nvcc's own f64 division, instruction for instruction (cuobjdump of `a / b` for sm_100a, CUDA 12.9):
-//   MUFU.RCP64H seed with the low word set to 1; e = fma(-b, r0, 1); e = fma(e, e, e); r1 = fma(r0, e, r0);
-//   e1 = fma(-b, r1, 1); r = fma(r1, e1, r1);                          <- depends on b alone: shared
-//   q0 = a * r; rem = fma(-b, q0, a); q = fma(r, rem, q0);              <- per numerator
-//   fast path taken iff |hi word of a, read as fp32| >= 0x03600000 (|a| >= 2^-969) and 0 * (hi word of b as fp32) +
-//   (hi word of q as fp32) is a normal fp32 in magnitude (q normal and finite, b below 2^1017)
-// so every quotient is the bit pattern `a / b` gives (rt_selftest_division checks that on the GPU over random and
-// structured operands); operands outside the fast path - zero numerators among them - take the plain division.
-RT_DEV double div_rcp(double b) {
-    double seed;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(b));
-    const double r0 = __hiloint2double(__double2hiint(seed), 1);
-    double e = fma(-b, r0, 1.0);
-    e = fma(e, e, e);
-    const double r1 = fma(r0, e, r0);
-    const double e1 = fma(-b, r1, 1.0);
-    return fma(r1, e1, r1);
-}
-RT_DEV double div_by(double a, double b, double r) {
-    const double q0 = a * r;
-    const double rem = fma(-b, q0, a);
-    const double q = fma(r, rem, q0);
-    const float ah = __int_as_float(__double2hiint(a)), bh = __int_as_float(__double2hiint(b)), qh = __int_as_float(__double2hiint(q));
-    if (fabsf(ah) >= 6.5827683646048100446e-37f && fabsf(fmaf(0.0f, bh, qh)) > 1.469367938527859385e-39f) return q;
-    return ddiv(a, b);
-}
-RT_DEV V3 operator/(V3 a, double s) {
-    const double r = div_rcp(s);
-    return mk(div_by(a.x, s, r), div_by(a.y, s, r), div_by(a.z, s, r));
-}
-#else
 RT_DEV V3 operator/(V3 a, double s) { return mk(ddiv(a.x, s), ddiv(a.y, s), ddiv(a.z, s)); }
-#endif
 RT_DEV double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }  // vec.rs:38-40
 RT_DEV double length(V3 a) { return sqrt(dot(a, a)); }                        // vec.rs:42-44
 RT_DEV V3 cross(V3 a, V3 b) {                                                 // vec.rs:46-54
@@ -114,7 +81,7 @@ RT_DEV V3 cross(V3 a, V3 b) {                                                 //
 RT_DEV V3 normalized(V3 a) {  // vec.rs:56-58: self / self.length(); x/1.0 == x exactly
     const double l2 = dot(a, a);
     // sqrt(1.0) == 1.0: axis-aligned unit normals (every wall of a Cornell box) skip the square root as well
-    if (RT_MICRO_OPT >= 3 && l2 == 1.0) return a;
+    if (RT_MICRO_OPT >= 2 && l2 == 1.0) return a;
     double l = sqrt(l2);
     if (l == 1.0) return a;
     return a / l;

@@ -438,10 +438,3 @@ def test_gpu_built_bvh_renders_the_same_image(rt, orc, detail):
     gpu_tree.close()
 
 
-
-def test_vec3_division_with_one_reciprocal_is_the_compilers_division(rt):
-    """trace.cuh divides a Vec3 by an f64 with one refined reciprocal for the three quotients (nvcc's own division
-    sequence with its first half shared).  Every quotient must be the bit pattern of `a / b`: 3 x 2^27 quotients over
-    random bit patterns, render-sized operands, zeros, extreme significands and the ends of the normal range."""
-    assert rt.selftest_division(1 << 27, seed=1) == 0
-    assert rt.selftest_division(1 << 25, seed=77) == 0
