@@ -37,10 +37,11 @@ inline namespace RT_VARIANT_NS {
 
 #define RT_DEV __device__ __forceinline__
 #ifndef RT_MICRO_OPT
-#define RT_MICRO_OPT 2  // A/B levels: 0 none; 1 branch-free accept, no mean over one light, item arithmetic by reciprocal
-                        // (r2-k: Cornell +6.6 %); 2 also one cosine / PI where the ONB's w is the normal and no square root for
-                        // vectors whose squared length is exactly 1.  (Vec3 / f64 with one shared reciprocal - the compiler's
-                        // division sequence restated, bit-exact on 4 x 10^8 quotients - was measured in r2-l: +0.3 %, removed.)
+// A/B switch of three instruction trims that cannot change a value (r2-k: Cornell +6.6 %, smoke +7.3 %): accept()
+// as selects, no mean over a single light, the item arithmetic by reciprocal multiplication.  0 restores the old
+// forms.  (Measured next and NOT kept, profiles/r2_m_instruction_trims.md: Vec3 / f64 with one shared reciprocal,
+// one cosine / PI where the ONB's w is the normal, no square root for vectors of squared length exactly 1.)
+#define RT_MICRO_OPT 1
 #endif
 __host__ __device__ __forceinline__ constexpr bool feat(uint32_t f) { return ((uint32_t)(RT_FEAT_MASK) & f) != 0u; }
 #define RT_DEV_COLD static __device__ __noinline__
@@ -79,10 +80,7 @@ RT_DEV V3 cross(V3 a, V3 b) {                                                 //
     return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 RT_DEV V3 normalized(V3 a) {  // vec.rs:56-58: self / self.length(); x/1.0 == x exactly
-    const double l2 = dot(a, a);
-    // sqrt(1.0) == 1.0: axis-aligned unit normals (every wall of a Cornell box) skip the square root as well
-    if (RT_MICRO_OPT >= 2 && l2 == 1.0) return a;
-    double l = sqrt(l2);
+    double l = length(a);
     if (l == 1.0) return a;
     return a / l;
 }
@@ -1181,11 +1179,7 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
         double cosine = dot(unit, uvw.w);  // pdf.rs:131-139
         double cosine_pdf = cosine > 0.0 ? cosine / kPi : 0.0;
         double pdf_value = 0.5 * light_pdf + 0.5 * cosine_pdf;  // pdf.rs:143-145
-        // mat.rs:246-249: max(normal . unit, 0) / PI.  uvw.w is normalized(rec.normal), which IS rec.normal when its
-        // length is exactly 1 (every axis-aligned surface): the two dot products are then the same number, and so
-        // are the two quotients (a cosine <= 0 or NaN gives 0 on both lines) - one division instead of two.
-        const bool w_is_normal = RT_MICRO_OPT >= 2 && uvw.w.x == rec.normal.x && uvw.w.y == rec.normal.y && uvw.w.z == rec.normal.z;
-        double spdf = w_is_normal ? cosine_pdf : fmax(dot(rec.normal, unit), 0.0) / kPi;
+        double spdf = fmax(dot(rec.normal, unit), 0.0) / kPi;    // mat.rs:246-249
         factor = (attenuation * spdf) / pdf_value;               // main.rs:97
     }
     ps.beta = ps.beta * factor;
