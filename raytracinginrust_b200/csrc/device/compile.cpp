@@ -1240,6 +1240,14 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         dm.node = (int32_t)pm.node;
         dm.rank = pm.rank;
         dm.density = n.v[0];
+        dm.convex_prim = 0xFFFFFFFFu;
+        dm.pad0 = dm.pad1 = dm.pad2 = 0;
+        if (dm.n_groups == 1 && !std::getenv("RTB200_NO_CONVEX_MEDIA")) {  // (the switch is for the A/B of r2-n)
+            const DGroup &bg = out.groups[dm.first_group];
+            if (bg.n_prims == 1 && bg.bvh_root < 0 && !(bg.flags & GROUP_CULL) &&
+                (out.prims[bg.first_prim].kind == PRIM_BOX || out.prims[bg.first_prim].kind == PRIM_SPHERE))
+                dm.convex_prim = bg.first_prim;
+        }
         out.media.push_back(dm);
     }
     w.stack.clear();

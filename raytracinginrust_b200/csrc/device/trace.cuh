@@ -264,18 +264,34 @@ RT_DEV V3 msphere_center(const double *pd, double time) {  // sphere.rs:144-146
     return c0 + ddiv(time - pd[6], pd[7] - pd[6]) * (c1 - c0);
 }
 
-RT_DEV void s_sphere(const SRay &r, V3 center, double radius, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+// Both roots of a sphere (search-grade), then the choice Sphere::hit makes for an interval (sphere.rs:56-73): the two
+// halves are separate so that a medium's two boundary queries can share the first (world_search).
+struct SphereRoots {
+    double t_near, t_far;
+    bool valid;
+};
+RT_DEV SphereRoots sphere_roots(const SRay &r, V3 center, double radius) {
     V3 oc = r.o - center;
     double a = dot(r.d, r.d);
     double half_b = dot(oc, r.d);
     double c = dot(oc, oc) - radius * radius;
     double disc = half_b * half_b - a * c;
-    if (!(disc >= 0.0)) return;
+    SphereRoots s;
+    s.valid = disc >= 0.0;
     double sq = sqrt(disc);
     double ia = rcp_fast(a);
-    double t = (-half_b - sq) * ia;
-    if (!(t >= t_min && t <= best.t)) t = (-half_b + sq) * ia;
+    s.t_near = (-half_b - sq) * ia;
+    s.t_far = (-half_b + sq) * ia;
+    return s;
+}
+RT_DEV void s_sphere_from(const SphereRoots &s, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    if (!s.valid) return;
+    double t = s.t_near;
+    if (!(t >= t_min && t <= best.t)) t = s.t_far;
     accept(t >= t_min && t <= best.t, t, pi, rank, 0, best);
+}
+RT_DEV void s_sphere(const SRay &r, V3 center, double radius, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    s_sphere_from(sphere_roots(r, center, radius), t_min, pi, rank, best);
 }
 RT_DEV void s_rect(const SRay &r, uint32_t plane, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
     double a0 = pd[0], a1 = pd[1], b0 = pd[2], b1 = pd[3], k = pd[4];
@@ -297,7 +313,12 @@ RT_DEV void s_rect(const SRay &r, uint32_t plane, const double *pd, double t_min
 }
 // Cube = six AARects in a list (cube.rs:17-25,35-37).  For a convex box the closest accepted
 // side is the entry point if it lies in the interval, else the exit point: a slab test.
-RT_DEV void s_box(const SRay &r, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+struct BoxSlab {
+    double t_in, t_out;
+    int f_in, f_out;
+    bool valid;
+};
+RT_DEV BoxSlab box_slab(const SRay &r, const double *pd) {
     double x0 = (pd[0] - r.o.x) * r.inv.x, x1 = (pd[3] - r.o.x) * r.inv.x;
     double y0 = (pd[1] - r.o.y) * r.inv.y, y1 = (pd[4] - r.o.y) * r.inv.y;
     double z0 = (pd[2] - r.o.z) * r.inv.z, z1 = (pd[5] - r.o.z) * r.inv.z;
@@ -306,19 +327,27 @@ RT_DEV void s_box(const SRay &r, const double *pd, double t_min, uint32_t pi, ui
     double nx = sx ? x0 : x1, fx = sx ? x1 : x0;
     double ny = sy ? y0 : y1, fy = sy ? y1 : y0;
     double nz = sz ? z0 : z1, fz = sz ? z1 : z0;
-    double t_in = nx;
-    int f_in = sx ? 5 : 4;
-    if (ny > t_in) { t_in = ny; f_in = sy ? 3 : 2; }
-    if (nz > t_in) { t_in = nz; f_in = sz ? 1 : 0; }
-    double t_out = fx;
-    int f_out = sx ? 4 : 5;
-    if (fy < t_out) { t_out = fy; f_out = sy ? 2 : 3; }
-    if (fz < t_out) { t_out = fz; f_out = sz ? 0 : 1; }
-    if (!(t_in <= t_out)) return;  // misses the box (NaN: a ray parallel to a slab on its plane -> no hit)
-    bool in_ok = t_in >= t_min && t_in <= best.t;
-    double t = in_ok ? t_in : t_out;
-    int f = in_ok ? f_in : f_out;
+    BoxSlab s;
+    s.t_in = nx;
+    s.f_in = sx ? 5 : 4;
+    if (ny > s.t_in) { s.t_in = ny; s.f_in = sy ? 3 : 2; }
+    if (nz > s.t_in) { s.t_in = nz; s.f_in = sz ? 1 : 0; }
+    s.t_out = fx;
+    s.f_out = sx ? 4 : 5;
+    if (fy < s.t_out) { s.t_out = fy; s.f_out = sy ? 2 : 3; }
+    if (fz < s.t_out) { s.t_out = fz; s.f_out = sz ? 0 : 1; }
+    s.valid = s.t_in <= s.t_out;  // false: misses the box (NaN: a ray parallel to a slab on its plane -> no hit)
+    return s;
+}
+RT_DEV void s_box_from(const BoxSlab &s, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    if (!s.valid) return;
+    bool in_ok = s.t_in >= t_min && s.t_in <= best.t;
+    double t = in_ok ? s.t_in : s.t_out;
+    int f = in_ok ? s.f_in : s.f_out;
     accept(t >= t_min && t <= best.t, t, pi, rank, f, best);
+}
+RT_DEV void s_box(const SRay &r, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
+    s_box_from(box_slab(r, pd), t_min, pi, rank, best);
 }
 RT_DEV void s_tri(const SRay &r, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
     V3 s = r.o - ld3(pd);
@@ -702,6 +731,8 @@ RT_DEV bool world_search(const DScene &sc, const Ray &r, const Rng &rng, Best &w
         double t_min = kTMin;
         Best b{RT_INF, kNoPrim, 0, 0};
         bool second = false;
+        double te = 0.0;
+        bool found = false, searched = false;
         if (q > 0) {
             mi = (q - 1u) >> 1;
             second = ((q - 1u) & 1u) != 0u;
@@ -711,12 +742,49 @@ RT_DEV bool world_search(const DScene &sc, const Ray &r, const Rng &rng, Best &w
             ng = m.n_groups;
             t_min = second ? t1 + 0.0001 : -DBL_MAX;  // boundary.hit(r, -MAX, MAX) ; boundary.hit(r, hit1.t + 0.0001, MAX)
             b.t = DBL_MAX;
+            if (!second && m.convex_prim != kNoPrim) {
+                // The boundary is one box or sphere (tables.h: DMedium::convex_prim): both queries come from ONE slab /
+                // root computation on ONE transformed ray, with the selection of s_box / s_sphere applied once per
+                // interval - the same comparisons on the same numbers as two searches of the boundary sub-scene,
+                // without the second ray transform, primitive test and object-space ray.  This iteration answers the
+                // first query and, if it hits, the second one too; the next iteration (q + 1) is skipped.
+                const uint32_t pi = m.convex_prim;
+                const DPrim &p = sc.prims[pi];
+                const SRay gr = group_ray(sc.groups[fg], r, inv);
+                V3 go, gd;
+                object_ray(sc, p.chain, r, go, gd);
+                Best b2{DBL_MAX, kNoPrim, 0, 0};
+                if (p.kind == PRIM_BOX) {
+                    const BoxSlab slab = box_slab(gr, p.d);
+                    s_box_from(slab, t_min, pi, p.rank, b);
+                    if (b.prim != kNoPrim) {
+                        t1 = exact_t_obj(sc, b, go, gd, r.time, t_min);
+                        s_box_from(slab, t1 + 0.0001, pi, p.rank, b2);
+                    }
+                } else {
+                    const SphereRoots roots = sphere_roots(gr, ld3(p.d), p.d[3]);
+                    s_sphere_from(roots, t_min, pi, p.rank, b);
+                    if (b.prim != kNoPrim) {
+                        t1 = exact_t_obj(sc, b, go, gd, r.time, t_min);
+                        s_sphere_from(roots, t1 + 0.0001, pi, p.rank, b2);
+                    }
+                }
+                have_t1 = false;  // the second query's iteration has nothing left to do
+                ++q;
+                if (b.prim == kNoPrim || b2.prim == kNoPrim) continue;
+                te = exact_t_obj(sc, b2, go, gd, r.time, t1 + 0.0001);
+                second = true;
+                found = true;
+                searched = true;
+            }
         }
-        trace_groups(sc, fg, ng, r, inv, t_min, b);
-        bool found = b.prim != kNoPrim;
-        if (q > 0 && !second) have_t1 = found;
-        if (!found) continue;
-        double te = exact_t(sc, r, b, t_min);
+        if (!searched) {
+            trace_groups(sc, fg, ng, r, inv, t_min, b);
+            found = b.prim != kNoPrim;
+            if (q > 0 && !second) have_t1 = found;
+            if (!found) continue;
+            te = exact_t(sc, r, b, t_min);
+        }
         if (q == 0) {
             win = b;
             closest = te;
