@@ -1244,7 +1244,9 @@ RtStatus compile_scene(const RtSceneDesc &d, CompiledScene &out, std::string &er
         dm.pad0 = dm.pad1 = dm.pad2 = 0;
         if (dm.n_groups == 1 && !std::getenv("RTB200_NO_CONVEX_MEDIA")) {  // (the switch is for the A/B of r2-n)
             const DGroup &bg = out.groups[dm.first_group];
-            if (bg.n_prims == 1 && bg.bvh_root < 0 && !(bg.flags & GROUP_CULL) &&
+            // only under a transform: that is what the second query would repeat (measured, r2-n: Cornell smoke's
+            // rotated boxes +11 %, the untransformed spheres of the Next Week final scene -2 %)
+            if (bg.n_prims == 1 && bg.bvh_root < 0 && !(bg.flags & GROUP_CULL) && (bg.flags & GROUP_XFORM) &&
                 (out.prims[bg.first_prim].kind == PRIM_BOX || out.prims[bg.first_prim].kind == PRIM_SPHERE))
                 dm.convex_prim = bg.first_prim;
         }

@@ -87,8 +87,8 @@ struct alignas(16) DMedium {
     int32_t node;                    // RtSceneDesc node index; also the RNG sub-slot
     uint32_t rank;
     double density;
-    // The boundary is ONE box or sphere primitive in one group (every medium of main.rs: a Cube or a Sphere): its
-    // index, else 0xFFFFFFFF.  world_search then answers both boundary queries of medium.rs:29-30 from one slab /
+    // The boundary is ONE box or sphere primitive in one group under a Translate / Rotate (the smoke boxes of
+    // cornell_box_with_smoke): its index, else 0xFFFFFFFF.  world_search then answers both boundary queries of medium.rs:29-30 from one slab /
     // root computation on one transformed ray instead of searching the boundary sub-scene twice.
     uint32_t convex_prim;
     uint32_t pad0, pad1, pad2;
