@@ -290,8 +290,20 @@ RT_DEV void s_sphere_from(const SphereRoots &s, double t_min, uint32_t pi, uint3
     if (!(t >= t_min && t <= best.t)) t = s.t_far;
     accept(t >= t_min && t <= best.t, t, pi, rank, 0, best);
 }
+// (the leaf test proper leaves before the square root when the ray misses, and makes the far root only if the
+// near one is outside the interval: RTiOW's leaves are sphere tests, most of them misses)
 RT_DEV void s_sphere(const SRay &r, V3 center, double radius, double t_min, uint32_t pi, uint32_t rank, Best &best) {
-    s_sphere_from(sphere_roots(r, center, radius), t_min, pi, rank, best);
+    V3 oc = r.o - center;
+    double a = dot(r.d, r.d);
+    double half_b = dot(oc, r.d);
+    double c = dot(oc, oc) - radius * radius;
+    double disc = half_b * half_b - a * c;
+    if (!(disc >= 0.0)) return;
+    double sq = sqrt(disc);
+    double ia = rcp_fast(a);
+    double t = (-half_b - sq) * ia;
+    if (!(t >= t_min && t <= best.t)) t = (-half_b + sq) * ia;
+    accept(t >= t_min && t <= best.t, t, pi, rank, 0, best);
 }
 RT_DEV void s_rect(const SRay &r, uint32_t plane, const double *pd, double t_min, uint32_t pi, uint32_t rank, Best &best) {
     double a0 = pd[0], a1 = pd[1], b0 = pd[2], b1 = pd[3], k = pd[4];
