@@ -378,18 +378,9 @@ RT_DEV void s_prim(const DScene &sc, uint32_t pi, const SRay &r, double t_min, B
     uint32_t kind = p.kind, rank = p.rank;
     if (feat(F_RECT) && kind == PRIM_RECT) s_rect(r, p.axis, p.d, t_min, pi, rank, best);
     else if (feat(F_BOX) && kind == PRIM_BOX) s_box(r, p.d, t_min, pi, rank, best);
+    else if (feat(F_SPHERE) && kind == PRIM_SPHERE) s_sphere(r, ld3(p.d), p.d[3], t_min, pi, rank, best);
     else if (feat(F_TRI) && kind == PRIM_TRI) s_tri(r, p.d, t_min, pi, rank, best);
-    else if (feat(F_SPHERE | F_MSPHERE)) {
-        // ONE sphere test for both kinds: the lanes of a warp hold spheres and moving spheres side by side in RTiOW's
-        // leaves (80 % of its small spheres move), and two inlined copies of the test ran one after the other
-        V3 center = ld3(p.d);
-        double radius = p.d[3];
-        if (feat(F_MSPHERE) && (!feat(F_SPHERE) || kind == PRIM_MSPHERE)) {
-            center = msphere_center(p.d, r.time);
-            radius = p.d[8];
-        }
-        s_sphere(r, center, radius, t_min, pi, rank, best);
-    }
+    else if (feat(F_MSPHERE)) s_sphere(r, msphere_center(p.d, r.time), p.d[8], t_min, pi, rank, best);
 }
 
 // Conservative slab test against [t_min, t_max] (culling only; NaN operands are ignored by fmin/fmax).
@@ -1018,9 +1009,9 @@ RT_DEV double reflectance(double cosine, double index_of_refraction) {  // mat.r
     double r0 = powi2((1.0 - index_of_refraction) / (1.0 + index_of_refraction));
     return r0 + (1.0 - r0) * powi5(1.0 - cosine);
 }
-// unit_direction: r_in.direction().normalized() (mat.rs:345), made by the caller
-RT_DEV V3 dielectric_direction(const DMaterial &m, V3 unit_direction, const HitRec &rec, const Rng &rng) {  // mat.rs:343-366
+RT_DEV V3 dielectric_direction(const DMaterial &m, V3 r_in_dir, const HitRec &rec, const Rng &rng) {  // mat.rs:343-366
     double refraction_ratio = rec.front_face ? 1.0 / m.ir : m.ir;
+    V3 unit_direction = normalized(r_in_dir);
     double cos_theta = fmin(dot((-1.0) * unit_direction, rec.normal), 1.0);
     double sin_theta = sqrt(1.0 - powi2(cos_theta));
     bool cannot_refract = refraction_ratio * sin_theta > 1.0;
@@ -1220,51 +1211,22 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
     }
     V3 new_dir = mk(0.0, 0.0, 0.0);
     V3 factor = mk(0.0, 0.0, 0.0);
-    // random_in_unit_sphere (vec.rs:78-85) for whichever material of this warp needs it - fuzzy Metal, and under the
-    // legacy integrator Lambertian and Isotropic - drawn ONCE, before the material switch: the draws are addressed by
-    // slot, so their values do not depend on where they are made, and three inlined copies of the rejection loop (two
-    // Philox calls per trip) no longer run one after the other for the lanes of one warp.
-    // Metal: the reference draws even for fuzz == 0 (§Q12); the product with fuzz is then exactly zero, so it is skipped.
-    const bool legacy = feat(F_LEGACY) && (!feat(F_HEAD) || integrator == RT_INTEGRATOR_LEGACY);
-    const bool need_ball = (feat(F_METAL) && mkind == RT_MAT_METAL && m.fuzz != 0.0) ||
-                           (legacy && (mkind == RT_MAT_LAMBERTIAN || mkind == RT_MAT_ISOTROPIC));
-    V3 ball = mk(0.0, 0.0, 0.0);
-    if (need_ball) ball = random_in_unit_sphere(ps.rng);
-    // ... and the ONE vector that Metal (the reflection, mat.rs:281), Dielectric (the incoming direction, mat.rs:345)
-    // and the legacy Lambertian (the ball sample, mat.rs:214) each normalise first, normalised once for the warp
-    const bool is_metal = feat(F_METAL) && mkind == RT_MAT_METAL, is_glass = feat(F_DIELECTRIC) && mkind == RT_MAT_DIELECTRIC;
-    // ... the HEAD integrator's Lambertian included: its direction is sampled first (main.rs:92-95: the mixture of the
-    // light pdf and the cosine pdf, pdf.rs:140-170), the pdfs that need the unit vector follow below
-    const bool head_lambert = feat(F_HEAD) && !legacy && !is_metal && !is_glass && !(feat(F_PBR) && mkind == RT_MAT_PBR) &&
-                              mkind == RT_MAT_LAMBERTIAN;
-    V3 unit = ball, onb_w = mk(0.0, 0.0, 0.0);
-    if (is_metal) unit = reflect(ps.ray.d, rec.normal);
-    else if (is_glass) unit = ps.ray.d;
-    else if (head_lambert) {
-        ONB uvw = onb_from_w(rec.normal);  // PDF::cosine_pdf (pdf.rs:83-87)
-        Draw d = draw(ps.rng, SLOT_SCATTER, 0);
-        if (d.bits_a & 1u)  // pdf.rs:169
-            new_dir = lights_random(sc, rec.p, d);
-        else
-            new_dir = onb_local(uvw, random_cosine_direction(d.a, d.b));
-        onb_w = uvw.w;
-        unit = new_dir;
-    }
-    if (is_metal || is_glass || head_lambert || (legacy && mkind == RT_MAT_LAMBERTIAN)) unit = normalized(unit);
-    if (is_metal) {  // mat.rs:280-293 == :269-278
-        V3 reflected = unit;
-        new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * ball : reflected;
+    if (feat(F_METAL) && mkind == RT_MAT_METAL) {  // mat.rs:280-293 == :269-278
+        V3 reflected = normalized(reflect(ps.ray.d, rec.normal));
+        // random_in_unit_sphere is drawn even for fuzz == 0 (§Q12); with slot addressing the
+        // draw can be skipped when its product with fuzz is exactly zero.
+        new_dir = m.fuzz != 0.0 ? reflected + m.fuzz * random_in_unit_sphere(ps.rng) : reflected;
         if (!(dot(new_dir, rec.normal) > 0.0)) return path_end_black(ps);  // None -> emitted (black)
         factor = ld3(m.albedo);
-    } else if (is_glass) {  // mat.rs:343-374 == :317-341
-        new_dir = dielectric_direction(m, unit, rec, ps.rng);
+    } else if (feat(F_DIELECTRIC) && mkind == RT_MAT_DIELECTRIC) {  // mat.rs:343-374 == :317-341
+        new_dir = dielectric_direction(m, ps.ray.d, rec, ps.rng);
         factor = mk(1.0, 1.0, 1.0);
-    } else if (legacy) {
+    } else if (feat(F_LEGACY) && (!feat(F_HEAD) || integrator == RT_INTEGRATOR_LEGACY)) {
         if (mkind == RT_MAT_LAMBERTIAN) {  // mat.rs:213-223
-            new_dir = rec.normal + unit;
+            new_dir = rec.normal + normalized(random_in_unit_sphere(ps.rng));
             if (near_zero(new_dir)) new_dir = rec.normal;
         } else if (mkind == RT_MAT_ISOTROPIC) {  // mat.rs:418-421
-            new_dir = ball;
+            new_dir = random_in_unit_sphere(ps.rng);
         } else {
             return path_end_black(ps);  // PBR has no legacy scatter (trait default None, mat.rs:56-58)
         }
@@ -1283,11 +1245,18 @@ RT_DEV bool path_shade(const DScene &sc, PathState &ps, bool hit, const HitRec &
         V3 f = pbr_brdf(&m, texture_value(sc, m.texture, rec.u, rec.v, rec.p), ps.ray.d, new_dir, rec.normal);
         factor = f / pdf_value;  // main.rs:104
     } else if (feat(F_HEAD)) {
-        if (!head_lambert) return path_end_black(ps);  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
-        // main.rs:92-98 (the direction was sampled above)
+        if (mkind != RT_MAT_LAMBERTIAN) return path_end_black(ps);  // Isotropic under HEAD: scatter_mc_method is None (§Q6)
+        // main.rs:92-98
         V3 attenuation = texture_value(sc, m.texture, rec.u, rec.v, rec.p);
+        ONB uvw = onb_from_w(rec.normal);  // PDF::cosine_pdf (pdf.rs:83-87)
+        Draw d = draw(ps.rng, SLOT_SCATTER, 0);
+        if (d.bits_a & 1u)  // pdf.rs:169
+            new_dir = lights_random(sc, rec.p, d);
+        else
+            new_dir = onb_local(uvw, random_cosine_direction(d.a, d.b));
         double light_pdf = lights_pdf_value(sc, rec.p, new_dir);
-        double cosine = dot(unit, onb_w);  // pdf.rs:131-139
+        V3 unit = normalized(new_dir);
+        double cosine = dot(unit, uvw.w);  // pdf.rs:131-139
         double cosine_pdf = cosine > 0.0 ? cosine / kPi : 0.0;
         double pdf_value = 0.5 * light_pdf + 0.5 * cosine_pdf;  // pdf.rs:143-145
         double spdf = fmax(dot(rec.normal, unit), 0.0) / kPi;    // mat.rs:246-249
