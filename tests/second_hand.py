@@ -15,6 +15,12 @@ INFRASTRUCTURE, written from the reference's sources alone, not from oracle/orac
   the sample closure                src/main.rs:811-820
   cornell_box / cornell_box_with_smoke and their cameras      src/main.rs:278-346, 700-705, 714-719
 
+r2-q adds the rest of what configs 1 and 5 reach, and a reader of the RtSceneDesc so that those scenes need not be
+built twice: Sphere / MovingSphere (src/sphere.rs:11-25,38-94,122-188), Triangle (src/tri.rs:24-57), Dielectric
+(src/mat.rs:303-374), fuzzy Metal, CheckTexture (src/texture.rs:45-54), the legacy integrator (the "old method" of
+src/main.rs:84-85 with Material::scatter, mat.rs:213-223,269-278,317-341,418-421).  A BVH node is read as the list of
+its members (bvh.rs only culls; the oracle's own tests assert BVH == list on these scenes).
+
 The one thing it shares with the oracle is the convention that replaces thread_rng: Philox4x32-10,
 restated here as well, addressed by (pixel, sample | bounce, slot, sub, seed).  The oracle's per-path radiance must
 equal this file's to rounding (tests/test_oracle_second_hand.py) - an anchor for the mixture weighting, the Rotate
@@ -399,3 +405,275 @@ def cornell_box_with_smoke(medium_draw_subs):
     world.push(ConstantMedium(box1, 0.01, ("isotropic", (1.0, 1.0, 1.0)), medium_draw_subs[0]))
     world.push(ConstantMedium(box2, 0.01, ("isotropic", (0.0, 0.0, 0.0)), medium_draw_subs[1]))
     return world, lights, (0.0, 0.0, 0.0), _camera()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# r2-q: spheres, triangles, glass, fuzzy metal, checker textures, the legacy integrator, scenes read from an RtSceneDesc
+# ---------------------------------------------------------------------------------------------------------------
+def get_sphere_uv(p):  # sphere.rs:11-25
+    phi = math.atan2(-p[2], p[0]) + math.pi
+    theta = math.acos(-p[1])
+    return phi / (2.0 * math.pi), theta / math.pi
+
+
+class Sphere:
+    def __init__(self, center, radius, material):
+        self.c, self.radius, self.material = center, radius, material
+
+    def center(self, time):
+        return self.c
+
+    def hit(self, r, t_min, t_max, ctx):  # sphere.rs:56-94 (== :150-188 with center(time))
+        center = self.center(r.time)
+        oc = sub(r.o, center)
+        a = length(r.d) ** 2
+        half_b = dot(oc, r.d)
+        c = length(oc) ** 2 - self.radius ** 2
+        discriminant = half_b ** 2 - a * c
+        if discriminant < 0.0:
+            return None
+        sqrt_d = math.sqrt(discriminant)
+        root = (-half_b - sqrt_d) / a
+        if root < t_min or root > t_max:
+            root = (-half_b + sqrt_d) / a
+            if root < t_min or root > t_max:
+                return None
+        h = Hit()
+        h.t = root
+        h.p = r.at(root)
+        h.material = self.material
+        outward = div(sub(h.p, center), self.radius)
+        h.set_face_normal(r, outward)
+        h.u, h.v = get_sphere_uv(outward)
+        return h
+
+
+class MovingSphere(Sphere):
+    def __init__(self, c0, c1, t0, t1, radius, material):
+        self.c0, self.c1, self.t0, self.t1, self.radius, self.material = c0, c1, t0, t1, radius, material
+
+    def center(self, time):  # sphere.rs:144-146
+        return add(self.c0, smul((time - self.t0) / (self.t1 - self.t0), sub(self.c1, self.c0)))
+
+
+class Triangle:
+    def __init__(self, v0, v1, v2, material):
+        self.v, self.material = (v0, v1, v2), material
+
+    def hit(self, r, t_min, t_max, ctx):  # tri.rs:24-57
+        s = sub(r.o, self.v[0])
+        e1 = sub(self.v[1], self.v[0])
+        e2 = sub(self.v[2], self.v[0])
+        s1 = cross(r.d, e2)
+        s2 = cross(s, e1)
+        s1_e1 = dot(s1, e1)
+        if s1_e1 == 0.0:
+            return None  # x / 0: every comparison of the reference then fails or yields inf / NaN; not reached by these scenes' rays
+        t = dot(s2, e2) / s1_e1
+        b1 = dot(s1, s) / s1_e1
+        b2 = dot(s2, r.d) / s1_e1
+        if t < t_min or t > t_max:
+            return None
+        if b1 < 0.0 or b2 < 0.0 or (1.0 - b1 - b2) < 0.0:
+            return None
+        h = Hit()
+        h.t, h.u, h.v = t, b1, b2
+        h.p = r.at(t)
+        h.material = self.material
+        h.set_face_normal(r, normalized(cross(e1, e2)))
+        return h
+
+
+def texture_value(tex, u, v, p):
+    """tex: ("constant", color) | ("checker", odd, even)   (texture.rs:23-27, 45-54)"""
+    while tex[0] == "checker":
+        sines = math.sin(10.0 * p[0]) * math.sin(10.0 * p[1]) * math.sin(10.0 * p[2])
+        tex = tex[1] if sines < 0.0 else tex[2]
+    return tex[1]
+
+
+def random_in_unit_sphere(draws, bounce):  # vec.rs:70-85 with the BALL slots of DESIGN.md §3
+    it = 0
+    while True:
+        a, b, _, _ = draws.draw(bounce, SLOT_BALL, 2 * it)
+        c = draws.draw(bounce, SLOT_BALL, 2 * it + 1)[0]
+        v = (-1.0 + (1.0 - -1.0) * a, -1.0 + (1.0 - -1.0) * b, -1.0 + (1.0 - -1.0) * c)
+        if length(v) < 1.0:
+            return v
+        it += 1
+
+
+def near_zero(a):  # vec.rs:107-110
+    return abs(a[0]) < 1.0e-8 and abs(a[1]) < 1.0e-8 and abs(a[2]) < 1.0e-8
+
+
+def refract(v, n, etai_over_etat):  # vec.rs:116-121
+    cos_theta = min(dot(smul(-1.0, v), n), 1.0)
+    r_out_perp = smul(etai_over_etat, add(v, smul(cos_theta, n)))
+    r_out_para = smul(-1.0 * math.sqrt(abs(1.0 - length(r_out_perp) ** 2)), n)
+    return add(r_out_perp, r_out_para)
+
+
+def dielectric_direction(ir, r_in, rec, draws, bounce):  # mat.rs:317-341 == :343-366
+    refraction_ratio = 1.0 / ir if rec.front_face else ir
+    unit_direction = normalized(r_in.d)
+    cos_theta = min(dot(smul(-1.0, unit_direction), rec.normal), 1.0)
+    sin_theta = math.sqrt(1.0 - cos_theta ** 2)
+    cannot_refract = refraction_ratio * sin_theta > 1.0
+    r0 = ((1.0 - refraction_ratio) / (1.0 + refraction_ratio)) ** 2  # mat.rs:303-307
+    reflectance = r0 + (1.0 - r0) * (1.0 - cos_theta) ** 5
+    will_reflect = draws.draw(bounce, SLOT_SCATTER, 0)[0] < reflectance
+    if cannot_refract or will_reflect:
+        return reflect(unit_direction, rec.normal)
+    return refract(unit_direction, rec.normal, refraction_ratio)
+
+
+def material_texture(m, rec):
+    return texture_value(m[1], rec.u, rec.v, rec.p)
+
+
+def scatter_legacy(m, ray, rec, draws, bounce):
+    """Material::scatter (the old method): (attenuation, scattered ray) or None."""
+    kind = m[0]
+    if kind == "lambertian":  # mat.rs:213-223
+        d = add(rec.normal, normalized(random_in_unit_sphere(draws, bounce)))
+        if near_zero(d):
+            d = rec.normal
+        return material_texture(m, rec), Ray(rec.p, d, ray.time)
+    if kind == "metal":  # mat.rs:269-278
+        reflected = normalized(reflect(ray.d, rec.normal))
+        d = add(reflected, smul(m[2], random_in_unit_sphere(draws, bounce))) if m[2] != 0.0 else reflected
+        return (m[1], Ray(rec.p, d, ray.time)) if dot(d, rec.normal) > 0.0 else None
+    if kind == "dielectric":
+        return (1.0, 1.0, 1.0), Ray(rec.p, dielectric_direction(m[1], ray, rec, draws, bounce), ray.time)
+    if kind == "isotropic":  # mat.rs:418-421
+        return material_texture(m, rec), Ray(rec.p, random_in_unit_sphere(draws, bounce), ray.time)
+    return None  # DiffuseLight (mat.rs:391-393)
+
+
+def ray_color_legacy(ray, background, world, depth, draws, max_depth):  # main.rs:41-47, 84-85, 111-119
+    if depth <= 0:
+        return (0.0, 0.0, 0.0)
+    bounce = max_depth - depth
+    rec = world.hit(ray, 0.00001, INF, (draws, bounce))
+    if rec is None:
+        return background
+    m = rec.material
+    emitted = (material_texture(m, rec) if rec.front_face else (0.0, 0.0, 0.0)) if m[0] == "light" else (0.0, 0.0, 0.0)
+    sc = scatter_legacy(m, ray, rec, draws, bounce)
+    if sc is None:
+        return emitted
+    attenuation, scattered = sc
+    return add(emitted, vmul(attenuation, ray_color_legacy(scattered, background, world, depth - 1, draws, max_depth)))
+
+
+def ray_color_general(ray, background, world, lights, depth, draws, max_depth):
+    """main.rs:41-120 for every material of configs 1-3 and 5 (the Cornell-only ray_color above plus Dielectric,
+    fuzzy Metal and textured Lambertian / DiffuseLight)."""
+    if depth <= 0:
+        return (0.0, 0.0, 0.0)
+    bounce = max_depth - depth
+    rec = world.hit(ray, 0.00001, INF, (draws, bounce))
+    if rec is None:
+        return background
+    m = rec.material
+    kind = m[0]
+    emitted = (material_texture(m, rec) if rec.front_face else (0.0, 0.0, 0.0)) if kind == "light" else (0.0, 0.0, 0.0)
+    if kind in ("metal", "dielectric"):  # ScatterRecord::Specular (mat.rs:280-293, :343-374)
+        sc = scatter_legacy(m, ray, rec, draws, bounce)
+        if sc is None:
+            return emitted
+        return vmul(sc[0], ray_color_general(sc[1], background, world, lights, depth - 1, draws, max_depth))
+    if kind == "lambertian":
+        uvw = onb_from_w(rec.normal)
+        a, b, bits_a, bits_b = draws.draw(bounce, SLOT_SCATTER, 0)
+        if bits_a & 1:
+            direction = lights.list[(bits_b * len(lights.list)) >> 11].random(rec.p, a, b)
+        else:
+            direction = onb_local(uvw, random_cosine_direction(a, b))
+        scattered = Ray(rec.p, direction, ray.time)
+        cosine = dot(normalized(direction), uvw[2])
+        cosine_pdf = cosine / math.pi if cosine > 0.0 else 0.0
+        pdf_value = 0.5 * lights.pdf_value(rec.p, direction) + 0.5 * cosine_pdf
+        scattering_pdf = max(dot(rec.normal, normalized(scattered.d)), 0.0) / math.pi
+        nxt = ray_color_general(scattered, background, world, lights, depth - 1, draws, max_depth)
+        return add(emitted, div(vmul(mul(material_texture(m, rec), scattering_pdf), nxt), pdf_value))
+    return emitted
+
+
+def scene_from_desc(abi, desc):
+    """The object graph of an RtSceneDesc (ctypes struct), in the classes of this file.  Unsupported here: image and
+    noise textures, the PBR material, sphere lights (configs 1-3 and 5 use none of them)."""
+    def tex(i):
+        t = desc.textures[i]
+        if t.kind == abi.TEX_CONSTANT:
+            return ("constant", tuple(t.color))
+        if t.kind == abi.TEX_CHECKER:
+            return ("checker", tex(t.a), tex(t.b))
+        raise NotImplementedError("texture kind %d" % t.kind)
+
+    def mat(i):
+        m = desc.materials[i]
+        if m.kind == abi.MAT_LAMBERTIAN:
+            return ("lambertian", tex(m.texture))
+        if m.kind == abi.MAT_METAL:
+            return ("metal", tuple(m.albedo), m.fuzz)
+        if m.kind == abi.MAT_DIELECTRIC:
+            return ("dielectric", m.ir)
+        if m.kind == abi.MAT_DIFFUSE_LIGHT:
+            return ("light", tex(m.texture))
+        if m.kind == abi.MAT_ISOTROPIC:
+            return ("isotropic", tex(m.texture))
+        raise NotImplementedError("material kind %d" % m.kind)
+
+    plane = {abi.PLANE_YZ: "YZ", abi.PLANE_XZ: "XZ", abi.PLANE_XY: "XY"}
+    axis = {abi.AXIS_X: "X", abi.AXIS_Y: "Y", abi.AXIS_Z: "Z"}
+
+    def node(i):
+        n = desc.nodes[i]
+        v = n.v
+        if n.kind == abi.NODE_SPHERE:
+            return Sphere((v[0], v[1], v[2]), v[3], mat(n.material))
+        if n.kind == abi.NODE_MOVING_SPHERE:
+            return MovingSphere((v[0], v[1], v[2]), (v[3], v[4], v[5]), v[6], v[7], v[8], mat(n.material))
+        if n.kind == abi.NODE_RECT:
+            return AARect(plane[n.axis], v[0], v[1], v[2], v[3], v[4], mat(n.material))
+        if n.kind == abi.NODE_TRIANGLE:
+            return Triangle((v[0], v[1], v[2]), (v[3], v[4], v[5]), (v[6], v[7], v[8]), mat(n.material))
+        if n.kind == abi.NODE_CUBE:
+            return cube((v[0], v[1], v[2]), (v[3], v[4], v[5]), mat(n.material))
+        if n.kind in (abi.NODE_LIST, abi.NODE_BVH):
+            return HittableList([node(desc.child_index[n.child + k]) for k in range(n.count)])
+        if n.kind == abi.NODE_TRANSLATE:
+            return Translate(node(n.child), (v[0], v[1], v[2]))
+        if n.kind == abi.NODE_ROTATE:
+            return Rotate(axis[n.axis], node(n.child), v[0])
+        if n.kind == abi.NODE_FLIP:
+            return FlipNormal(node(n.child))
+        if n.kind == abi.NODE_MEDIUM:
+            return ConstantMedium(node(n.child), v[0], mat(n.material), i)
+        raise NotImplementedError("node kind %d" % n.kind)
+
+    return node(desc.world), node(desc.lights), tuple(desc.background)
+
+
+class CameraPod:
+    """Camera::get_ray (camera.rs:51-59) over the nine fields of an RtCamera."""
+
+    def __init__(self, c):
+        self.origin, self.llc = tuple(c.origin), tuple(c.lower_left_corner)
+        self.horizontal, self.vertical, self.cu, self.cv = tuple(c.horizontal), tuple(c.vertical), tuple(c.cu), tuple(c.cv)
+        self.lens_radius, self.time0, self.time1 = c.lens_radius, c.time0, c.time1
+
+    get_ray = Camera.get_ray
+
+
+def path_radiance_general(world, lights, background, camera, width, height, max_depth, seed, i, j, sample, legacy):
+    draws = Draws(seed, j * width + i, sample)
+    ru, rv, _, _ = draws.draw(0, SLOT_PIXEL, 0)
+    u = (float(i) + ru) / float(width - 1)
+    v = (float(j) + rv) / float(height - 1)
+    ray = camera.get_ray(u, v, draws)
+    if legacy:
+        return ray_color_legacy(ray, background, world, max_depth, draws, max_depth)
+    return ray_color_general(ray, background, world, lights, max_depth, draws, max_depth)

@@ -68,3 +68,38 @@ def test_cornell_smoke_paths(rt, orc):
     media = [k for k in range(d.n_nodes) if d.nodes[k].kind == rt._abi.NODE_MEDIUM]
     assert len(media) == 2
     _compare(sh.cornell_box_with_smoke(media), rgb, px, py, s)
+
+
+def _general(rt, orc, hs, legacy, n_paths, seed, depth=DEPTH):
+    world, lights, background = sh.scene_from_desc(rt._abi, hs.scene_desc.struct)
+    cam = sh.CameraPod(hs.camera)
+    px, py, s = _ids(n_paths, seed)
+    osc = orc.OracleScene(hs.scene_desc)
+    integrator = rt.INTEGRATOR_LEGACY if legacy else rt.INTEGRATOR_HEAD
+    rgb, _ = osc.path_radiance(hs.camera, W, H, depth, rt.render_opts(seed=SEED, integrator=integrator), px, py, s)
+    mine = np.array([sh.path_radiance_general(world, lights, background, cam, W, H, depth, SEED, int(i), int(j), int(k), legacy)
+                     for i, j, k in zip(px, py, s)])
+    finite = np.isfinite(mine).all(axis=1) & np.isfinite(rgb).all(axis=1)
+    assert finite.mean() > 0.999
+    err = np.abs(mine[finite] - rgb[finite]) / np.maximum(np.abs(rgb[finite]), 1e-12)
+    print("paths %d, nonzero %d, max rel err %.3e, identical %.4f" % (n_paths, (rgb > 0).any(axis=1).sum(), err.max(), (mine == rgb).all(axis=1).mean()))
+    assert (rgb > 0).any(axis=1).sum() > n_paths // 10
+    assert err.max() <= 1e-10  # (sin / atan2 / acos of libm on both sides; recursion order is the reference's on both)
+    osc.close()
+
+
+def test_rtiow_random_spheres_legacy_paths(rt, orc):
+    """Config 1: spheres, moving spheres, glass, fuzzy metal, the checker ground, the legacy integrator - read from the
+    same RtSceneDesc the oracle gets, evaluated by the second restatement (a BVH node read as the list of its members)."""
+    _general(rt, orc, host_scene(rt, "random"), True, 400, 3)
+
+
+def test_cornell_scenes_through_the_scene_reader(rt, orc):
+    """The reader itself: the two Cornell scenes read from the description agree as well as the hand-built ones."""
+    _general(rt, orc, host_scene(rt, "cornell"), False, 500, 4)
+    _general(rt, orc, host_scene(rt, "cornell_smoke"), False, 500, 5)
+
+
+def test_mesh_scene_head_paths(rt, orc):
+    """Config 5 at the tests' mesh size: triangles (Moeller-Trumbore as written in tri.rs), walls, the rect light."""
+    _general(rt, orc, host_scene(rt, "mesh"), False, 40, 6, depth=12)
