@@ -17,7 +17,8 @@ INFRASTRUCTURE, written from the reference's sources alone, not from oracle/orac
 
 r2-q adds the rest of what configs 1 and 5 reach, and a reader of the RtSceneDesc so that those scenes need not be
 built twice: Sphere / MovingSphere (src/sphere.rs:11-25,38-94,122-188), Triangle (src/tri.rs:24-57), Dielectric
-(src/mat.rs:303-374), fuzzy Metal, CheckTexture (src/texture.rs:45-54), the legacy integrator (the "old method" of
+(src/mat.rs:303-374), fuzzy Metal, CheckTexture / NoiseTexture over Perlin / ImageTexture (src/texture.rs:45-121,
+src/perlin.rs:39-121), the legacy integrator (the "old method" of
 src/main.rs:84-85 with Material::scatter, mat.rs:213-223,269-278,317-341,418-421).  A BVH node is read as the list of
 its members (bvh.rs only culls; the oracle's own tests assert BVH == list on these scenes).
 
@@ -80,6 +81,19 @@ def normalized(a): return div(a, length(a))
 def reflect(v, n): return add(v, smul(-dot(v, n) * 2.0, n))   # vec.rs:112-114: self + (-self.dot(n) * 2.0 * n)
 
 
+def powi(x, n):
+    """f64::powi: square-and-multiply (compiler-rt __powidf2 / LLVM's expansion), not libm pow - Python's `x ** 2` goes
+    through pow(), which is within an ulp of x * x but not always equal to it."""
+    r = 1.0
+    while True:
+        if n & 1:
+            r *= x
+        n >>= 1
+        if n == 0:
+            return r
+        x *= x
+
+
 class Ray:
     def __init__(self, o, d, time):
         self.o, self.d, self.time = o, d, time
@@ -131,7 +145,7 @@ class AARect:
         if rec is None:
             return 0.0
         area = (self.a1 - self.a0) * (self.b1 - self.b0)
-        distance_squared = rec.t ** 2 * length(v) ** 2
+        distance_squared = powi(rec.t, 2) * powi(length(v), 2)
         cosine = abs(dot(v, rec.normal)) / length(v)
         return distance_squared / (cosine * area) if cosine != 0.0 else 0.0
 
@@ -426,10 +440,10 @@ class Sphere:
     def hit(self, r, t_min, t_max, ctx):  # sphere.rs:56-94 (== :150-188 with center(time))
         center = self.center(r.time)
         oc = sub(r.o, center)
-        a = length(r.d) ** 2
+        a = powi(length(r.d), 2)
         half_b = dot(oc, r.d)
-        c = length(oc) ** 2 - self.radius ** 2
-        discriminant = half_b ** 2 - a * c
+        c = powi(length(oc), 2) - powi(self.radius, 2)
+        discriminant = powi(half_b, 2) - a * c
         if discriminant < 0.0:
             return None
         sqrt_d = math.sqrt(discriminant)
@@ -484,11 +498,60 @@ class Triangle:
         return h
 
 
+def as_usize(x):  # Rust `as usize`: saturating, NaN -> 0
+    if x != x or x <= 0.0:
+        return 0
+    return int(x) if x < 18446744073709551615.0 else 0xFFFFFFFFFFFFFFFF
+
+
+def perlin_noise(tables, p, scale):  # perlin.rs:77-109 and perlin_interp :39-56 (the Hermite curve is applied twice, as written)
+    ranvec, perm_x, perm_y, perm_z = tables
+    u = scale * p[0] - math.floor(scale * p[0])
+    v = scale * p[1] - math.floor(scale * p[1])
+    w = scale * p[2] - math.floor(scale * p[2])
+    u = u * u * (3.0 - 2.0 * u)
+    v = v * v * (3.0 - 2.0 * v)
+    w = w * w * (3.0 - 2.0 * w)
+    i, j, k = as_usize(math.floor(scale * p[0])), as_usize(math.floor(scale * p[1])), as_usize(math.floor(scale * p[2]))
+    uu = u * u * (3.0 - 2.0 * u)
+    vv = v * v * (3.0 - 2.0 * v)
+    ww = w * w * (3.0 - 2.0 * w)
+    accum = 0.0
+    for di in range(2):
+        for dj in range(2):
+            for dk in range(2):
+                c = ranvec[perm_x[(i + di) & 255] ^ perm_y[(j + dj) & 255] ^ perm_z[(k + dk) & 255]]
+                weight = (u - float(di), v - float(dj), w - float(dk))
+                accum += (float(di) * uu + float(1 - di) * (1.0 - uu)) * (float(dj) * vv + float(1 - dj) * (1.0 - vv)) * \
+                         (float(dk) * ww + float(1 - dk) * (1.0 - ww)) * dot(c, weight)
+    return accum
+
+
+def perlin_turb(tables, p, scale, depth):  # perlin.rs:111-121
+    accum, temp_p, weight = 0.0, p, 1.0
+    for _ in range(depth):
+        accum += weight * perlin_noise(tables, temp_p, scale)
+        weight *= 0.5
+        temp_p = mul(temp_p, 2.0)
+    return abs(accum)
+
+
 def texture_value(tex, u, v, p):
-    """tex: ("constant", color) | ("checker", odd, even)   (texture.rs:23-27, 45-54)"""
+    """tex: ("constant", color) | ("checker", odd, even) | ("noise", scale, tables) | ("image", width, height, bytes)
+    (texture.rs:23-27, 45-54, 71-79, 99-121)"""
     while tex[0] == "checker":
         sines = math.sin(10.0 * p[0]) * math.sin(10.0 * p[1]) * math.sin(10.0 * p[2])
         tex = tex[1] if sines < 0.0 else tex[2]
+    if tex[0] == "noise":
+        return mul(mul((1.0, 1.0, 1.0), 0.5), 1.0 + math.sin(tex[1] * p[2] + 10.0 * perlin_turb(tex[2], p, tex[1], 7)))
+    if tex[0] == "image":
+        width, height, data = tex[1], tex[2], tex[3]
+        i = as_usize(min(max(u, 0.0), 1.0) * float(width))
+        j = as_usize(min(max(1.0 - v, 0.0), 1.0) * float(height))
+        i = min(i, width - 1)
+        j = min(j, height - 1)
+        idx = 3 * i + 3 * width * j
+        return (data[idx] / 255.0, data[idx + 1] / 255.0, data[idx + 2] / 255.0)
     return tex[1]
 
 
@@ -510,7 +573,7 @@ def near_zero(a):  # vec.rs:107-110
 def refract(v, n, etai_over_etat):  # vec.rs:116-121
     cos_theta = min(dot(smul(-1.0, v), n), 1.0)
     r_out_perp = smul(etai_over_etat, add(v, smul(cos_theta, n)))
-    r_out_para = smul(-1.0 * math.sqrt(abs(1.0 - length(r_out_perp) ** 2)), n)
+    r_out_para = smul(-1.0 * math.sqrt(abs(1.0 - powi(length(r_out_perp), 2))), n)
     return add(r_out_perp, r_out_para)
 
 
@@ -518,10 +581,10 @@ def dielectric_direction(ir, r_in, rec, draws, bounce):  # mat.rs:317-341 == :34
     refraction_ratio = 1.0 / ir if rec.front_face else ir
     unit_direction = normalized(r_in.d)
     cos_theta = min(dot(smul(-1.0, unit_direction), rec.normal), 1.0)
-    sin_theta = math.sqrt(1.0 - cos_theta ** 2)
+    sin_theta = math.sqrt(1.0 - powi(cos_theta, 2))
     cannot_refract = refraction_ratio * sin_theta > 1.0
-    r0 = ((1.0 - refraction_ratio) / (1.0 + refraction_ratio)) ** 2  # mat.rs:303-307
-    reflectance = r0 + (1.0 - r0) * (1.0 - cos_theta) ** 5
+    r0 = powi((1.0 - refraction_ratio) / (1.0 + refraction_ratio), 2)  # mat.rs:303-307
+    reflectance = r0 + (1.0 - r0) * powi(1.0 - cos_theta, 5)
     will_reflect = draws.draw(bounce, SLOT_SCATTER, 0)[0] < reflectance
     if cannot_refract or will_reflect:
         return reflect(unit_direction, rec.normal)
@@ -602,14 +665,22 @@ def ray_color_general(ray, background, world, lights, depth, draws, max_depth):
 
 
 def scene_from_desc(abi, desc):
-    """The object graph of an RtSceneDesc (ctypes struct), in the classes of this file.  Unsupported here: image and
-    noise textures, the PBR material, sphere lights (configs 1-3 and 5 use none of them)."""
+    """The object graph of an RtSceneDesc (ctypes struct), in the classes of this file.  Unsupported here: the PBR material
+    and sphere lights (the five configs use neither)."""
     def tex(i):
         t = desc.textures[i]
         if t.kind == abi.TEX_CONSTANT:
             return ("constant", tuple(t.color))
         if t.kind == abi.TEX_CHECKER:
             return ("checker", tex(t.a), tex(t.b))
+        if t.kind == abi.TEX_NOISE:
+            pt = desc.perlin[t.a]
+            ranvec = [(pt.ranvec[3 * k], pt.ranvec[3 * k + 1], pt.ranvec[3 * k + 2]) for k in range(256)]
+            return ("noise", t.scale, (ranvec, list(pt.perm_x), list(pt.perm_y), list(pt.perm_z)))
+        if t.kind == abi.TEX_IMAGE:
+            im = desc.images[t.a]
+            n = 3 * im.width * im.height
+            return ("image", im.width, im.height, bytes(bytearray(desc.texels[im.offset + k] for k in range(n))))
         raise NotImplementedError("texture kind %d" % t.kind)
 
     def mat(i):

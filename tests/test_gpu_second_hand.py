@@ -15,7 +15,9 @@ SEED = 7
 
 
 @pytest.mark.parametrize("name,legacy,n,depth", [("cornell", False, 600, 50), ("cornell_smoke", False, 600, 50),
-                                                 ("random", True, 300, 50), ("mesh", False, 40, 12)])
+                                                 ("random", True, 300, 50), ("mesh", False, 40, 12),
+                                                 ("final", False, 150, 50), ("two_perlin_spheres", True, 300, 50),
+                                                 ("earth", True, 300, 50)])
 def test_gpu_paths_match_the_second_restatement(rt, name, legacy, n, depth):
     hs = host_scene(rt, name)
     world, lights, background = sh.scene_from_desc(rt._abi, hs.scene_desc.struct)

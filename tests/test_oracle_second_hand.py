@@ -103,3 +103,16 @@ def test_cornell_scenes_through_the_scene_reader(rt, orc):
 def test_mesh_scene_head_paths(rt, orc):
     """Config 5 at the tests' mesh size: triangles (Moeller-Trumbore as written in tri.rs), walls, the rect light."""
     _general(rt, orc, host_scene(rt, "mesh"), False, 40, 6, depth=12)
+
+
+def test_next_week_final_scene_head_paths(rt, orc):
+    """Config 4: the ground boxes, the moving sphere, glass, fuzzy metal, two spherical media, the earth image texture,
+    the marble sphere (Perlin, restated here once more), 1000 spheres under Rotate + Translate."""
+    _general(rt, orc, host_scene(rt, "final"), False, 150, 8)
+
+
+def test_perlin_and_earth_scenes_under_the_sky(rt, orc):
+    """Every path of these two ends in the sky colour, so every texel and every marble value on the way is in the result
+    (main.rs:229-262: two_perlin_sphere, earth)."""
+    _general(rt, orc, host_scene(rt, "two_perlin_spheres"), True, 300, 9)
+    _general(rt, orc, host_scene(rt, "earth"), True, 300, 10)
