@@ -9,9 +9,12 @@
 // golden vectors and an OS-seeded RNG; the Rust toolchain is absent, so the
 // reference cannot be run here.  The only known-answer data it holds is the
 // six-entry get_sphere_uv table in the comment at src/sphere.rs:12-17, which
-// tests/test_oracle_kat.py checks.  Everything else is "parity unpinned" by
-// the reference itself and pinned only by this file's fidelity to the cited
-// lines.  Third-party arithmetic that lives outside /root/reference:
+// tests/test_oracle_kat.py checks; two pictures it published (img/earth.png,
+// img/TextureMapping.png) pin the camera, the sphere, its uv, the image and
+// checker textures and format_color to the pixel (tests/test_reference_images.py).
+// Everything else - every value that depends on a random draw - is "parity
+// unpinned" by the reference itself and pinned only by this file's fidelity to
+// the cited lines.  Third-party arithmetic that lives outside /root/reference:
 //   rand 0.8.5 (thread_rng / gen / gen_range / gen::<bool> / choose) — replaced
 //     by design with slot-addressed Philox4x32-10 (BASELINE north_star (4));
 //     only the mapping uniform -> sample written in the reference's own files

@@ -1,0 +1,99 @@
+"""Renders against two pictures the REFERENCE ITSELF published (README.md:6-12 -> img/earth.png, img/TextureMapping.png),
+through fixtures made by tools/make_reference_image_fixtures.py (tests/golden/reference_images.npz; the pictures stay in
+/root/reference).  The pictures come from an older revision (a sky gradient behind the scene, unknown spp, unseeded rand),
+so brightness of the sky and noise are not comparable; the GEOMETRY is, to the pixel: Camera::new / get_ray at vfov 20 and
+aspect 3:2, the sphere intersection, get_sphere_uv, ImageTexture's nearest texel over the JPEG decoded here by PIL,
+CheckTexture's sin product, Lambertian albedo under a bright sky, and format_color's gamma-2 8-bit output.  This is the
+one place where the restated path meets output of the real `cargo run`; it covers the oracle (CPU tier) and the CUDA path
+with rt_encode_rgb8 (GPU tier)."""
+import os
+
+import numpy as np
+import pytest
+from scipy import ndimage as ndi
+
+from util import host_scene
+
+W, H = 900, 600
+FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_images.npz")
+
+
+def _camera(rt, aperture):  # main.rs:642-649 / :667-680 with the 900x600 image the pictures have
+    return rt.camera_new((13.0, 2.0, 3.0), (0.0, 0.0, 0.0), (0.0, 1.0, 0.0), 20.0, W / H, aperture, 10.0, 0.0, 1.0)
+
+
+def _oracle_rgb8(rt, orc, name, aperture, spp):
+    hs = host_scene(rt, name)
+    sc = orc.OracleScene(hs.scene_desc)
+    sums, _ = sc.render(_camera(rt, aperture), W, H, spp, 50, rt.render_opts(seed=3, integrator=rt.INTEGRATOR_LEGACY))
+    sc.close()
+    return rt.format_image(sums.reshape(-1, 3), spp).reshape(H, W, 3)
+
+
+def _gpu_rgb8(rt, name, aperture, spp):
+    hs = host_scene(rt, name)
+    dev = rt.DeviceScene(hs.scene_desc, device=0)
+    dev.render(_camera(rt, aperture), W, H, spp, 50, rt.render_opts(seed=3, integrator=rt.INTEGRATOR_LEGACY), want_sums=False)
+    out = dev.encode_rgb8(W, H, spp)  # format_color on the GPU
+    dev.close()
+    return out
+
+
+def _check_earth(rgb8):
+    ref = np.load(FIXTURES)["earth_half"].astype(np.float64)
+    mine = rgb8.astype(np.float64).reshape(H // 2, 2, W // 2, 2, 3).mean(axis=(1, 3))
+    sky = rgb8[0, 0].astype(np.float64)
+    assert tuple(rgb8[0, 0]) == (214, 228, 255)  # format_color of (0.7, 0.8, 1.0): 256 * sqrt(c) clamped to 0.999
+    globe = np.abs(mine - sky).max(axis=2) > 6
+    globe_ref = ~((ref[..., 0] > 205) & (ref[..., 1] > 215) & (ref[..., 2] > 245))  # not the white-to-blue sky
+    iou = (globe & globe_ref).sum() / (globe | globe_ref).sum()
+    core = ndi.binary_erosion(globe, iterations=3)
+
+    def corr(a):
+        return min(np.corrcoef(a[..., c][core], ref[..., c][core])[0, 1] for c in range(3))
+
+    here = corr(mine)
+    moved = max(corr(np.roll(mine, s, axis=(0, 1))) for s in ((0, 1), (0, -1), (1, 0), (-1, 0)))
+    fits = [np.polyfit(mine[..., c][core], ref[..., c][core], 1) for c in range(3)]
+    print("silhouette IoU %.4f, correlation on the globe %.5f (two image pixels to the side: %.5f), fits %s" % (
+        iou, here, moved, [(round(float(k), 3), round(float(b), 2)) for k, b in fits]))
+    assert iou > 0.99               # same disc: camera, fov, aspect, sphere
+    assert here > 0.998             # same texel at the same pixel, all three channels
+    assert moved < here - 0.005     # ... and two image pixels to any side it is already visibly worse
+    for k, b in fits:               # same brightness scale: texel / 255, albedo times sky, gamma 2
+        assert abs(k - 1.0) < 0.03 and abs(b) < 3.0
+
+
+def _check_checker(rgb8):
+    z = np.load(FIXTURES)
+    ref = np.unpackbits(z["checker_dark"])[: H * W].reshape(H, W).astype(bool)
+    a = rgb8.astype(np.float64)
+    mine = (a[..., 0] + 1.0) / (a[..., 2] + 1.0) < 0.65
+    u8 = mine.astype(np.uint8)
+    interior = ndi.minimum_filter(u8, 3) == ndi.maximum_filter(u8, 3)  # not on the edge of a square
+    agree_all = (mine == ref).mean()
+    agree_in = (mine == ref)[interior].mean()
+    moved = max((np.roll(mine, s, axis=(0, 1)) == ref).mean() for s in ((0, 1), (0, -1), (1, 0), (-1, 0)))
+    print("checker: %.4f of all pixels, %.5f of the %.0f %% away from an edge; one pixel away %.4f" % (
+        agree_all, agree_in, 100 * interior.mean(), moved))
+    assert interior.mean() > 0.6
+    assert agree_in > 0.999          # every square of both spheres is where the reference drew it
+    assert agree_all > 0.93 and moved < agree_all - 0.005  # edges included; one pixel to any side is worse
+
+
+def test_oracle_earth_is_the_picture_the_reference_published(rt, orc):
+    _check_earth(_oracle_rgb8(rt, orc, "earth", 0.1, 32))
+
+
+def test_oracle_checkered_spheres_are_the_picture_the_reference_published(rt, orc):
+    _check_checker(_oracle_rgb8(rt, orc, "two_spheres", 0.0, 16))
+
+
+@pytest.mark.gpu
+def test_gpu_earth_is_the_picture_the_reference_published(rt):
+    _check_earth(_gpu_rgb8(rt, "earth", 0.1, 64))
+
+
+@pytest.mark.gpu
+def test_gpu_checkered_spheres_are_the_picture_the_reference_published(rt):
+    _check_checker(_gpu_rgb8(rt, "two_spheres", 0.0, 64))

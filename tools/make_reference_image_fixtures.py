@@ -1,0 +1,38 @@
+#!/usr/bin/env python
+"""Fixtures derived from two pictures the reference publishes (README.md:6-12 links img/): what tests/test_reference_images.py
+compares a render with.  Run in the container that has /root/reference; the .npz travels, the pictures do not.
+
+  img/earth.png           900x600  `Scene::Earth` (main.rs:246-254, camera :667-680): a sphere with the earth map
+                          -> `earth_half`: RGB box-averaged 2x2 to 450x300, uint8
+  img/TextureMapping.png  900x600  `Scene::TwoSpheres` (main.rs:212-227, camera :642-649): two checkered spheres
+                          -> `checker_dark`: one bit per pixel, set where the pixel is a dark (0.3, 0.3, 1) square
+                             ((R+1)/(B+1) < 0.65: the ratio does not depend on how bright the square is lit)
+
+Both were rendered by an older revision than HEAD (a white-to-blue sky gradient behind the scene instead of the constant
+background of main.rs:670, unknown spp, unseeded rand): the sky and the noise are not comparable, the geometry is - camera,
+sphere intersection, get_sphere_uv, the nearest-texel lookup, the JPEG decode, the checker's sin product, the gamma-2
+8-bit output - and that is what the tests use."""
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+SRC = "/root/reference/img"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "reference_images.npz")
+
+
+def main():
+    earth = np.asarray(Image.open(os.path.join(SRC, "earth.png")).convert("RGB")).astype(np.float64)
+    h, w, _ = earth.shape
+    assert (w, h) == (900, 600)
+    earth_half = np.rint(earth.reshape(h // 2, 2, w // 2, 2, 3).mean(axis=(1, 3))).astype(np.uint8)
+    chk = np.asarray(Image.open(os.path.join(SRC, "TextureMapping.png")).convert("RGB")).astype(np.float64)
+    assert chk.shape == (600, 900, 3)
+    dark = (chk[..., 0] + 1.0) / (chk[..., 2] + 1.0) < 0.65
+    np.savez_compressed(OUT, earth_half=earth_half, checker_dark=np.packbits(dark), checker_shape=np.array(dark.shape))
+    print("wrote", os.path.normpath(OUT), os.path.getsize(OUT), "bytes")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
