@@ -7,8 +7,11 @@ compares a render with.  Run in the container that has /root/reference; the .npz
   img/TextureMapping.png  900x600  `Scene::TwoSpheres` (main.rs:212-227, camera :642-649): two checkered spheres
                           -> `checker_dark`: one bit per pixel, set where the pixel is a dark (0.3, 0.3, 1) square
                              ((R+1)/(B+1) < 0.65: the ratio does not depend on how bright the square is lit)
+  img/CornellBox.png      600x600  `Scene::CornellBox` (main.rs:278-311, camera :700-719) at a revision whose tall box
+                          was still white (HEAD: Metal, main.rs:306)
+                          -> `cornell_quarter`: RGB box-averaged 4x4 to 150x150, uint8
 
-Both were rendered by an older revision than HEAD (a white-to-blue sky gradient behind the scene instead of the constant
+All three were rendered by an older revision than HEAD (a white-to-blue sky gradient behind the scene instead of the constant
 background of main.rs:670, unknown spp, unseeded rand): the sky and the noise are not comparable, the geometry is - camera,
 sphere intersection, get_sphere_uv, the nearest-texel lookup, the JPEG decode, the checker's sin product, the gamma-2
 8-bit output - and that is what the tests use."""
@@ -30,7 +33,11 @@ def main():
     chk = np.asarray(Image.open(os.path.join(SRC, "TextureMapping.png")).convert("RGB")).astype(np.float64)
     assert chk.shape == (600, 900, 3)
     dark = (chk[..., 0] + 1.0) / (chk[..., 2] + 1.0) < 0.65
-    np.savez_compressed(OUT, earth_half=earth_half, checker_dark=np.packbits(dark), checker_shape=np.array(dark.shape))
+    box = np.asarray(Image.open(os.path.join(SRC, "CornellBox.png")).convert("RGB")).astype(np.float64)
+    assert box.shape == (600, 600, 3)
+    cornell_quarter = np.rint(box.reshape(150, 4, 150, 4, 3).mean(axis=(1, 3))).astype(np.uint8)
+    np.savez_compressed(OUT, earth_half=earth_half, checker_dark=np.packbits(dark), checker_shape=np.array(dark.shape),
+                        cornell_quarter=cornell_quarter)
     print("wrote", os.path.normpath(OUT), os.path.getsize(OUT), "bytes")
 
 
