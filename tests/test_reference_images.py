@@ -1,5 +1,5 @@
-"""Renders against three pictures the REFERENCE ITSELF published (README.md:6-12 -> img/earth.png, img/TextureMapping.png,
-img/CornellBox.png),
+"""Renders against four pictures the REFERENCE ITSELF published (README.md:6-12 -> img/earth.png, img/TextureMapping.png,
+img/CornellBox.png, img/volume.png),
 through fixtures made by tools/make_reference_image_fixtures.py (tests/golden/reference_images.npz; the pictures stay in
 /root/reference).  The pictures come from an older revision (a sky gradient behind the scene, unknown spp, unseeded rand),
 so brightness of the sky and noise are not comparable; the GEOMETRY is, to the pixel: Camera::new / get_ray at vfov 20 and
@@ -149,6 +149,45 @@ def test_gpu_cornell_box_is_the_picture_the_reference_published(rt):
     out = dev.encode_rgb8(600, 600, 256)
     dev.close()
     _check_cornell(out, 0.04)
+
+
+SMOKE_REGIONS = {"floor, front": (135, 140, 62, 88), "floor, left": (130, 135, 15, 28), "back wall": (38, 60, 82, 112),
+                 "ceiling": (10, 15, 100, 115), "red wall": (62, 88, 130, 140), "green wall": (62, 88, 10, 20),
+                 "white smoke, front": (108, 125, 83, 110), "dark smoke, front": (75, 112, 50, 72)}
+
+
+def _check_smoke(lin, spread_max):
+    """img/volume.png: its revision's smoke scattered (Isotropic::scatter through the `old method`, main.rs:82-84), which is
+    what the LEGACY integrator does with HEAD's cornell_box_with_smoke.  `lin`: (600, 600, 3) linear radiance.  Same
+    reading as the Cornell picture: the picture is the render times one factor in every region - through the dark and the
+    white smoke too - and it is the SAME factor (1.67-1.70: a 13 x 13 sample loop divided by 100 would give 1.69; HEAD
+    has no such loop).  ConstantMedium's boundary queries and free-flight distance and Isotropic's scatter are in it."""
+    ref = np.load(FIXTURES)["smoke_quarter"].astype(np.float64)
+    mine = lin.reshape(150, 4, 150, 4, 3).mean(axis=(1, 3))
+    ratios = np.array([((ref[y0:y1, x0:x1] / 256.0) ** 2).mean(axis=(0, 1)) / mine[y0:y1, x0:x1].mean(axis=(0, 1))
+                       for y0, y1, x0, x1 in SMOKE_REGIONS.values()])
+    spread = np.abs(ratios / np.median(ratios) - 1.0).max()
+    print("smoke: picture / render in linear radiance: median %.3f, every region and channel within %.1f %% of it" % (
+        np.median(ratios), 100 * spread))
+    assert spread < spread_max
+    assert 1.6 < np.median(ratios) < 1.8
+
+
+def test_oracle_cornell_smoke_is_the_picture_the_reference_published(rt, orc):
+    hs = host_scene(rt, "cornell_smoke")
+    sc = orc.OracleScene(hs.scene_desc)
+    sums, _ = sc.render(hs.camera, 600, 600, 24, 50, rt.render_opts(seed=3, integrator=rt.INTEGRATOR_LEGACY))
+    sc.close()
+    _check_smoke(np.nan_to_num(sums) / 24.0, 0.15)  # brute force at 24 spp: region means are within 10 % (256 spp: 3.5 %)
+
+
+@pytest.mark.gpu
+def test_gpu_cornell_smoke_is_the_picture_the_reference_published(rt):
+    hs = host_scene(rt, "cornell_smoke")
+    dev = rt.DeviceScene(hs.scene_desc, device=0)
+    sums, _ = dev.render(hs.camera, 600, 600, 4096, 50, rt.render_opts(seed=3, integrator=rt.INTEGRATOR_LEGACY))
+    dev.close()
+    _check_smoke(np.nan_to_num(sums.astype(np.float64)) / 4096.0, 0.05)
 
 
 def test_oracle_earth_is_the_picture_the_reference_published(rt, orc):

@@ -10,8 +10,11 @@ compares a render with.  Run in the container that has /root/reference; the .npz
   img/CornellBox.png      600x600  `Scene::CornellBox` (main.rs:278-311, camera :700-719) at a revision whose tall box
                           was still white (HEAD: Metal, main.rs:306)
                           -> `cornell_quarter`: RGB box-averaged 4x4 to 150x150, uint8
+  img/volume.png          600x600  `Scene::CornellSmoke` (main.rs:313-346) at a revision whose smoke still scattered
+                          (the `old method` of main.rs:82-84; at HEAD Isotropic has no scatter_mc_method and absorbs, §Q6)
+                          -> `smoke_quarter`: RGB box-averaged 4x4 to 150x150, uint8
 
-All three were rendered by an older revision than HEAD (a white-to-blue sky gradient behind the scene instead of the constant
+All four were rendered by an older revision than HEAD (a white-to-blue sky gradient behind the scene instead of the constant
 background of main.rs:670, unknown spp, unseeded rand): the sky and the noise are not comparable, the geometry is - camera,
 sphere intersection, get_sphere_uv, the nearest-texel lookup, the JPEG decode, the checker's sin product, the gamma-2
 8-bit output - and that is what the tests use."""
@@ -23,6 +26,12 @@ from PIL import Image
 
 SRC = "/root/reference/img"
 OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "reference_images.npz")
+
+
+def quarter(name):
+    a = np.asarray(Image.open(os.path.join(SRC, name)).convert("RGB")).astype(np.float64)
+    assert a.shape == (600, 600, 3)
+    return np.rint(a.reshape(150, 4, 150, 4, 3).mean(axis=(1, 3))).astype(np.uint8)
 
 
 def main():
@@ -37,7 +46,7 @@ def main():
     assert box.shape == (600, 600, 3)
     cornell_quarter = np.rint(box.reshape(150, 4, 150, 4, 3).mean(axis=(1, 3))).astype(np.uint8)
     np.savez_compressed(OUT, earth_half=earth_half, checker_dark=np.packbits(dark), checker_shape=np.array(dark.shape),
-                        cornell_quarter=cornell_quarter)
+                        cornell_quarter=cornell_quarter, smoke_quarter=quarter("volume.png"))
     print("wrote", os.path.normpath(OUT), os.path.getsize(OUT), "bytes")
 
 
