@@ -71,13 +71,13 @@ def _check_checker(rgb8):
     a = rgb8.astype(np.float64)
     mine = (a[..., 0] + 1.0) / (a[..., 2] + 1.0) < 0.65
     u8 = mine.astype(np.uint8)
-    interior = ndi.minimum_filter(u8, 3) == ndi.maximum_filter(u8, 3)  # not on the edge of a square
+    interior = ndi.minimum_filter(u8, 5) == ndi.maximum_filter(u8, 5)  # not within two pixels of the edge of a square
     agree_all = (mine == ref).mean()
     agree_in = (mine == ref)[interior].mean()
     moved = max((np.roll(mine, s, axis=(0, 1)) == ref).mean() for s in ((0, 1), (0, -1), (1, 0), (-1, 0)))
     print("checker: %.4f of all pixels, %.5f of the %.0f %% away from an edge; one pixel away %.4f" % (
         agree_all, agree_in, 100 * interior.mean(), moved))
-    assert interior.mean() > 0.6
+    assert interior.mean() > 0.5
     assert agree_in > 0.999          # every square of both spheres is where the reference drew it
     assert agree_all > 0.93 and moved < agree_all - 0.005  # edges included; one pixel to any side is worse
 
