@@ -535,7 +535,43 @@ struct RefOrder {
     };
     const std::vector<RefBox> &boxes;
     std::vector<Item> items;  // permutation of [0, n), sorted range by range
+    std::vector<Item> tmp;    // the radix sort's other buffer (a node only touches its own range)
     std::atomic<int> bad{0};  // 1: NaN extent, 2: NaN centroid
+
+    // Stable LSD radix sort of items[first, first + n) by key (no NaN among them): the same order as
+    // std::stable_sort with `x.key < y.key`, in a third of the time on the large nodes of a mesh.  -0.0 and +0.0
+    // compare equal there, so both map to the same integer here.
+    static uint64_t sortable(double key) {
+        uint64_t u;
+        key += 0.0;  // -0.0 -> +0.0
+        std::memcpy(&u, &key, 8);
+        return u ^ ((u >> 63) ? ~0ull : 0x8000000000000000ull);
+    }
+    void radix_sort(size_t first, size_t n) {
+        uint32_t hist[8][256];
+        std::memset(hist, 0, sizeof(hist));
+        Item *a = items.data() + first, *b = tmp.data() + first;
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t u = sortable(a[i].key);
+            for (int d = 0; d < 8; ++d) hist[d][(u >> (8 * d)) & 255u]++;
+        }
+        for (int d = 0; d < 8; ++d) {
+            uint32_t *h = hist[d];
+            bool trivial = false;
+            for (int k = 0; k < 256; ++k)
+                if (h[k] == n) trivial = true;  // every key has the same digit here
+            if (trivial) continue;
+            uint32_t acc = 0;
+            for (int k = 0; k < 256; ++k) {
+                const uint32_t c = h[k];
+                h[k] = acc;
+                acc += c;
+            }
+            for (size_t i = 0; i < n; ++i) b[h[(sortable(a[i].key) >> (8 * d)) & 255u]++] = a[i];
+            std::swap(a, b);
+        }
+        if (a != items.data() + first) std::copy(a, a + n, items.data() + first);
+    }
 
     void rec(size_t first, size_t n, int depth) {
         if (n <= 1 || bad.load(std::memory_order_relaxed)) return;
@@ -571,7 +607,8 @@ struct RefOrder {
         }
         // bvh.rs:51 sort_unstable_by: the order of equal keys is unspecified in the reference;
         // a stable sort fixes it (same choice as the oracle)
-        std::stable_sort(items.begin() + first, items.begin() + first + n, [](const Item &x, const Item &y) { return x.key < y.key; });
+        if (n >= 1024 && !std::getenv("RTB200_COMPILE_SERIAL")) radix_sort(first, n);  // (the switch: the tests compare the two)
+        else std::stable_sort(items.begin() + first, items.begin() + first + n, [](const Item &x, const Item &y) { return x.key < y.key; });
         const size_t half = n / 2;
         if (n >= 16384 && depth < 5) {
             auto left = std::async(std::launch::async, [&] { rec(first, half, depth + 1); });
@@ -603,7 +640,7 @@ bool ref_bvh_order(const RtSceneDesc &d, const std::vector<uint32_t> &hit, doubl
         return false;
     }
     lap("boxes");
-    RefOrder ro{boxes, std::vector<RefOrder::Item>(hit.size())};
+    RefOrder ro{boxes, std::vector<RefOrder::Item>(hit.size()), std::vector<RefOrder::Item>(hit.size())};
     for (size_t i = 0; i < hit.size(); ++i) ro.items[i] = RefOrder::Item{0.0, (uint32_t)i};
     ro.rec(0, hit.size(), 0);
     lap("sort");
