@@ -282,13 +282,21 @@ def compile_scene(scene_desc):
     DeviceScene.from_compiled (multi_gpu.render_distributed does that over torch.distributed)."""
     h = C.c_void_p()
     _check(_dev.rt_compile(scene_desc.ptr, C.byref(h)))
-    try:
-        n = int(_dev.rt_compiled_size(h))
-        blob = np.empty(n, dtype=np.uint8)
-        C.memmove(blob.ctypes.data, _dev.rt_compiled_data(h), n)
-    finally:
-        _dev.rt_compiled_destroy(h)
-    return blob
+    n = int(_dev.rt_compiled_size(h))
+    # a view of the library's buffer, not a copy (64 MB for config 5): the handle lives as long as the array does
+    buf = (C.c_ubyte * n).from_address(_dev.rt_compiled_data(h))
+    buf._owner = _CompiledHandle(h)
+    return np.frombuffer(buf, dtype=np.uint8)
+
+
+class _CompiledHandle:
+    def __init__(self, handle):
+        self._h = handle
+
+    def __del__(self):
+        if self._h is not None and _dev is not None:
+            _dev.rt_compiled_destroy(self._h)
+            self._h = None
 
 
 def compiled_hash(blob):

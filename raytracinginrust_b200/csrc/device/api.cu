@@ -581,12 +581,13 @@ void rt_scene_destroy(RtScene *scene) { delete scene; }
 // ---------------------------------------------------------------------------
 }  // extern "C"
 
-struct RtCompiled {
-    std::vector<unsigned char> blob;
+struct RtCompiled {  // (not a std::vector: 64 MB of zero fill before every byte is overwritten cost 25 ms on config 5)
+    std::unique_ptr<unsigned char[]> data;
+    uint64_t size = 0;
 };
 
 namespace {
-constexpr uint64_t kBlobMagic = 0x3130424c42425452ull;  // "RTBBLB01"
+constexpr uint64_t kBlobMagic = 0x3230424c42425452ull;  // "RTBBLB02" (02: four-lane checksum)
 constexpr uint32_t kBlobTables = 12;
 struct BlobHeader {
     uint64_t magic;
@@ -597,17 +598,43 @@ struct BlobHeader {
     uint32_t n_world_groups, max_bvh_depth, shutter_limited, pad;
     double background[3];
 };
+// FNV-1a over 64-bit words in four interleaved lanes (the multiply is a 3-4 cycle dependency: one lane hashes 64 MB in
+// ~25 ms, four in ~8), the lanes folded at the end, the tail byte by byte.
 uint64_t fnv1a(const unsigned char *p, uint64_t n) {
-    uint64_t h = 1469598103934665603ull;
-    // eight bytes per step keeps 75 MB at a few tens of ms; the tail byte by byte
+    const uint64_t kPrime = 1099511628211ull;
+    uint64_t h0 = 1469598103934665603ull, h1 = h0 ^ 1u, h2 = h0 ^ 2u, h3 = h0 ^ 3u;
     uint64_t i = 0;
-    for (; i + 8 <= n; i += 8) {
-        uint64_t w;
-        std::memcpy(&w, p + i, 8);
-        h = (h ^ w) * 1099511628211ull;
+    for (; i + 32 <= n; i += 32) {
+        uint64_t w[4];
+        std::memcpy(w, p + i, 32);
+        h0 = (h0 ^ w[0]) * kPrime;
+        h1 = (h1 ^ w[1]) * kPrime;
+        h2 = (h2 ^ w[2]) * kPrime;
+        h3 = (h3 ^ w[3]) * kPrime;
     }
-    for (; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    uint64_t h = h0;
+    h = (h ^ h1) * kPrime;
+    h = (h ^ h2) * kPrime;
+    h = (h ^ h3) * kPrime;
+    for (; i < n; ++i) h = (h ^ p[i]) * kPrime;
     return h;
+}
+// memcpy with a few threads for the large tables (a fresh 64 MB destination is mostly page faults)
+void copy_bytes(unsigned char *dst, const void *src, uint64_t bytes) {
+    const uint64_t kPiece = 8ull << 20;
+    if (bytes < 2 * kPiece) {
+        if (bytes) std::memcpy(dst, src, bytes);
+        return;
+    }
+    const unsigned n = (unsigned)std::min<uint64_t>(4, bytes / kPiece);
+    const uint64_t per = ((bytes + n - 1) / n + 63) & ~63ull;
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < n; ++t) {
+        const uint64_t a = t * per, b = std::min(bytes, a + per);
+        if (a < b) pool.emplace_back([=] { std::memcpy(dst + a, (const unsigned char *)src + a, b - a); });
+    }
+    std::memcpy(dst, src, std::min(bytes, per));
+    for (std::thread &th : pool) th.join();
 }
 uint64_t pad16(uint64_t n) { return (n + 15u) & ~15ull; }
 
@@ -618,7 +645,7 @@ void for_each_table(CompiledScene &cs, F f) {
     f(k++, cs.lights); f(k++, cs.materials); f(k++, cs.textures); f(k++, cs.images); f(k++, cs.perlin); f(k++, cs.texels);
 }
 
-void serialize(CompiledScene &cs, std::vector<unsigned char> &blob) {
+void serialize(CompiledScene &cs, RtCompiled &dst) {
     BlobHeader h;
     std::memset(&h, 0, sizeof(h));
     h.magic = kBlobMagic;
@@ -635,15 +662,19 @@ void serialize(CompiledScene &cs, std::vector<unsigned char> &blob) {
     h.max_bvh_depth = cs.max_bvh_depth;
     h.shutter_limited = cs.shutter_limited ? 1u : 0u;
     for (int a = 0; a < 3; ++a) h.background[a] = cs.background[a];
-    blob.assign(total, 0);
+    dst.data.reset(new unsigned char[total]);
+    dst.size = total;
+    unsigned char *blob = dst.data.get();
+    std::memset(blob, 0, h.header_bytes);
     uint64_t off = h.header_bytes;
     for_each_table(cs, [&](int, auto &v) {
         const uint64_t bytes = v.size() * sizeof(v[0]);
-        if (bytes) std::memcpy(blob.data() + off, v.data(), bytes);
+        copy_bytes(blob + off, v.data(), bytes);
+        std::memset(blob + off + bytes, 0, pad16(bytes) - bytes);
         off += pad16(bytes);
     });
-    h.hash = fnv1a(blob.data() + h.header_bytes, total - h.header_bytes);
-    std::memcpy(blob.data(), &h, sizeof(h));
+    h.hash = fnv1a(blob + h.header_bytes, total - h.header_bytes);
+    std::memcpy(blob, &h, sizeof(h));
 }
 
 // false: not a blob of this library (message in err)
@@ -667,7 +698,7 @@ bool deserialize(const void *data, uint64_t size, CompiledScene &cs, std::string
     for_each_table(cs, [&](int k, auto &v) {
         v.resize(h.count[k]);
         const uint64_t bytes = h.count[k] * sizeof(v[0]);
-        if (bytes) std::memcpy(v.data(), p + off, bytes);
+        copy_bytes((unsigned char *)v.data(), p + off, bytes);
         off += pad16(bytes);
     });
     cs.n_world_groups = h.n_world_groups;
@@ -693,17 +724,24 @@ extern "C" {
 RtStatus rt_compile(const RtSceneDesc *desc, RtCompiled **out_compiled) {
     if (!desc || !out_compiled) return fail(RT_ERR_BAD_ARGUMENT, "null argument");
     *out_compiled = nullptr;
+    auto T0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[rt_compile] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
+    {
     CompiledScene cs;
     std::string err;
     RtStatus st = compile_scene(*desc, cs, err);
+    lap("compile_scene");
     if (st != RT_OK) return fail(st, err);
     std::unique_ptr<RtCompiled> c(new RtCompiled());
-    serialize(cs, c->blob);
+    serialize(cs, *c);
+    lap("serialize");
     *out_compiled = c.release();
+    }
+    lap("destroy");
     return RT_OK;
 }
-const void *rt_compiled_data(const RtCompiled *c) { return c ? c->blob.data() : nullptr; }
-uint64_t rt_compiled_size(const RtCompiled *c) { return c ? c->blob.size() : 0; }
+const void *rt_compiled_data(const RtCompiled *c) { return c ? c->data.get() : nullptr; }
+uint64_t rt_compiled_size(const RtCompiled *c) { return c ? c->size : 0; }
 uint64_t rt_compiled_hash(const void *data, uint64_t size) {
     BlobHeader h;
     if (!data || size < sizeof(h)) return 0;
