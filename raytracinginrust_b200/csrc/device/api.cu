@@ -726,7 +726,6 @@ RtStatus rt_compile(const RtSceneDesc *desc, RtCompiled **out_compiled) {
     *out_compiled = nullptr;
     auto T0 = std::chrono::steady_clock::now();
     auto lap = [&](const char *what) { if (getenv("RTB200_COMPILE_TIMING")) { auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[rt_compile] %s %.3f s\n", what, std::chrono::duration<double>(t - T0).count()); T0 = t; } };
-    {
     CompiledScene cs;
     std::string err;
     RtStatus st = compile_scene(*desc, cs, err);
@@ -736,8 +735,6 @@ RtStatus rt_compile(const RtSceneDesc *desc, RtCompiled **out_compiled) {
     serialize(cs, *c);
     lap("serialize");
     *out_compiled = c.release();
-    }
-    lap("destroy");
     return RT_OK;
 }
 const void *rt_compiled_data(const RtCompiled *c) { return c ? c->data.get() : nullptr; }

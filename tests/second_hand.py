@@ -73,7 +73,21 @@ def sub(a, b): return (a[0] - b[0], a[1] - b[1], a[2] - b[2])
 def mul(a, s): return (a[0] * s, a[1] * s, a[2] * s)          # Vec3 * f64
 def smul(s, a): return (s * a[0], s * a[1], s * a[2])         # f64 * Vec3
 def vmul(a, b): return (a[0] * b[0], a[1] * b[1], a[2] * b[2])
-def div(a, s): return (a[0] / s, a[1] / s, a[2] / s)
+def fdiv(x, y):
+    """IEEE division (Python raises where f64 gives inf or NaN; the PBR material reaches 0/0, main.rs:104)."""
+    try:
+        return x / y
+    except ZeroDivisionError:
+        if x != x or x == 0.0:
+            return float("nan")
+        return math.copysign(float("inf"), x) * math.copysign(1.0, y)
+
+
+def fsqrt(x):  # f64::sqrt of a negative number is NaN
+    return math.sqrt(x) if x >= 0.0 else float("nan")
+
+
+def div(a, s): return (fdiv(a[0], s), fdiv(a[1], s), fdiv(a[2], s))
 def dot(a, b): return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]
 def length(a): return math.sqrt(dot(a, a))
 def cross(a, b): return (a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0])
@@ -462,6 +476,29 @@ class Sphere:
         return h
 
 
+def _sphere_pdf_value(self, o, v):  # sphere.rs:103-111
+    if self.hit(Ray(o, v, 0.0), 0.001, 1.7976931348623157e308, None) is None:
+        return 0.0
+    cos_theta_max = fsqrt(1.0 - fdiv(powi(self.radius, 2), powi(length(sub(self.c, o)), 2)))
+    solid_angle = 2.0 * math.pi * (1.0 - cos_theta_max)
+    return fdiv(1.0, solid_angle)
+
+
+def _sphere_random(self, o, r1, r2):  # sphere.rs:113-118 over random_to_sphere, :27-36
+    direction = sub(self.c, o)
+    distance_squared = powi(length(direction), 2)
+    uvw = onb_from_w(direction)
+    z = 1.0 + r2 * (fsqrt(1.0 - fdiv(powi(self.radius, 2), distance_squared)) - 1.0)
+    phi = 2.0 * math.pi * r1
+    x = math.cos(phi) * fsqrt(1.0 - powi(z, 2))
+    y = math.sin(phi) * fsqrt(1.0 - powi(z, 2))
+    return onb_local(uvw, (x, y, z))
+
+
+Sphere.pdf_value = _sphere_pdf_value
+Sphere.random = _sphere_random
+
+
 class MovingSphere(Sphere):
     def __init__(self, c0, c1, t0, t1, radius, material):
         self.c0, self.c1, self.t0, self.t1, self.radius, self.material = c0, c1, t0, t1, radius, material
@@ -630,6 +667,146 @@ def ray_color_legacy(ray, background, world, depth, draws, max_depth):  # main.r
     return add(emitted, vmul(attenuation, ray_color_legacy(scattered, background, world, depth - 1, draws, max_depth)))
 
 
+def _clamp01(x):
+    return min(max(x, 0.0), 1.0)
+
+
+def schlick_fresnel(u):  # mat.rs:10-14
+    m = _clamp01(1.0 - u)
+    m2 = powi(m, 2)
+    return m2 * m2 * m
+
+
+def gtr_1(n_dot_h, a):  # mat.rs:16-24
+    if a >= 1.0:
+        return 1.0 / math.pi
+    a2 = a * a
+    t = 1.0 + (a2 - 1.0) * n_dot_h * n_dot_h
+    return fdiv(a2 - 1.0, math.pi * math.log2(a2) * t)
+
+
+def gtr_2_aniso(n_dot_h, h_dot_x, h_dot_y, ax, ay):  # mat.rs:32-34
+    return fdiv(1.0, math.pi * ax * ay * powi(powi(h_dot_x / ax, 2) + powi(h_dot_y / ay, 2) + n_dot_h * n_dot_h, 2))
+
+
+def smith_g_ggx(n_dot_v, alpha_g):  # mat.rs:36-40
+    a = alpha_g * alpha_g
+    b = n_dot_v * n_dot_v
+    return fdiv(1.0, n_dot_v + fsqrt(a + b - a * b))
+
+
+def smith_g_ggx_aniso(n_dot_v, v_dot_x, v_dot_y, ax, ay):  # mat.rs:42-44
+    return fdiv(1.0, n_dot_v + math.sqrt(powi(v_dot_x * ax, 2) + powi(v_dot_y * ay, 2) + powi(n_dot_v, 2)))
+
+
+def mix(a, b, t):  # mat.rs:50-52
+    return a * (1.0 - t) + b * t
+
+
+def vmix(a, b, t):  # vec.rs:60-68
+    return (a[0] * (1.0 - t) + b[0] * t, a[1] * (1.0 - t) + b[1] * t, a[2] * (1.0 - t) + b[2] * t)
+
+
+def _powf(x, y):  # f64::powf is libm's pow; a negative base with a fractional exponent is NaN there, an exception here
+    try:
+        return math.pow(x, y)
+    except ValueError:
+        return float("nan")
+
+
+def _aniso_alphas(roughness, anisotropic):  # mat.rs:170-172 == pdf.rs:43-45,121-123
+    aspect = math.sqrt(1.0 - anisotropic * 0.9)
+    return max(powi(roughness, 2) / aspect, 0.001), max(powi(roughness, 2) * aspect, 0.001)
+
+
+def pbr_brdf(m, r_in, r_out, rec):  # mat.rs:134-198
+    _, base, metallic, subsurface, specular, roughness, specular_tint, anisotropic, sheen, sheen_tint, clearcoat, clearcoat_gloss = m
+    l = mul(normalized(r_in.d), -1.0)
+    v = normalized(r_out.d)
+    x, y, n = onb_from_w(rec.normal)
+    n_dot_v = dot(n, v)
+    n_dot_l = dot(n, l)
+    if n_dot_l < 0.0 or n_dot_v < 0.0:
+        return (0.0, 0.0, 0.0)
+    h = normalized(add(l, v))
+    n_dot_h = dot(n, h)
+    l_dot_h = dot(l, h)
+    c = texture_value(base, rec.u, rec.v, rec.p)
+    cd_lin = (_powf(c[0], 2.2), _powf(c[1], 2.2), _powf(c[2], 2.2))  # mon_to_lin, mat.rs:46-48
+    cd_lum = 0.3 * cd_lin[0] + 0.6 * cd_lin[1] + 0.1 * cd_lin[2]
+    white = (1.0, 1.0, 1.0)
+    c_tint = div(cd_lin, cd_lum) if cd_lum > 0.0 else white
+    c_spec0 = vmix(mul(mul(vmix(white, c_tint, specular_tint), 0.08), specular), cd_lin, metallic)
+    c_sheen = vmix(white, c_tint, sheen_tint)
+    fresnel_l = schlick_fresnel(n_dot_l)
+    fresnel_v = schlick_fresnel(n_dot_v)
+    fresnel_diffuse_90 = 0.5 + 2.0 * l_dot_h * l_dot_h * roughness
+    fresnel_diffuse = mix(1.0, fresnel_diffuse_90, fresnel_l) * mix(1.0, fresnel_diffuse_90, fresnel_v)
+    fss90 = l_dot_h * l_dot_h * roughness
+    fss = mix(1.0, fss90, fresnel_l) * mix(1.0, fss90, fresnel_v)
+    subface_scatter = 1.25 * (fss * (fdiv(1.0, n_dot_l + n_dot_v) - 0.5) + 0.5)
+    ax, ay = _aniso_alphas(roughness, anisotropic)
+    d_specular = gtr_2_aniso(n_dot_h, dot(h, x), dot(h, y), ax, ay)
+    fresnel_h = schlick_fresnel(l_dot_h)
+    f_specular = vmix(c_spec0, white, fresnel_h)
+    g_specular = smith_g_ggx_aniso(n_dot_l, dot(l, x), dot(l, y), ax, ay) * smith_g_ggx_aniso(n_dot_v, dot(v, x), dot(v, y), ax, ay)
+    fresnel_sheen = smul(fresnel_h * sheen, c_sheen)  # f64 * f64 * Vec3, left to right
+    d_reflect = gtr_1(n_dot_h, mix(0.1, 0.001, clearcoat_gloss))
+    f_reflect = mix(0.04, 1.0, fresnel_h)
+    g_reflect = smith_g_ggx(n_dot_l, 0.25) * smith_g_ggx(n_dot_v, 0.25)
+    # ((1/pi) * mix(..) * cd_lin + sheen) * (1 - metallic) + g * f * d + 0.25 * clearcoat * g_r * f_r * d_r, as written
+    diffuse = add(smul((1.0 / math.pi) * mix(fresnel_diffuse, subface_scatter, subsurface), cd_lin), fresnel_sheen)
+    spec = mul(smul(g_specular, f_specular), d_specular)
+    coat = mul(mul(mul(mul((0.25, 0.25, 0.25), clearcoat), g_reflect), f_reflect), d_reflect)
+    return add(add(mul(diffuse, 1.0 - metallic), spec), coat)
+
+
+def brdf_pdf_value(uvw, r_in_d, m, r_out):  # pdf.rs:103-129
+    roughness, anisotropic, clearcoat_gloss = m[5], m[7], m[11]
+    cosine = dot(normalized(r_out), uvw[2])
+    if cosine <= 0.0:
+        return 0.0
+    diffuse_pdf = cosine / math.pi
+    l = mul(normalized(r_in_d), -1.0)
+    v = normalized(r_out)
+    x, y, n = uvw
+    n_dot_l = dot(n, l)
+    h = normalized(add(l, v))
+    n_dot_h = dot(n, h)
+    if n_dot_h <= 0.0:
+        return 0.0
+    ax, ay = _aniso_alphas(roughness, anisotropic)
+    specular_pdf = fdiv(gtr_2_aniso(n_dot_h, dot(h, x), dot(h, y), ax, ay) * abs(n_dot_h) * 0.25, n_dot_l)
+    clearcoat_pdf = fdiv(gtr_1(n_dot_h, mix(0.1, 0.001, clearcoat_gloss)) * abs(n_dot_h) * 0.25, n_dot_l)
+    return (diffuse_pdf + specular_pdf + clearcoat_pdf) / 3.0
+
+
+def brdf_pdf_generate(uvw, r_in_d, m, selector, r1, r2):  # pdf.rs:152-161 over :20-63
+    roughness, anisotropic, clearcoat_gloss = m[5], m[7], m[11]
+    if selector < 0.333:
+        return onb_local(uvw, random_cosine_direction(r1, r2))
+    if selector < 0.666:  # GTR_1_direction
+        a = mix(0.1, 0.001, clearcoat_gloss)
+        a2 = a * a
+        cos_theta = math.sqrt(max(0.001, (1.0 - _powf(a2, 1.0 - r1)) / (1.0 - a2)))
+        sin_theta = math.sqrt(max(0.001, 1.0 - cos_theta * cos_theta))
+        phi = math.pi * 2.0 * r2
+        wh = (sin_theta * math.cos(phi), sin_theta * math.sin(phi), cos_theta)  # spherical_direction(.., sin_phi, cos_phi)
+        return onb_local(uvw, reflect(r_in_d, wh))
+    ax, ay = _aniso_alphas(roughness, anisotropic)  # GTR_2_aniso_direction
+    phi = math.atan(ay / ax * math.tan(2.0 * math.pi * r2 + 0.5 * math.pi))
+    if r2 > 0.5:
+        phi += math.pi
+    sin_phi, cos_phi = math.sin(phi), math.cos(phi)
+    ax_2, ay_2 = ax * ax, ay * ay
+    a2 = fdiv(1.0, cos_phi * cos_phi / ax_2 + sin_phi * sin_phi / ay_2)
+    tan_theta_2 = fdiv(a2 * r1, 1.0 - r1)
+    cos_theta = fdiv(1.0, fsqrt(1.0 + tan_theta_2))
+    sin_theta = math.sqrt(max(0.001, 1.0 - cos_theta * cos_theta))
+    wh = (sin_theta * math.cos(phi), sin_theta * math.sin(phi), cos_theta)
+    return onb_local(uvw, reflect(r_in_d, wh))
+
+
 def ray_color_general(ray, background, world, lights, depth, draws, max_depth):
     """main.rs:41-120 for every material of configs 1-3 and 5 (the Cornell-only ray_color above plus Dielectric,
     fuzzy Metal and textured Lambertian / DiffuseLight)."""
@@ -661,12 +838,22 @@ def ray_color_general(ray, background, world, lights, depth, draws, max_depth):
         scattering_pdf = max(dot(rec.normal, normalized(scattered.d)), 0.0) / math.pi
         nxt = ray_color_general(scattered, background, world, lights, depth - 1, draws, max_depth)
         return add(emitted, div(vmul(mul(material_texture(m, rec), scattering_pdf), nxt), pdf_value))
+    if kind == "pbr":  # ScatterRecord::Microfacet, main.rs:99-105 over mat.rs:119-132
+        uvw = onb_from_w(rec.normal)
+        a, b, bits_a, bits_b = draws.draw(bounce, SLOT_SCATTER, 0)
+        if bits_a & 1:
+            direction = lights.list[(bits_b * len(lights.list)) >> 11].random(rec.p, a, b)
+        else:
+            direction = brdf_pdf_generate(uvw, ray.d, m, draws.draw(bounce, SLOT_SCATTER, 1)[0], a, b)
+        scattered = Ray(rec.p, direction, ray.time)
+        pdf_value = 0.5 * lights.pdf_value(rec.p, direction) + 0.5 * brdf_pdf_value(uvw, ray.d, m, direction)
+        nxt = ray_color_general(scattered, background, world, lights, depth - 1, draws, max_depth)
+        return add(emitted, div(vmul(pbr_brdf(m, ray, scattered, rec), nxt), pdf_value))
     return emitted
 
 
 def scene_from_desc(abi, desc):
-    """The object graph of an RtSceneDesc (ctypes struct), in the classes of this file.  Unsupported here: the PBR material
-    and sphere lights (the five configs use neither)."""
+    """The object graph of an RtSceneDesc (ctypes struct), in the classes of this file."""
     def tex(i):
         t = desc.textures[i]
         if t.kind == abi.TEX_CONSTANT:
@@ -695,6 +882,9 @@ def scene_from_desc(abi, desc):
             return ("light", tex(m.texture))
         if m.kind == abi.MAT_ISOTROPIC:
             return ("isotropic", tex(m.texture))
+        if m.kind == abi.MAT_PBR:  # rtb200.h RT_PBR_*: metallic, subsurface, specular, roughness, specular_tint, anisotropic,
+            q = m.pbr              # sheen, sheen_tint, clearcoat, clearcoat_gloss
+            return ("pbr", tex(m.texture)) + tuple(q[k] for k in range(10))
         raise NotImplementedError("material kind %d" % m.kind)
 
     plane = {abi.PLANE_YZ: "YZ", abi.PLANE_XZ: "XZ", abi.PLANE_XY: "XY"}

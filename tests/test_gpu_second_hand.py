@@ -17,7 +17,8 @@ SEED = 7
 @pytest.mark.parametrize("name,legacy,n,depth", [("cornell", False, 600, 50), ("cornell_smoke", False, 600, 50),
                                                  ("random", True, 300, 50), ("mesh", False, 40, 12),
                                                  ("final", False, 150, 50), ("two_perlin_spheres", True, 300, 50),
-                                                 ("earth", True, 300, 50)])
+                                                 ("earth", True, 300, 50), ("cornell_pbr", False, 400, 50),
+                                                 ("progress_showcase", False, 300, 50)])
 def test_gpu_paths_match_the_second_restatement(rt, name, legacy, n, depth):
     hs = host_scene(rt, name)
     world, lights, background = sh.scene_from_desc(rt._abi, hs.scene_desc.struct)
@@ -30,7 +31,12 @@ def test_gpu_paths_match_the_second_restatement(rt, name, legacy, n, depth):
     want = np.array([sh.path_radiance_general(world, lights, background, cam, W, H, depth, SEED, int(i), int(j), int(k), legacy)
                      for i, j, k in zip(px, py, s)])
     finite = np.isfinite(want).all(axis=1) & np.isfinite(got).all(axis=1)
-    assert finite.mean() > 0.995
+    if name == "cornell_pbr":  # 0/0 at main.rs:104 (§Q10): the paths the reference turns into NaN are NaN here too
+        nan_w, nan_g = ~np.isfinite(want).all(axis=1), ~np.isfinite(got).all(axis=1)
+        print("non-finite paths: restatement %d, GPU %d, in common %d" % (nan_w.sum(), nan_g.sum(), (nan_w & nan_g).sum()))
+        assert nan_w.sum() > 0 and (nan_w == nan_g).mean() >= 0.995
+    else:
+        assert finite.mean() > 0.995
     err = np.abs(got[finite] - want[finite]) / np.maximum(np.abs(want[finite]), 1e-9)
     ok = (err.max(axis=1) <= 1e-4).mean()
     print("%s: %d paths, nonzero %d, within 1e-4: %.5f, median err %.2e, max err %.2e" % (
