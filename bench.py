@@ -50,8 +50,9 @@ WORKLOADS = {
 }
 # The other four configs of BASELINE.json, measured next to the headline: configs[0] and [2] at their full spp, the
 # two the scaling targets name ([3], [4]) at a bounded spp (throughput is linear in spp; image size, depth and scene
-# are the config's own).
-EXTRA_WORKLOADS = {"final": 2000, "mesh": 32, "cornell_smoke": 1000, "random": 800}
+# are the config's own).  The mesh scene's `e2e` contains one scene compile (~0.25 s for its 394 k triangles) per step:
+# at 128 of the config's 1024 spp that is a fifth of the step, at 32 spp (r2-b .. r2-p) it was half of it.
+EXTRA_WORKLOADS = {"final": 2000, "mesh": 128, "cornell_smoke": 1000, "random": 800}
 
 # f64 bytes a test has to read (the reference's own parameters), SURVEY §8(d) restated for f64:
 # AABB 6 doubles; sphere c+r; moving sphere c0,c1,t0,t1,r; rect a0,a1,b0,b1,k; triangle 3 vertices;
