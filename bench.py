@@ -44,6 +44,7 @@ WORKLOADS = {
     # name: description
     "cornell": "Cornell box (BASELINE configs[1]): 600x600, 1000 spp, depth 100, HEAD integrator",
     "cornell_smoke": "Cornell smoke (configs[2]): 600x600, 1000 spp",
+    "cornell_smoke_legacy": "Cornell smoke (configs[2]) under the legacy integrator (the smoke scatters: main.rs:82-84): 600x600, 1000 spp",
     "random": "RTiOW random spheres (configs[0]): 500x500, 800 spp, legacy integrator",
     "final": "Next Week final scene (configs[3]): 800x800, 10000 spp",
     "mesh": "Triangle-mesh scene (configs[4]): 3840x2160, 1024 spp (Venus stand-in + teapot)",
@@ -52,7 +53,9 @@ WORKLOADS = {
 # two the scaling targets name ([3], [4]) at a bounded spp (throughput is linear in spp; image size, depth and scene
 # are the config's own).  The mesh scene's `e2e` contains one scene compile (~0.25 s for its 394 k triangles) per step:
 # at 128 of the config's 1024 spp that is a fifth of the step, at 32 spp (r2-b .. r2-p) it was half of it.
-EXTRA_WORKLOADS = {"final": 2000, "mesh": 128, "cornell_smoke": 1000, "random": 800}
+EXTRA_WORKLOADS = {"final": 2000, "cornell_smoke": 1000, "cornell_smoke_legacy": 1000, "random": 800, "mesh": 128}
+# a workload that is a scene under another integrator than its own: name -> (scene, integrator)
+VARIANT_OF = {"cornell_smoke_legacy": ("cornell_smoke", 1)}  # "also report the legacy integrator"
 
 # f64 bytes a test has to read (the reference's own parameters), SURVEY §8(d) restated for f64:
 # AABB 6 doubles; sphere c+r; moving sphere c0,c1,t0,t1,r; rect a0,a1,b0,b1,k; triangle 3 vertices;
@@ -240,11 +243,13 @@ class Job:
         from raytracinginrust_b200.multi_gpu import sample_partition
         self.rt, self.torch, self.dist, self.name = rt, torch, dist, name
         self.rank, self.local_rank, self.world = rank, local_rank, world
-        self.hs = rt.HostScene(name)
+        scene_name, integrator = VARIANT_OF.get(name, (name, None))
+        self.hs = rt.HostScene(scene_name)
+        self.integrator = self.hs.integrator if integrator is None else integrator
         self.W, self.H, self.depth = self.hs.width, self.hs.height, self.hs.max_depth
         self.spp = spp or self.hs.spp
         self.begin, self.count = sample_partition(self.spp, rank, world)
-        self.opts = rt.render_opts(seed=1, integrator=self.hs.integrator, sample_begin=self.begin, sample_count=self.count)
+        self.opts = rt.render_opts(seed=1, integrator=self.integrator, sample_begin=self.begin, sample_count=self.count)
         self.out = torch.zeros((self.H, self.W, 3), dtype=torch.float32, device="cuda")
         self.stream = torch.cuda.current_stream()
 
@@ -415,13 +420,14 @@ def main():
             xd = xj.device_timed(3, 3, flush)
             xe = xj.e2e(3)
             info = dict(kv.split("=", 1) for kv in xd["info"].split() if "=" in kv) if isinstance(xd["info"], str) else xd["info"]
-            extras[name] = {"config": {"workload": WORKLOADS[name], "scene": name, "width": xj.W, "height": xj.H,
+            extras[name] = {"config": {"workload": WORKLOADS[name], "scene": VARIANT_OF.get(name, (name, None))[0],
+                                       "integrator": "HEAD" if xj.integrator == 0 else "LEGACY", "width": xj.W, "height": xj.H,
                                        "spp": xj.spp, "spp_of_config": xj.hs.spp, "max_depth": xj.depth,
                                        "pipeline": info.get("pipeline"), "variant": info.get("variant")},
                             "value": xd["value"], "unit": "Mpaths/s", "mrays_per_s": xd["mrays"],
                             "ms_per_step": xd["total_ms"] / xd["steps"], "steps": xd["steps"], "warmup": 3,
                             "e2e": xe, "gpu_launches": int(xd["launches"]), "checksum": xd["checksum"],
-                            "_kern_ms": xd["kern_ms"], "_rank_rays": xd["rank_rays"], "_job": (xj.W, xj.H, xj.depth, xj.hs.integrator)}
+                            "_kern_ms": xd["kern_ms"], "_rank_rays": xd["rank_rays"], "_job": (xj.W, xj.H, xj.depth, xj.integrator)}
             del xj
 
     # ---- the whole `cargo run --release > image.ppm` job at N=1: scene graph -> flatten -> compile/upload ->
@@ -514,8 +520,8 @@ def main():
         xk, xr = x.pop("_kern_ms"), x.pop("_rank_rays")
         xw, xh, xdepth, xint = x.pop("_job")
         if world == 1 and not args.no_cpu_baseline and xk:
-            small = {"final": 2, "mesh": 1, "cornell_smoke": 8, "random": 8}.get(name, 1)
-            r = cpu_oracle_run(name, xw, xh, small, xdepth, xint)
+            small = {"final": 2, "mesh": 1, "cornell_smoke": 8, "cornell_smoke_legacy": 4, "random": 8}.get(name, 1)
+            r = cpu_oracle_run(VARIANT_OF.get(name, (name, None))[0], xw, xh, small, xdepth, xint)
             _, _, xflops = algorithmic_work(r["counters"])
             x["roofline"] = fp64_roofline(xflops, xr / len(xk), sum(xk) / len(xk) * 1e-3, fp64_peak,
                                           kernel_names(x["config"]["pipeline"]))

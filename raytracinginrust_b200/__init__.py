@@ -35,6 +35,8 @@ _dev.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.POINTER(C.c_
 _dev.rt_scene_create_ex.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
 _dev.rt_scene_destroy.argtypes = [C.c_void_p]
 _dev.rt_scene_destroy.restype = None
+_dev.rt_release_cached_memory.argtypes = []
+_dev.rt_release_cached_memory.restype = None
 _dev.rt_scene_device_bytes.argtypes = [C.c_void_p]
 _dev.rt_scene_device_bytes.restype = C.c_uint64
 _dev.rt_render_info.argtypes = [C.c_void_p]
@@ -90,6 +92,11 @@ def _check(status):
 
 def device_count():
     return int(_dev.rt_device_count())
+
+
+def release_cached_memory():
+    """rt_release_cached_memory: return the device blocks parked by destroyed scenes to the driver."""
+    _dev.rt_release_cached_memory()
 
 
 def measure_fp64_peak(device=0):

@@ -97,7 +97,7 @@ HIT_DTYPE = [("node", "<i4"), ("face", "<i4"), ("material", "<i4"), ("front_face
              ("position", "<f8", 3), ("normal", "<f8", 3), ("u", "<f8"), ("v", "<f8")]
 
 # every symbol include/rtb200.h declares (checked by tests/test_abi.py)
-EXPORTS = ["rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_scene_device_bytes", "rt_render",
+EXPORTS = ["rt_device_count", "rt_scene_create", "rt_scene_destroy", "rt_release_cached_memory", "rt_scene_device_bytes", "rt_render",
            "rt_render_device", "rt_render_wait", "rt_trace_first_hit", "rt_path_radiance", "rt_camera_rays",
            "rt_measure_fp64_peak", "rt_render_info", "rt_last_error", "rt_version",
            "rt_scene_group_create", "rt_scene_group_destroy", "rt_scene_group_size", "rt_scene_group_scene",

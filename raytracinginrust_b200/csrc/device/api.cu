@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -43,10 +44,149 @@ double now_ms() {
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------
+// Device memory that outlives its scene.  A host that renders scene after scene (bench.py's end-to-end leg, an
+// animation) creates and destroys gigabytes per job: the f64 sample planes (1.1 GB for the Cornell box at 1000 spp,
+// up to 4 GiB), the wavefront pool (0.7 GB), the tables of a mesh.  cudaMalloc / cudaFree of such blocks cost the job
+// 5-30 ms of a 126 ms render, and occasionally hundreds (profiles/r1_h_whole_job_phases_cornell.txt; the smoke leg of
+// profiles/r2_u_bench.json after the mesh leg had freed 4 GiB; single calls of 0.6-1.1 s in profiles/r2_v_*).  Device
+// blocks are therefore parked here when their owner goes and handed to the next request of their size class, up to RTB200_SCRATCH_CACHE_MB (default 8192; 0 = off)
+// per process; rt_release_cached_memory() returns them to the driver.
+// ---------------------------------------------------------------------------
+namespace {
+struct ScratchCache {
+    struct Entry {
+        int device;
+        size_t bytes;
+        void *p;
+    };
+    std::mutex m;
+    std::vector<Entry> idle;
+    size_t held = 0;
+    static constexpr size_t kMinBytes = 256;
+    // what a request is rounded up to, so that blocks find new owners: powers of two below 1 MiB, multiples of 2 MiB above
+    static size_t size_class(size_t bytes) {
+        if (bytes <= kMinBytes) return kMinBytes;
+        if (bytes < (1u << 20)) {
+            size_t c = kMinBytes;
+            while (c < bytes) c <<= 1;
+            return c;
+        }
+        return (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+    }
+
+    static size_t cap() {
+        static const size_t c = [] {
+            long long mb = 8192;
+            if (const char *v = std::getenv("RTB200_SCRATCH_CACHE_MB")) mb = std::atoll(v);
+            return mb > 0 ? (size_t)mb << 20 : (size_t)0;
+        }();
+        return c;
+    }
+    // the smallest parked block of this device that holds `bytes` (a size class): of exactly that class below 1 MiB,
+    // without wasting more than half of itself above
+    void *take(int device, size_t bytes, size_t &capacity) {
+        std::lock_guard<std::mutex> lock(m);
+        const size_t most = bytes < (1u << 20) ? bytes : 2 * bytes + (64u << 20);
+        size_t best = idle.size();
+        for (size_t i = 0; i < idle.size(); ++i)
+            if (idle[i].device == device && idle[i].bytes >= bytes && idle[i].bytes <= most &&
+                (best == idle.size() || idle[i].bytes < idle[best].bytes))
+                best = i;
+        if (best == idle.size()) return nullptr;
+        void *p = idle[best].p;
+        capacity = idle[best].bytes;
+        held -= capacity;
+        idle.erase(idle.begin() + (long)best);
+        return p;
+    }
+    // false: not kept (too small, the cache is off or full) - the caller frees it
+    bool give(int device, void *p, size_t bytes) {
+        std::lock_guard<std::mutex> lock(m);
+        if (held + bytes > cap()) return false;
+        idle.push_back(Entry{device, bytes, p});
+        held += bytes;
+        return true;
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> lock(m);
+        int before = 0;
+        cudaGetDevice(&before);
+        for (const Entry &e : idle) {
+            cudaSetDevice(e.device);
+            cudaFree(e.p);
+        }
+        cudaSetDevice(before);
+        idle.clear();
+        held = 0;
+    }
+};
+ScratchCache g_scratch;
+
+// cudaMalloc through the cache; `capacity` is what scratch_free must be told
+cudaError_t scratch_alloc(int device, size_t bytes, void **p, size_t *capacity) {
+    bytes = ScratchCache::size_class(bytes);
+    size_t cap = bytes;
+    if (void *q = g_scratch.take(device, bytes, cap)) {
+        *p = q;
+        *capacity = cap;
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation && g_scratch.held) {  // the parked blocks are in the way: let them go and retry
+        cudaGetLastError();
+        g_scratch.release_all();
+        e = cudaMalloc(p, bytes);
+    }
+    *capacity = bytes;
+    return e;
+}
+// the caller has made sure that no work is in flight on the block (the scene's destructor synchronises the device)
+void scratch_free(int device, void *p, size_t capacity) {
+    if (!p) return;
+    if (!g_scratch.give(device, p, capacity)) cudaFree(p);
+}
+struct Block {
+    void *p;
+    size_t capacity;
+};
+
+// The same for the few small pinned host blocks of a scene (counters, wavefront status): cudaFreeHost synchronises.
+struct PinnedCache {
+    std::mutex m;
+    std::vector<void *> idle;  // blocks of kBytes
+    static constexpr size_t kBytes = 256;
+    cudaError_t alloc(void **p) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            if (!idle.empty()) {
+                *p = idle.back();
+                idle.pop_back();
+                return cudaSuccess;
+            }
+        }
+        return cudaMallocHost(p, kBytes);
+    }
+    void free(void *p) {
+        if (!p) return;
+        std::lock_guard<std::mutex> lock(m);
+        if (ScratchCache::cap() && idle.size() < 64) idle.push_back(p);
+        else cudaFreeHost(p);
+    }
+    void release_all() {
+        std::lock_guard<std::mutex> lock(m);
+        for (void *p : idle) cudaFreeHost(p);
+        idle.clear();
+    }
+};
+PinnedCache g_pinned;
+static_assert(sizeof(WfCtl) <= PinnedCache::kBytes && sizeof(unsigned long long) * kNumCounters <= PinnedCache::kBytes, "pinned block size");
+}  // namespace
+
 struct RtScene {
     int device = 0;
     DScene ds{};
-    std::vector<void *> allocations;
+    std::vector<Block> allocations;
     uint64_t device_bytes = 0;
     uint32_t n_lights = 0;
     cudaStream_t stream = nullptr;
@@ -56,15 +196,16 @@ struct RtScene {
     int render_variant = 0;    // bits 0-1: register budget of the megakernel, bit 2: media
     // scratch reused across render calls (the handle is thread-compatible, not thread-safe)
     double *planes = nullptr;
-    size_t planes_bytes = 0;
+    size_t planes_bytes = 0;     // what a render may use
+    size_t planes_capacity = 0;  // what the block holds (scratch_alloc)
     float *out_dev = nullptr;
-    size_t out_bytes = 0;
+    size_t out_bytes = 0, out_capacity = 0;
     uint32_t out_width = 0, out_height = 0;  // the image out_dev holds (rt_render / rt_render_multi), for rt_encode_*
     unsigned long long *counters = nullptr;
     unsigned long long *counters_host = nullptr;  // pinned
     // wavefront pipeline: path pool + queues, allocated on first use
     WfPool wf{};
-    std::vector<void *> wf_allocations;
+    std::vector<Block> wf_allocations;
     unsigned *wf_status_host = nullptr;  // pinned
     int sms = 148;
     bool has_media = false;
@@ -84,17 +225,18 @@ struct RtScene {
 
     ~RtScene() {
         cudaSetDevice(device);
-        for (void *p : allocations) cudaFree(p);
-        if (planes) cudaFree(planes);
-        if (out_dev) cudaFree(out_dev);
-        if (counters) cudaFree(counters);
-        if (counters_host) cudaFreeHost(counters_host);
+        cudaDeviceSynchronize();  // nothing of this scene is in flight when its blocks are parked (cudaFree used to imply it)
+        for (const Block &b : allocations) scratch_free(device, b.p, b.capacity);
+        if (planes) scratch_free(device, planes, planes_capacity);
+        if (out_dev) scratch_free(device, out_dev, out_capacity);
+        if (counters) scratch_free(device, counters, ScratchCache::size_class(sizeof(unsigned long long) * kNumCounters));
+        g_pinned.free(counters_host);
         if (wf_exec) cudaGraphExecDestroy(wf_exec);
         if (wf_graph) cudaGraphDestroy(wf_graph);
         if (wf_capture_stream) cudaStreamDestroy(wf_capture_stream);
-        if (wf_ctl_host) cudaFreeHost(wf_ctl_host);
-        for (void *p : wf_allocations) cudaFree(p);
-        if (wf_status_host) cudaFreeHost(wf_status_host);
+        g_pinned.free(wf_ctl_host);
+        for (const Block &b : wf_allocations) scratch_free(device, b.p, b.capacity);
+        g_pinned.free(wf_status_host);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -105,10 +247,10 @@ namespace {
 
 template <class T>
 RtStatus upload(RtScene &s, const std::vector<T> &v, const T *&dev) {
-    size_t bytes = v.size() * sizeof(T);
+    size_t bytes = v.size() * sizeof(T), capacity = 0;
     void *p = nullptr;
-    CU(cudaMalloc(&p, bytes ? bytes : 16));
-    s.allocations.push_back(p);
+    CU(scratch_alloc(s.device, bytes, &p, &capacity));
+    s.allocations.push_back(Block{p, capacity});
     if (bytes) CU(cudaMemcpy(p, v.data(), bytes, cudaMemcpyHostToDevice));
     s.device_bytes += bytes;
     dev = (const T *)p;
@@ -241,19 +383,19 @@ const PipelineVariant *pick_variant(const RtScene &s, uint32_t integrator) {
 
 RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
     size_t plane_bytes = (size_t)P.n_chunks * P.width * P.height * 3 * sizeof(double);
-    if (plane_bytes > s.planes_bytes) {
-        if (s.planes) cudaFree(s.planes);
+    if (plane_bytes > s.planes_capacity) {
+        if (s.planes) scratch_free(s.device, s.planes, s.planes_capacity);  // (no render of this scene is pending here)
         s.planes = nullptr;
-        s.planes_bytes = 0;
-        CU(cudaMalloc((void **)&s.planes, plane_bytes));
-        s.planes_bytes = plane_bytes;
+        s.planes_bytes = s.planes_capacity = 0;
+        CU(scratch_alloc(s.device, plane_bytes, (void **)&s.planes, &s.planes_capacity));
     }
+    s.planes_bytes = plane_bytes;
     size_t out_bytes = (size_t)P.width * P.height * 3 * sizeof(float);
     if (need_out && out_bytes > s.out_bytes) {
-        if (s.out_dev) cudaFree(s.out_dev);
+        if (s.out_dev) scratch_free(s.device, s.out_dev, s.out_capacity);
         s.out_dev = nullptr;
-        s.out_bytes = 0;
-        CU(cudaMalloc((void **)&s.out_dev, out_bytes));
+        s.out_bytes = s.out_capacity = 0;
+        CU(scratch_alloc(s.device, out_bytes, (void **)&s.out_dev, &s.out_capacity));
         s.out_bytes = out_bytes;
     }
     return RT_OK;
@@ -262,8 +404,9 @@ RtStatus ensure_scratch(RtScene &s, const RenderParams &P, bool need_out) {
 template <class T>
 RtStatus wf_alloc(RtScene &s, T *&ptr, size_t count) {
     void *p = nullptr;
-    CU(cudaMalloc(&p, count * sizeof(T)));
-    s.wf_allocations.push_back(p);
+    size_t capacity = 0;
+    CU(scratch_alloc(s.device, count * sizeof(T), &p, &capacity));
+    s.wf_allocations.push_back(Block{p, capacity});
     ptr = (T *)p;
     return RT_OK;
 }
@@ -271,7 +414,7 @@ RtStatus wf_alloc(RtScene &s, T *&ptr, size_t count) {
 RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
     const uint32_t cap = wf_pool_capacity();
     if (s.wf.capacity != cap) {
-        for (void *p : s.wf_allocations) cudaFree(p);
+        for (const Block &b : s.wf_allocations) scratch_free(s.device, b.p, b.capacity);
         s.wf_allocations.clear();
         s.wf = WfPool{};
         WfPool w{};
@@ -284,8 +427,8 @@ RtStatus ensure_wavefront_pool(RtScene &s, const RenderParams &P) {
 #undef WA
         w.capacity = cap;
         s.wf = w;
-        if (!s.wf_status_host) CU(cudaMallocHost((void **)&s.wf_status_host, sizeof(unsigned)));
-        if (!s.wf_ctl_host) CU(cudaMallocHost((void **)&s.wf_ctl_host, sizeof(WfCtl)));
+        if (!s.wf_status_host) CU(g_pinned.alloc((void **)&s.wf_status_host));
+        if (!s.wf_ctl_host) CU(g_pinned.alloc((void **)&s.wf_ctl_host));
     }
     // never more slots than there are work items
     uint64_t items = (uint64_t)P.width * P.height * P.n_chunks;
@@ -507,8 +650,11 @@ RtStatus create_on_device(const CompiledScene &cs, int device, RtScene **out_sce
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&s->ev0));
     CU(cudaEventCreate(&s->ev1));
-    CU(cudaMalloc((void **)&s->counters, sizeof(unsigned long long) * kNumCounters));
-    CU(cudaMallocHost((void **)&s->counters_host, sizeof(unsigned long long) * kNumCounters));
+    {
+        size_t cap = 0;
+        CU(scratch_alloc(device, sizeof(unsigned long long) * kNumCounters, (void **)&s->counters, &cap));
+    }
+    CU(g_pinned.alloc((void **)&s->counters_host));
     // register budget of the megakernel (megakernel.inl: 0 = 6 blocks/SM, 1 = 8, 2 = 12) + media bit
     s->features = scene_features(cs);
     {
@@ -575,6 +721,11 @@ RtStatus rt_scene_create(const RtSceneDesc *desc, int device, RtScene **out_scen
 }
 
 void rt_scene_destroy(RtScene *scene) { delete scene; }
+
+void rt_release_cached_memory(void) {
+    g_scratch.release_all();
+    g_pinned.release_all();
+}
 
 // ---------------------------------------------------------------------------
 // Compile once, create many: CompiledScene <-> a relocatable blob
@@ -1050,11 +1201,13 @@ RtStatus rt_encode_rgb8(const RtScene *scene, const float *rgb_sum_device, uint3
     CU(cudaSetDevice(s.device));
     const uint64_t n_values = (uint64_t)width * height * 3;
     uint8_t *d = nullptr;
-    CU(cudaMalloc((void **)&d, n_values + 16));
+    size_t d_cap = 0;
+    CU(scratch_alloc(s.device, n_values + 16, (void **)&d, &d_cap));
     cudaError_t e = launch_format_rgb8(src, d, n_values, (double)samples_per_pixel, s.sms, s.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgb8, d, n_values, cudaMemcpyDeviceToHost, s.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-    cudaFree(d);
+    if (e != cudaSuccess) cudaStreamSynchronize(s.stream);
+    scratch_free(s.device, d, d_cap);
     if (e != cudaSuccess) return cuda_fail(e, "rt_encode_rgb8");
     return RT_OK;
 }
@@ -1078,7 +1231,8 @@ RtStatus rt_encode_ppm(const RtScene *scene, const float *rgb_sum_device, uint32
     const size_t off_bytes = (size_t)(((uint64_t)nb * 8 + 255) & ~255ull);
     const size_t len_bytes = (size_t)(((uint64_t)nb * 4 + 255) & ~255ull);
     char *d = nullptr;
-    CU(cudaMalloc((void **)&d, body_bytes + packed_bytes + off_bytes + 256 + len_bytes));
+    size_t d_cap = 0;
+    CU(scratch_alloc(s.device, body_bytes + packed_bytes + off_bytes + 256 + len_bytes, (void **)&d, &d_cap));
     char *body = d;
     uint32_t *packed = (uint32_t *)(d + body_bytes);
     uint64_t *block_off = (uint64_t *)(d + body_bytes + packed_bytes);
@@ -1089,14 +1243,15 @@ RtStatus rt_encode_ppm(const RtScene *scene, const float *rgb_sum_device, uint32
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, total_dev, sizeof(total), cudaMemcpyDeviceToHost, s.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
     if (e == cudaSuccess && (uint64_t)hl + total > capacity) {
-        cudaFree(d);
+        scratch_free(s.device, d, d_cap);
         *length = (uint64_t)hl + total;  // what it would have taken
         return fail(RT_ERR_BAD_ARGUMENT, "output buffer too small for the PPM (32 + 12*W*H always suffices)");
     }
     if (e == cudaSuccess) e = launch_ppm_write(packed, block_off, body, n_pixels, s.stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(out + hl, body, total, cudaMemcpyDeviceToHost, s.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
-    cudaFree(d);
+    if (e != cudaSuccess) cudaStreamSynchronize(s.stream);
+    scratch_free(s.device, d, d_cap);
     if (e != cudaSuccess) return cuda_fail(e, "rt_encode_ppm");
     std::memcpy(out, header, (size_t)hl);
     *length = (uint64_t)hl + total;

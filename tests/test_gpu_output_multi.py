@@ -208,3 +208,32 @@ def test_scene_from_compiled_blob_renders_the_same_image(rt, name):
     assert a.render_info == b.render_info
     a.close()
     b.close()
+
+
+def test_device_blocks_are_recycled_between_scenes(rt):
+    """The sample planes, the wavefront pool and the tables of a destroyed scene are parked and handed to the next scene
+    (api.cu ScratchCache): a render in a recycled block - whatever the previous scene left in it - gives the same image,
+    for the megakernel and the wavefront pipeline, and rt_release_cached_memory returns the blocks to the driver."""
+    import torch
+
+    def image(name, w, h, spp):
+        hs = host_scene(rt, name)
+        dev = rt.DeviceScene(hs.scene_desc, device=0)
+        img, st = dev.render(hs.camera, w, h, spp, 50, rt.render_opts(seed=4, integrator=hs.integrator))
+        assert st.paths == w * h * spp
+        dev.close()
+        return img
+
+    rt.release_cached_memory()
+    first = {n: image(n, 256, 192, 24) for n in ("cornell", "final", "mesh")}
+    image("cornell_smoke", 320, 320, 16)   # another scene with other sizes scribbles over what it is given
+    for n, want in first.items():
+        assert np.array_equal(image(n, 256, 192, 24), want), n
+    torch.cuda.synchronize()
+    before = torch.cuda.mem_get_info()[0]
+    rt.release_cached_memory()
+    parked = torch.cuda.mem_get_info()[0] - before
+    print("parked blocks returned to the driver: %.1f MB" % (parked / 1e6))
+    assert parked >= 64 << 20              # the planes and the wavefront pool of the scenes above were parked
+    assert np.array_equal(image("cornell", 256, 192, 24), first["cornell"])
+    rt.release_cached_memory()
