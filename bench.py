@@ -230,7 +230,7 @@ def run_reference(args, rank):
         "note": "CPU f64 restatement of the reference (oracle/oracle.cpp); cargo/rustc are absent so `cargo run --release` "
                 "cannot be timed; this process holds librtb200_scenes.so and the oracle only (no CUDA library)",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -363,7 +363,31 @@ def kernel_names(pipeline):
     return "render_kernel" if pipeline == "megakernel" else "wf_extend_kernel + wf_shade_kernel + wf_generate_kernel"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries ONE line, the JSON.  Everything else a library writes to file descriptor 1 while the bench runs -
+    NCCL's version banner under torchrun at 8 GPUs, whatever NCCL_DEBUG_FILE says - goes to stderr: fd 1 is pointed at
+    fd 2 for the run and the JSON line is written to the descriptor stdout had."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -546,7 +570,7 @@ def main():
         "workloads": extras,
         "algorithmic_tests_per_segment": per_seg, "checksum": dev["checksum"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -213,8 +213,10 @@ struct Builder {
     std::atomic<int> next{0};
     std::atomic<uint32_t> max_depth{0};
     std::vector<double> cx[3];
+    size_t n_threads;  // (asked once: hardware_concurrency is a system call)
 
     Builder(const std::vector<Box> &b, std::vector<uint32_t> &o) : boxes(b), order(o) {
+        n_threads = std::getenv("RTB200_COMPILE_SERIAL") ? 1 : std::min<size_t>(std::thread::hardware_concurrency(), kMaxPieces);
         for (int a = 0; a < 3; ++a) cx[a].resize(b.size());
         parallel_for(b.size(), [&](size_t i0, size_t i1) {
             for (int a = 0; a < 3; ++a)
@@ -222,18 +224,74 @@ struct Builder {
         });
     }
 
-    // The two halves of a node own disjoint ranges of order[] and disjoint node ids, so large
-    // subtrees are built in parallel (the tree does not depend on the schedule).
-    int build(uint32_t first, uint32_t count, uint32_t depth) {
-        int id = next.fetch_add(1);
-        Box box, cbox;
+    struct Bins {
+        Box bb[3][N_BINS];
+        uint32_t bn[3][N_BINS];
+        void reset() {
+            for (int ax = 0; ax < 3; ++ax)
+                for (int k = 0; k < N_BINS; ++k) {
+                    bb[ax][k].reset();
+                    bn[ax][k] = 0;
+                }
+        }
+    };
+    static constexpr uint32_t kBigNode = 65536;  // nodes of this many primitives bin with all host threads
+    static constexpr int kMaxPieces = 16;
+
+    // f(piece, i0, i1) over contiguous pieces of [first, first + count): threads for a big node, one piece otherwise.
+    // What the pieces compute is merged with min / max / integer sums only, so the result never depends on the split.
+    template <class F>
+    int pieces(uint32_t first, uint32_t count, F f) const {
+        size_t threads = n_threads;
+        if (count < kBigNode || threads < 2) {
+            f(0, (size_t)first, (size_t)first + count);
+            return 1;
+        }
+        const size_t per = (count + threads - 1) / threads;
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < threads; ++t) {
+            const size_t a = first + t * per, b = std::min((size_t)first + count, a + per);
+            pool.emplace_back([=, &f] { f((int)t, a, std::max(a, b)); });
+        }
+        f(0, (size_t)first, std::min((size_t)first + count, (size_t)first + per));
+        for (std::thread &th : pool) th.join();
+        return (int)threads;
+    }
+
+    // bounds of the primitives and of their centroids over a range of order[]
+    void bounds(uint32_t first, uint32_t count, Box &box, Box &cbox) const {
+        Box pb[kMaxPieces], pc[kMaxPieces];
+        const int n = pieces(first, count, [&](int k, size_t i0, size_t i1) {
+            Box b, c;
+            b.reset();
+            c.reset();
+            for (size_t i = i0; i < i1; ++i) {
+                b.grow(boxes[order[i]]);
+                double cc[3] = {cx[0][order[i]], cx[1][order[i]], cx[2][order[i]]};
+                c.grow(cc);
+            }
+            pb[k] = b;
+            pc[k] = c;
+        });
         box.reset();
         cbox.reset();
-        for (uint32_t i = first; i < first + count; ++i) {
-            box.grow(boxes[order[i]]);
-            double c[3] = {cx[0][order[i]], cx[1][order[i]], cx[2][order[i]]};
-            cbox.grow(c);
+        for (int k = 0; k < n; ++k) {
+            box.grow(pb[k]);
+            cbox.grow(pc[k]);
         }
+    }
+
+    int build(uint32_t first, uint32_t count, uint32_t depth) {
+        Box box, cbox;
+        bounds(first, count, box, cbox);
+        return build_node(first, count, depth, box, cbox);
+    }
+
+    // The two halves of a node own disjoint ranges of order[] and disjoint node ids, so large
+    // subtrees are built in parallel (the tree does not depend on the schedule).  A node gets its bounds from the
+    // pass that partitioned its parent (the predicate sees every primitive exactly once and knows its side).
+    int build_node(uint32_t first, uint32_t count, uint32_t depth, const Box &box, const Box &cbox) {
+        int id = next.fetch_add(1);
         nodes[id].box = box;
         for (uint32_t seen = max_depth.load(); seen < depth && !max_depth.compare_exchange_weak(seen, depth);) {
         }
@@ -248,31 +306,38 @@ struct Builder {
         if (ext[2] > ext[axis]) axis = 2;
         uint32_t mid = first + count / 2;
         bool done = false;
+        Box side_box[2], side_cbox[2];
         if ((int)depth < FORCE_MEDIAN_DEPTH && ext[axis] > 0.0) {
             // binned SAH over all three axes; one pass over the primitives fills the bins of every axis
             double best_cost = DBL_MAX;
             int best_axis = -1, best_bin = -1;
-            Box bb[3][N_BINS];
-            uint32_t bn[3][N_BINS];
             double scale3[3];
-            for (int ax = 0; ax < 3; ++ax) {
-                scale3[ax] = ext[ax] > 0.0 ? (double)N_BINS / ext[ax] : 0.0;
-                for (int k = 0; k < N_BINS; ++k) {
-                    bb[ax][k].reset();
-                    bn[ax][k] = 0;
+            for (int ax = 0; ax < 3; ++ax) scale3[ax] = ext[ax] > 0.0 ? (double)N_BINS / ext[ax] : 0.0;
+            Bins one;
+            std::unique_ptr<Bins[]> many(count >= kBigNode && n_threads > 1 ? new Bins[kMaxPieces] : nullptr);
+            Bins *part = many ? many.get() : &one;
+            const int n_parts = pieces(first, count, [&](int k, size_t i0, size_t i1) {
+                Bins &B = part[k];
+                B.reset();
+                for (size_t i = i0; i < i1; ++i) {
+                    const uint32_t p = order[i];
+                    const Box &pb = boxes[p];
+                    for (int ax = 0; ax < 3; ++ax) {
+                        if (!(ext[ax] > 0.0)) continue;
+                        int b = (int)((cx[ax][p] - cbox.lo[ax]) * scale3[ax]);
+                        b = std::min(std::max(b, 0), N_BINS - 1);
+                        B.bb[ax][b].grow(pb);
+                        B.bn[ax][b]++;
+                    }
                 }
-            }
-            for (uint32_t i = first; i < first + count; ++i) {
-                const uint32_t p = order[i];
-                const Box &pb = boxes[p];
-                for (int ax = 0; ax < 3; ++ax) {
-                    if (!(ext[ax] > 0.0)) continue;
-                    int k = (int)((cx[ax][p] - cbox.lo[ax]) * scale3[ax]);
-                    k = std::min(std::max(k, 0), N_BINS - 1);
-                    bb[ax][k].grow(pb);
-                    bn[ax][k]++;
-                }
-            }
+            });
+            Bins &B = part[0];
+            for (int k = 1; k < n_parts; ++k)
+                for (int ax = 0; ax < 3; ++ax)
+                    for (int b = 0; b < N_BINS; ++b) {
+                        if (part[k].bn[ax][b]) B.bb[ax][b].grow(part[k].bb[ax][b]);
+                        B.bn[ax][b] += part[k].bn[ax][b];
+                    }
             for (int ax = 0; ax < 3; ++ax) {
                 if (!(ext[ax] > 0.0)) continue;
                 double right_area[N_BINS];
@@ -281,16 +346,16 @@ struct Builder {
                 acc.reset();
                 uint32_t n = 0;
                 for (int k = N_BINS - 1; k > 0; --k) {
-                    if (bn[ax][k]) acc.grow(bb[ax][k]);
-                    n += bn[ax][k];
+                    if (B.bn[ax][k]) acc.grow(B.bb[ax][k]);
+                    n += B.bn[ax][k];
                     right_area[k] = n ? acc.area() : 0.0;
                     right_n[k] = n;
                 }
                 acc.reset();
                 n = 0;
                 for (int k = 0; k < N_BINS - 1; ++k) {
-                    if (bn[ax][k]) acc.grow(bb[ax][k]);
-                    n += bn[ax][k];
+                    if (B.bn[ax][k]) acc.grow(B.bb[ax][k]);
+                    n += B.bn[ax][k];
                     if (n == 0 || right_n[k + 1] == 0) continue;
                     double cost = acc.area() * (double)n + right_area[k + 1] * (double)right_n[k + 1];
                     if (cost < best_cost) {
@@ -303,10 +368,18 @@ struct Builder {
             if (best_axis >= 0) {
                 double scale = (double)N_BINS / ext[best_axis];
                 double lo = cbox.lo[best_axis];
+                for (int sd = 0; sd < 2; ++sd) {
+                    side_box[sd].reset();
+                    side_cbox[sd].reset();
+                }
                 auto it = std::partition(order.begin() + first, order.begin() + first + count, [&](uint32_t p) {
                     int k = (int)((cx[best_axis][p] - lo) * scale);
                     k = std::min(std::max(k, 0), N_BINS - 1);
-                    return k <= best_bin;
+                    const int sd = k <= best_bin ? 0 : 1;  // std::partition applies the predicate exactly once per element
+                    side_box[sd].grow(boxes[p]);
+                    double cc[3] = {cx[0][p], cx[1][p], cx[2][p]};
+                    side_cbox[sd].grow(cc);
+                    return sd == 0;
                 });
                 mid = (uint32_t)(it - order.begin());
                 done = mid > first && mid < first + count;
@@ -316,15 +389,17 @@ struct Builder {
             mid = first + count / 2;
             std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count,
                              [&](uint32_t a, uint32_t b) { return cx[axis][a] < cx[axis][b]; });
+            bounds(first, mid - first, side_box[0], side_cbox[0]);
+            bounds(mid, first + count - mid, side_box[1], side_cbox[1]);
         }
         int l, r;
         if (count >= 32768 && depth <= 6) {
-            auto left = std::async(std::launch::async, [&] { return build(first, mid - first, depth + 1); });
-            r = build(mid, first + count - mid, depth + 1);
+            auto left = std::async(std::launch::async, [&] { return build_node(first, mid - first, depth + 1, side_box[0], side_cbox[0]); });
+            r = build_node(mid, first + count - mid, depth + 1, side_box[1], side_cbox[1]);
             l = left.get();
         } else {
-            l = build(first, mid - first, depth + 1);
-            r = build(mid, first + count - mid, depth + 1);
+            l = build_node(first, mid - first, depth + 1, side_box[0], side_cbox[0]);
+            r = build_node(mid, first + count - mid, depth + 1, side_box[1], side_cbox[1]);
         }
         nodes[id].left = l;
         nodes[id].right = r;
