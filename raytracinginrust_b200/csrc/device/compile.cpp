@@ -200,16 +200,16 @@ void point_to_outer(const std::vector<DOp> &ops, double p[3]) {
 // ---------------------------------------------------------------------------
 // Binned SAH BVH2
 // ---------------------------------------------------------------------------
-struct TNode {
+struct TNode {  // (no default initialisers: the builder sizes its array for 2 n nodes and writes the ones it hands out)
     Box box;
-    int left = -1, right = -1;  // inner
-    uint32_t first = 0, count = 0;  // leaf (into the order[] permutation)
+    int left, right;        // inner; -1, -1 for a leaf
+    uint32_t first, count;  // leaf (into the order[] permutation)
 };
 
 struct Builder {
     const std::vector<Box> &boxes;
     std::vector<uint32_t> &order;
-    std::vector<TNode> nodes;  // pre-sized to 2 * count; ids are handed out by `next`
+    std::unique_ptr<TNode[]> nodes;  // 2 * count of them, not initialised; ids are handed out by `next`
     std::atomic<int> next{0};
     std::atomic<uint32_t> max_depth{0};
     std::vector<double> cx[3];
@@ -237,6 +237,7 @@ struct Builder {
     };
     static constexpr uint32_t kBigNode = 65536;  // nodes of this many primitives bin with all host threads
     static constexpr int kMaxPieces = 16;
+    static constexpr uint32_t kTaskMin = 4096;
 
     // f(piece, i0, i1) over contiguous pieces of [first, first + count): threads for a big node, one piece otherwise.
     // What the pieces compute is merged with min / max / integer sums only, so the result never depends on the split.
@@ -293,6 +294,8 @@ struct Builder {
     int build_node(uint32_t first, uint32_t count, uint32_t depth, const Box &box, const Box &cbox) {
         int id = next.fetch_add(1);
         nodes[id].box = box;
+        nodes[id].left = nodes[id].right = -1;
+        nodes[id].first = nodes[id].count = 0;
         for (uint32_t seen = max_depth.load(); seen < depth && !max_depth.compare_exchange_weak(seen, depth);) {
         }
         if (count <= LEAF_MAX) {
@@ -393,7 +396,9 @@ struct Builder {
             bounds(mid, first + count - mid, side_box[1], side_cbox[1]);
         }
         int l, r;
-        if (count >= 32768 && depth <= 6) {
+        // a thread per left subtree down to kTaskMin primitives (a few hundred tasks for a mesh of 400 k triangles: with
+        // 32768 and at most 64 tasks the 24 threads of the GPU box waited for the largest of ~20 subtrees)
+        if (mid - first >= kTaskMin && first + count - mid >= kTaskMin && n_threads > 1) {
             auto left = std::async(std::launch::async, [&] { return build_node(first, mid - first, depth + 1, side_box[0], side_cbox[0]); });
             r = build_node(mid, first + count - mid, depth + 1, side_box[1], side_cbox[1]);
             l = left.get();
@@ -435,11 +440,11 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     });
     lap("boxes");
     Builder b(boxes, order);
-    b.nodes.resize(2 * (size_t)count);
+    b.nodes.reset(new TNode[2 * (size_t)count + 1]);
     lap("builder init");
     int root = b.build(0, count, 1);
     lap("build");
-    b.nodes.resize((size_t)b.next.load());
+    const size_t n_tnodes = (size_t)b.next.load();
     out.max_bvh_depth = std::max(out.max_bvh_depth, b.max_depth.load());
     // permute the primitives into leaf order
     {
@@ -453,7 +458,7 @@ int32_t build_group_bvh(CompiledScene &out, uint32_t first, uint32_t count) {
     // breadth-first emission of the inner nodes
     uint32_t base = (uint32_t)out.nodes.size();
     std::vector<int> bfs;  // temp-node ids of inner nodes in BFS order
-    std::vector<int32_t> slot(b.nodes.size(), -1);
+    std::vector<int32_t> slot(n_tnodes, -1);
     bfs.push_back(root);
     slot[root] = 0;
     for (size_t h = 0; h < bfs.size(); ++h) {
