@@ -77,12 +77,10 @@ static cudaError_t with_render_kernel(int variant, F f) {
     switch (variant & 7) {
         case 0: return f(render_kernel<6, false>, kRenderBlock);
         case 1: return f(render_kernel<8, false>, kRenderBlock);
-        case 2: return f(render_kernel<12, false>, kRenderBlock);
-        case 3: return f(render_kernel<10, false>, kRenderBlock);
+        case 2: case 3: return f(render_kernel<12, false>, kRenderBlock);
         case 4: return f(render_kernel<6, true>, kRenderBlock);
         case 5: return f(render_kernel<8, true>, kRenderBlock);
-        case 6: return f(render_kernel<12, true>, kRenderBlock);
-        default: return f(render_kernel<10, true>, kRenderBlock);
+        default: return f(render_kernel<12, true>, kRenderBlock);
     }
 }
 static cudaError_t render_grid_size(int device, int variant, int *blocks_out) {
