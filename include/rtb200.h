@@ -259,7 +259,7 @@ void rt_scene_destroy(RtScene *scene);
 /* Device blocks (sample planes, the wavefront pool, the tables, the scratch of rt_encode_*) and the
  * few pinned host blocks of a scene are not returned to the driver when their owner is destroyed but
  * parked for the next request of the same device and size class, up to RTB200_SCRATCH_CACHE_MB
- * (default 8192, 0 = off) per process: a host that renders scene after scene pays cudaMalloc /
+ * (default 24576, 0 = off) per process: a host that renders scene after scene pays cudaMalloc /
  * cudaFree once.  This returns the parked blocks to the driver. */
 void rt_release_cached_memory(void);
 

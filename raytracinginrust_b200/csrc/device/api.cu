@@ -50,7 +50,8 @@ double now_ms() {
 // up to 4 GiB), the wavefront pool (0.7 GB), the tables of a mesh.  cudaMalloc / cudaFree of such blocks cost the job
 // 5-30 ms of a 126 ms render, and occasionally hundreds (profiles/r1_h_whole_job_phases_cornell.txt; the smoke leg of
 // profiles/r2_u_bench.json after the mesh leg had freed 4 GiB; single calls of 0.6-1.1 s in profiles/r2_v_*).  Device
-// blocks are therefore parked here when their owner goes and handed to the next request of their size class, up to RTB200_SCRATCH_CACHE_MB (default 8192; 0 = off)
+// blocks are therefore parked here when their owner goes and handed to the next request of their size class, up to
+// RTB200_SCRATCH_CACHE_MB (default 24576 - the planes of the Next Week final scene at 2000 spp are 15 GB; 0 = off)
 // per process; rt_release_cached_memory() returns them to the driver.
 // ---------------------------------------------------------------------------
 namespace {
@@ -77,7 +78,7 @@ struct ScratchCache {
 
     static size_t cap() {
         static const size_t c = [] {
-            long long mb = 8192;
+            long long mb = 24576;
             if (const char *v = std::getenv("RTB200_SCRATCH_CACHE_MB")) mb = std::atoll(v);
             return mb > 0 ? (size_t)mb << 20 : (size_t)0;
         }();
@@ -311,18 +312,25 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     P.tiles_y = (height + 3) / 4;
     P.items_per_chunk = (uint64_t)P.tiles_x * P.tiles_y * 32ull;
     // Work items are (chunk of consecutive samples, pixel).  Small items keep the end of a render short: the last item
-    // of every lane / pool slot is run to its end while the others idle (measured on the wavefront pipeline, final
-    // scene at 2048 spp: 20 samples per item 1114 ms, 8 per item 1063 ms); items that are too small hammer the one
-    // work counter (an atomic per item) and multiply the f64 planes.  So: about 8 samples per item, but at least 2^23
-    // items when the image is small or the render short, and never more planes than 4 GiB / 1024 (16 GiB of planes
-    // bought the final scene at 10000 spp another 3 % of device time and cost as much again in cudaMalloc).
-    // The partition depends only on the image and the sample range, not on the pipeline or the GPU, so the f64
-    // summation order - and with it every bit of the image - is the same whichever way it is rendered.
-    const uint64_t kSamplesPerItem = 8, kMinItems = 1ull << 23;
+    // of every lane / pool slot is run to its end while the others idle; items that are too small hammer the one work
+    // counter (an atomic per item) and multiply the f64 planes.  How many samples an item should hold depends on the
+    // scene (r2-ac / r2-ad, profiles/r2_ad_samples_per_item.md):
+    //  * flat scenes (no tree: the Cornell boxes) gain nothing from lanes that restart together and pay the item fetch
+    //    at 2 active lanes: 32 samples per item (Cornell x1000 117.1 -> 113.9 ms, smoke 137.6 -> 135.2);
+    //  * trees over spheres and boxes (RTiOW, the Next Week final scene): lanes / slots that ask for work together get
+    //    neighbouring pixels, so short items keep a warp's rays together in the tree - 2 samples per item (RTiOW x800
+    //    208.0 -> 191.7 ms, final x512 271.9 -> 249.4); this is where the planes grow, so the budget is 16 GiB there;
+    //  * triangle meshes: 8 as before (1 .. 16 samples per item: 489.6 .. 498 ms at 64 spp, the 4K planes are 199 MB each).
+    // At least 2^23 items when the image is small or the render short, and never more planes than the budget.
+    // The partition depends only on the scene, the image and the sample range, not on the pipeline or the GPU, so the
+    // f64 summation order - and with it every bit of the image - is the same whichever way it is rendered.
+    const bool tree = (s.features & F_BVH) != 0u, tris = (s.features & F_TRI) != 0u;
+    const uint64_t kSamplesPerItem = !tree ? 32 : (tris ? 8 : 2), kMinItems = 1ull << 23;
+    const uint64_t plane_budget = (tree && !tris) ? (16ull << 30) : (4ull << 30);
     uint64_t chunks = (count + kSamplesPerItem - 1) / kSamplesPerItem;
     const uint64_t for_balance = (kMinItems + P.items_per_chunk - 1) / P.items_per_chunk;
     if (chunks < for_balance) chunks = for_balance;
-    uint64_t plane_cap = (4ull << 30) / ((uint64_t)width * height * 3 * sizeof(double));
+    uint64_t plane_cap = plane_budget / ((uint64_t)width * height * 3 * sizeof(double));
     if (plane_cap < 1) plane_cap = 1;
     if (chunks > plane_cap) chunks = plane_cap;
     if (chunks > 1024) chunks = 1024;
