@@ -318,14 +318,15 @@ RtStatus make_params(const RtScene &s, uint32_t width, uint32_t height, uint32_t
     //  * flat scenes (no tree: the Cornell boxes) gain nothing from lanes that restart together and pay the item fetch
     //    at 2 active lanes: 32 samples per item (Cornell x1000 117.1 -> 113.9 ms, smoke 137.6 -> 135.2);
     //  * trees over spheres and boxes (RTiOW, the Next Week final scene): lanes / slots that ask for work together get
-    //    neighbouring pixels, so short items keep a warp's rays together in the tree - 2 samples per item (RTiOW x800
-    //    208.0 -> 191.7 ms, final x512 271.9 -> 249.4); this is where the planes grow, so the budget is 16 GiB there;
+    //    neighbouring pixels, so short items keep a warp's rays together in the tree - ONE sample per item where the
+    //    planes allow it (RTiOW x800 208.0 -> 191.7 ms at 2 or 1 per item, x100 - what one of eight GPUs renders - 24.9 ->
+    //    22.8 ms at 1; final x512 271.9 -> 249.4 at 2); this is where the planes grow, so the budget is 16 GiB there;
     //  * triangle meshes: 8 as before (1 .. 16 samples per item: 489.6 .. 498 ms at 64 spp, the 4K planes are 199 MB each).
     // At least 2^23 items when the image is small or the render short, and never more planes than the budget.
     // The partition depends only on the scene, the image and the sample range, not on the pipeline or the GPU, so the
     // f64 summation order - and with it every bit of the image - is the same whichever way it is rendered.
     const bool tree = (s.features & F_BVH) != 0u, tris = (s.features & F_TRI) != 0u;
-    const uint64_t kSamplesPerItem = !tree ? 32 : (tris ? 8 : 2), kMinItems = 1ull << 23;
+    const uint64_t kSamplesPerItem = !tree ? 32 : (tris ? 8 : 1), kMinItems = 1ull << 23;
     const uint64_t plane_budget = (tree && !tris) ? (16ull << 30) : (4ull << 30);
     uint64_t chunks = (count + kSamplesPerItem - 1) / kSamplesPerItem;
     const uint64_t for_balance = (kMinItems + P.items_per_chunk - 1) / P.items_per_chunk;
