@@ -303,6 +303,13 @@ def test_render_info_reports_pipeline_and_variant(rt, orc):
         dev.render(hs.camera, 32, 32, 2, 10, rt.render_opts(seed=1, integrator=hs.integrator))
         info = dev.render_info
         assert (info["pipeline"], info["variant"]) == (pipeline, variant), (name, info)
+    # a tree over spheres without media takes the wavefront pipeline once the render is long (api.cu kWavefrontLongPaths)
+    hs, dev, _ = scenes(rt, orc, "random")
+    a, sa = dev.render(hs.camera, 1000, 1000, 80, 50, rt.render_opts(seed=1, integrator=hs.integrator))
+    assert dev.render_info["pipeline"] == "wavefront" and dev.render_info["variant"] == "vspheres"
+    b, sb = dev.render(hs.camera, 1000, 1000, 80, 50, rt.render_opts(seed=1, integrator=hs.integrator, flags=abi.FLAG_MEGAKERNEL))
+    assert dev.render_info["pipeline"] == "megakernel" and sa.paths == sb.paths
+    assert (a != b).any(axis=2).sum() <= 2  # (the same image; DESIGN.md §5.2 on the last fp32 bit of a pixel in a million)
     hs, dev, _ = scenes(rt, orc, "cornell")
     dev.render(hs.camera, 32, 32, 2, 10, rt.render_opts(seed=1, flags=abi.FLAG_WAVEFRONT))
     assert dev.render_info["pipeline"] == "wavefront" and int(dev.render_info["pool_slots"]) == 32 * 32 * 2
